@@ -1,0 +1,73 @@
+"""ctypes binding of libmmad_b200.so (the C-ABI in include/mmad_b200.h).
+
+There is no fallback: if the library is missing and cannot be built, or a call
+fails, this raises.  Nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "csrc", "libmmad_b200.so")
+_lib = None
+
+
+class MmadError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if the .so is absent) and declare every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        from . import build as _build
+
+        _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise MmadError(f"CUDA library not found at {_LIB_PATH}; run python -m multimodal_ad_b200.build")
+    lib = ctypes.CDLL(_LIB_PATH)
+
+    lib.mmad_last_error.restype = c_char_p
+    lib.mmad_last_error.argtypes = []
+    lib.mmad_abi_version.restype = ctypes.c_int
+    lib.mmad_launch_count.restype = c_int64
+
+    P = c_void_p
+    lib.mmad_roi_plan_create.argtypes = [P, c_int64, c_int32, POINTER(P)]
+    lib.mmad_roi_plan_create_ex.argtypes = [P, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(P)]
+    lib.mmad_roi_plan_destroy.argtypes = [P]
+    lib.mmad_roi_plan_counts.argtypes = [P, P]
+    lib.mmad_roi_plan_counts_dev.argtypes = [P, POINTER(P)]
+    lib.mmad_roi_pool_f32.argtypes = [P, P, c_int64, P, P, P, P]
+    lib.mmad_roi_pool_host_f32.argtypes = [P, P, c_int64, P, P, P]
+    lib.mmad_roi_pool_mean_backward_f32.argtypes = [P, P, c_int64, P, P]
+    lib.mmad_roi_pool_algorithmic_bytes.argtypes = [P, c_int64]
+    lib.mmad_roi_pool_algorithmic_bytes.restype = c_int64
+    lib.mmad_roi_plan_programme.argtypes = [P, P, POINTER(c_int64), P, POINTER(c_int32), POINTER(c_int32),
+                                            POINTER(c_int64)]
+    lib.mmad_roi_plan_binding.argtypes = [P, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
+                                          P, P, P, P, P, P, P, POINTER(c_int64)]
+    for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",
+                 "mmad_roi_plan_counts_dev", "mmad_roi_pool_f32", "mmad_roi_pool_host_f32",
+                 "mmad_roi_pool_mean_backward_f32", "mmad_roi_plan_programme", "mmad_roi_plan_binding"):
+        getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mmad_last_error().decode("utf-8", "replace")
+        raise MmadError(f"{what} failed ({rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().mmad_launch_count())

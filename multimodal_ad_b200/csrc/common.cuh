@@ -1,0 +1,84 @@
+// Shared host/device helpers for the mmad_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <atomic>
+#include <cstdio>
+#include "../../include/mmad_b200.h"
+
+namespace mmad {
+
+// ---- host-side error plumbing ------------------------------------------------
+std::string& last_error_ref();
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const std::string& msg) {
+    last_error_ref() = msg;
+    return code;
+}
+
+#define MMAD_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t _e = (call);                                                     \
+        if (_e != cudaSuccess)                                                       \
+            return ::mmad::fail(MMAD_ECUDA, std::string(#call) + ": " +              \
+                                                cudaGetErrorString(_e));             \
+    } while (0)
+
+#define MMAD_CHECK_ARG(cond, msg)                                                    \
+    do {                                                                             \
+        if (!(cond)) return ::mmad::fail(MMAD_EINVAL, std::string(msg));             \
+    } while (0)
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- device-side PTX wrappers (mbarrier / bulk async copy) ---------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// Make barrier initialisation visible to the async (TMA) proxy.
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP).  src, dst and
+// bytes must be multiples of 16.  Completion is signalled on `bar` as tx bytes.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace mmad

@@ -1,0 +1,705 @@
+// Atlas ROI pooling for sm_100a: segmented mean / max / argmax of MRI volumes
+// over an atlas label map.  Replaces /root/reference/image_features.py:80-82,
+// 111-114 (one-hot mask product-sum) behind include/mmad_b200.h, part 1.
+//
+// Design (DESIGN.md "ROI pooling" has the long form):
+//  * The atlas is the same for every volume of a batch, so the label map is
+//    run-length encoded ONCE on the host into a per-tile "run programme"; the
+//    kernel never touches per-voxel labels.
+//  * A CTA owns 32 volumes x a contiguous range of voxel tiles.  A producer
+//    warp stages each tile (32 rows of TILE voxels, one row per volume) into
+//    shared memory with 1-D bulk async copies (TMA engine) through an mbarrier
+//    ring; the tile's run programme rides along on the same barrier.
+//  * Consumer warps run with lane = volume.  Every lane sees the same labels,
+//    so control flow is warp-uniform, and lane-private accumulator columns
+//    need no atomics.  Labels are partitioned across the consumer warps, so no
+//    two warps ever touch the same accumulator either.
+//  * Sums are carried in double per (ROI, volume); partials leave the CTA once
+//    per work item and a small second kernel reduces them in a fixed order:
+//    results are bit-reproducible run to run.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace mmad {
+
+constexpr int kConsumerWarps = 8;                 // NW
+constexpr int kHdrWords = 12;                     // per-tile programme header (NW+1 offsets, padded)
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxSmem = 227 * 1024;
+
+__host__ __device__ constexpr int row_pitch(int tile) { return tile + 4; }                 // floats; == 4 (mod 32)
+__host__ __device__ constexpr int prog_words(int tile) { return (kHdrWords + tile + 3) / 4 * 4; }
+__host__ __device__ constexpr int stage_bytes(int tile) { return 32 * row_pitch(tile) * 4 + prog_words(tile) * 4; }
+
+struct RoiParams {
+    const float* vols;
+    long long n_vols;
+    long long V;
+    int R;
+    int ns;        // pipeline stages
+    int n_items;
+    const uint32_t* prog;        // run programme, 16-byte units addressed by prog_off
+    const int32_t* prog_off;     // [n_tiles + 1], in 16-byte units
+    const int32_t* item_group;   // [n_items]
+    const int32_t* item_t0;      // [n_items]
+    const int32_t* item_t1;      // [n_items]
+    const int32_t* item_slot_ptr;  // [n_items + 1]
+    const uint8_t* slot_label;     // [n_slots], label 1..R of every partial slot
+    double* slot_sum;              // [n_slots][32]
+    float* slot_max;               // [n_slots][32]
+    int32_t* slot_arg;             // [n_slots][32]
+};
+
+// Row of volume `lane` inside a stage.  Rows of the four volumes of a quad land
+// 8 rows apart, so that with pitch == 4 (mod 32) and the per-volume alignment
+// shift (distinct inside a quad when V is odd) the 32 lanes of a consumer warp
+// read 32 different banks.
+__device__ __forceinline__ int stage_row(int lane) { return (lane >> 2) + 8 * (lane & 3); }
+
+template <int TILE>
+__global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams p) {
+    constexpr int P = row_pitch(TILE);
+    constexpr int STAGE = stage_bytes(TILE);
+    extern __shared__ __align__(16) unsigned char smem[];
+
+    const int R = p.R;
+    double* bins_sum = reinterpret_cast<double*>(smem);
+    float* bins_max = reinterpret_cast<float*>(smem + (size_t)R * 256);
+    int* bins_arg = reinterpret_cast<int*>(smem + (size_t)R * 384);
+    unsigned char* stages = smem + (((size_t)R * 512 + 15) & ~(size_t)15);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)p.ns * STAGE);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = smem_u32(bars + p.ns);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ns = p.ns;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ns; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int rho = stage_row(lane);
+    uint32_t it = 0;   // tiles consumed/produced so far by this CTA (ring position)
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp: one bulk copy per volume row =====================
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int g = p.item_group[item];
+            const int t0 = p.item_t0[item], t1 = p.item_t1[item];
+            const long long vol = (long long)g * 32 + lane;
+            const bool act = vol < p.n_vols;
+            const float* vbase = p.vols + (act ? vol : 0) * p.V;
+            const uint32_t sb = (uint32_t)((reinterpret_cast<uintptr_t>(vbase) >> 2) & 3);
+            for (int tb = t0; tb < t1; tb += 32) {
+                const int tt = tb + lane;
+                const int o0 = tt < t1 ? p.prog_off[tt] : 0;
+                const int o1 = tt < t1 ? p.prog_off[tt + 1] : 0;
+                const int nt = min(32, t1 - tb);
+                for (int k = 0; k < nt; ++k, ++it) {
+                    const int t = tb + k;
+                    const uint32_t s = it % ns;
+                    const uint32_t ph = (it / ns) & 1;
+                    const int po0 = __shfl_sync(0xffffffffu, o0, k);
+                    const int po1 = __shfl_sync(0xffffffffu, o1, k);
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const long long v0 = (long long)t * TILE;
+                    const int L = (int)min((long long)TILE, p.V - v0);
+                    const uint32_t bytes = act ? ((sb + (uint32_t)L + 3u) & ~3u) * 4u : 0u;
+                    const uint32_t pbytes = (uint32_t)(po1 - po0) * 16u;
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes) + pbytes;
+                    if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * s, total);
+                    __syncwarp();
+                    const uint32_t sbase = smem_u32(stages + (size_t)s * STAGE);
+                    if (act)
+                        bulk_g2s(sbase + (uint32_t)rho * P * 4u,
+                                 reinterpret_cast<const char*>(vbase + v0) - sb * 4u, bytes, full0 + 8 * s);
+                    if (lane == 0)
+                        bulk_g2s(sbase + 32u * P * 4u, p.prog + (size_t)po0 * 4, pbytes, full0 + 8 * s);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps: lane = volume, warp owns labels l % NW == warp =====================
+    constexpr int NCT = kConsumerWarps * 32;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int g = p.item_group[item];
+        const int t0 = p.item_t0[item], t1 = p.item_t1[item];
+        const long long vol = (long long)g * 32 + lane;
+        const bool act = vol < p.n_vols;
+        const float* vbase = p.vols + (act ? vol : 0) * p.V;
+        const uint32_t sb = (uint32_t)((reinterpret_cast<uintptr_t>(vbase) >> 2) & 3);
+
+        for (int i = threadIdx.x; i < R * 32; i += NCT) {
+            bins_sum[i] = 0.0;
+            bins_max[i] = -INFINITY;
+            bins_arg[i] = -1;
+        }
+        named_bar_sync(1, NCT);
+
+        for (int t = t0; t < t1; ++t, ++it) {
+            const uint32_t s = it % ns;
+            const uint32_t ph = (it / ns) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            const unsigned char* sbase = stages + (size_t)s * STAGE;
+            const float* rowp = reinterpret_cast<const float*>(sbase) + rho * P + sb;
+            const uint32_t* prog = reinterpret_cast<const uint32_t*>(sbase + 32 * P * 4);
+            const uint32_t r0 = prog[warp], r1 = prog[warp + 1];
+            const int gbase = t * TILE;
+
+            int cur = 0;
+            double ds = 0.0;
+            float mx = -INFINITY;
+            int arg = -1;
+            for (uint32_t i = r0; i < r1; ++i) {
+                const uint32_t run = prog[kHdrWords + i];
+                const int label = (int)(run >> 24);
+                int q = (int)((run >> 12) & 0xfffu);
+                const int e = q + (int)(run & 0xfffu) + 1;
+                if (label != cur) {
+                    if (cur) {
+                        const int b = (cur - 1) * 32 + lane;
+                        bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
+                    }
+                    cur = label;
+                    const int b = (cur - 1) * 32 + lane;
+                    ds = bins_sum[b]; mx = bins_max[b]; arg = bins_arg[b];
+                }
+                if (act) {
+#define MMAD_UPD(v, idx) if ((v) > mx || arg < 0) { mx = (v); arg = gbase + (idx); }
+                    for (; q + 8 <= e; q += 8) {
+                        const float a0 = rowp[q], a1 = rowp[q + 1], a2 = rowp[q + 2], a3 = rowp[q + 3];
+                        const float a4 = rowp[q + 4], a5 = rowp[q + 5], a6 = rowp[q + 6], a7 = rowp[q + 7];
+                        ds += (double)(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
+                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1) MMAD_UPD(a2, q + 2) MMAD_UPD(a3, q + 3)
+                        MMAD_UPD(a4, q + 4) MMAD_UPD(a5, q + 5) MMAD_UPD(a6, q + 6) MMAD_UPD(a7, q + 7)
+                    }
+                    if (q + 4 <= e) {
+                        const float a0 = rowp[q], a1 = rowp[q + 1], a2 = rowp[q + 2], a3 = rowp[q + 3];
+                        ds += (double)((a0 + a1) + (a2 + a3));
+                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1) MMAD_UPD(a2, q + 2) MMAD_UPD(a3, q + 3)
+                        q += 4;
+                    }
+                    if (q + 2 <= e) {
+                        const float a0 = rowp[q], a1 = rowp[q + 1];
+                        ds += (double)(a0 + a1);
+                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1)
+                        q += 2;
+                    }
+                    if (q < e) {
+                        const float a0 = rowp[q];
+                        ds += (double)a0;
+                        MMAD_UPD(a0, q)
+                    }
+#undef MMAD_UPD
+                }
+            }
+            if (cur) {
+                const int b = (cur - 1) * 32 + lane;
+                bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+
+        named_bar_sync(1, NCT);
+        const int sp0 = p.item_slot_ptr[item], sp1 = p.item_slot_ptr[item + 1];
+        for (int j = sp0 + warp; j < sp1; j += kConsumerWarps) {
+            const int b = ((int)p.slot_label[j] - 1) * 32 + lane;
+            p.slot_sum[(size_t)j * 32 + lane] = bins_sum[b];
+            p.slot_max[(size_t)j * 32 + lane] = bins_max[b];
+            p.slot_arg[(size_t)j * 32 + lane] = bins_arg[b];
+        }
+        named_bar_sync(1, NCT);
+    }
+}
+
+// Second pass: one warp per (volume group, ROI) walks that ROI's partial slots in
+// ascending tile order (fixed order => reproducible; strict '>' keeps the first max).
+__global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restrict__ slot_sum,
+                                                           const float* __restrict__ slot_max,
+                                                           const int32_t* __restrict__ slot_arg,
+                                                           const int32_t* __restrict__ fin_ptr,
+                                                           const int32_t* __restrict__ fin_slots,
+                                                           const int32_t* __restrict__ counts, int n_groups, int R,
+                                                           long long n_vols, float* __restrict__ mean,
+                                                           float* __restrict__ mx_out, int32_t* __restrict__ arg_out) {
+    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= n_groups * R) return;
+    const int g = w / R, r = w - g * R;
+    double s = 0.0;
+    float mx = -INFINITY;
+    int arg = -1;
+    const int k0 = fin_ptr[w], k1 = fin_ptr[w + 1];
+    for (int k = k0; k < k1; ++k) {
+        const size_t o = (size_t)fin_slots[k] * 32 + lane;
+        s += slot_sum[o];
+        const float m = slot_max[o];
+        const int a = slot_arg[o];
+        if (a >= 0 && (arg < 0 || m > mx)) { mx = m; arg = a; }
+    }
+    const long long vol = (long long)g * 32 + lane;
+    if (vol >= n_vols) return;
+    const int cnt = counts[r];
+    const float den = fmaxf((float)cnt, 1e-6f);
+    const size_t o = (size_t)vol * R + r;
+    if (mean) mean[o] = (float)s / den;
+    if (mx_out) mx_out[o] = cnt ? mx : 0.0f;
+    if (arg_out) arg_out[o] = cnt ? arg : -1;
+}
+
+// Per-ROI voxel counts of the uint8 label map (plan creation, once per atlas).
+__global__ void __launch_bounds__(256) roi_count_kernel(const uint8_t* __restrict__ labels, long long V,
+                                                        int32_t* __restrict__ counts, int R) {
+    __shared__ int hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&hist[labels[i]], 1);
+    __syncthreads();
+    const int l = threadIdx.x;
+    if (l >= 1 && l <= R && hist[l]) atomicAdd(&counts[l - 1], hist[l]);
+}
+
+// d mean / d vols  (image_features.py:111-114 under autograd).
+__global__ void __launch_bounds__(256) roi_mean_bwd_kernel(const float* __restrict__ gmean,
+                                                           const uint8_t* __restrict__ labels,
+                                                           const int32_t* __restrict__ counts, long long V, int R,
+                                                           long long n_vols, float* __restrict__ gvol) {
+    const long long total = n_vols * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / V;
+        const long long v = i - n * V;
+        const int l = labels[v];
+        float o = 0.0f;
+        if (l) o = __ldg(&gmean[n * R + (l - 1)]) / fmaxf((float)__ldg(&counts[l - 1]), 1e-6f);
+        gvol[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------
+struct Binding {
+    long long n_vols = 0;
+    int n_groups = 0, n_items = 0, grid = 0, n_slots = 0;
+    std::vector<int32_t> h_item_group, h_item_t0, h_item_t1, h_item_slot_ptr, h_fin_ptr, h_fin_slots;
+    std::vector<uint8_t> h_slot_label;
+    int32_t *d_item_group = nullptr, *d_item_t0 = nullptr, *d_item_t1 = nullptr, *d_item_slot_ptr = nullptr;
+    int32_t *d_fin_ptr = nullptr, *d_fin_slots = nullptr;
+    uint8_t* d_slot_label = nullptr;
+    double* d_slot_sum = nullptr;
+    float* d_slot_max = nullptr;
+    int32_t* d_slot_arg = nullptr;
+    void release() {
+        cudaFree(d_item_group); cudaFree(d_item_t0); cudaFree(d_item_t1); cudaFree(d_item_slot_ptr);
+        cudaFree(d_fin_ptr); cudaFree(d_fin_slots); cudaFree(d_slot_label);
+        cudaFree(d_slot_sum); cudaFree(d_slot_max); cudaFree(d_slot_arg);
+    }
+};
+
+}  // namespace mmad
+
+struct mmad_roi_plan {
+    long long V = 0;
+    int R = 0, tile = 256, n_tiles = 0, ns = 0, sms = 148, device = 0;
+    size_t smem_bytes = 0;
+    std::vector<uint32_t> h_prog;         // words
+    std::vector<int32_t> h_prog_off;      // 16-byte units, n_tiles + 1
+    std::vector<uint64_t> h_tile_mask;    // n_tiles x 4 (bit l set: label l has voxels in the tile)
+    std::vector<int32_t> h_counts;
+    uint32_t* d_prog = nullptr;
+    int32_t* d_prog_off = nullptr;
+    uint8_t* d_labels = nullptr;
+    int32_t* d_counts = nullptr;
+    std::map<long long, mmad::Binding*> bindings;
+    // host-buffer pipeline (mmad_roi_pool_host_f32)
+    float* d_stage[2] = {nullptr, nullptr};
+    long long stage_vols = 0;
+    float* d_omean = nullptr; float* d_omax = nullptr; int32_t* d_oarg = nullptr;
+    long long out_cap = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+namespace mmad {
+
+// Host-only: run-length encode the label map into the per-tile programme.
+// Exposed through mmad_roi_plan_host_debug for the CPU tests.
+static int build_programme(const int32_t* labels, long long V, int R, int tile, std::vector<uint32_t>& prog,
+                           std::vector<int32_t>& prog_off, std::vector<uint64_t>& tile_mask, int& n_tiles) {
+    n_tiles = (int)((V + tile - 1) / tile);
+    prog.clear();
+    prog_off.assign((size_t)n_tiles + 1, 0);
+    tile_mask.assign((size_t)n_tiles * 4, 0ull);
+    std::vector<uint32_t> runs[kConsumerWarps];
+    for (int t = 0; t < n_tiles; ++t) {
+        for (auto& r : runs) r.clear();
+        const long long v0 = (long long)t * tile;
+        const int L = (int)std::min<long long>(tile, V - v0);
+        int q = 0;
+        while (q < L) {
+            const int32_t l = labels[v0 + q];
+            if (l < 0 || l > R) return -1;
+            int e = q + 1;
+            while (e < L && labels[v0 + e] == l) ++e;
+            if (l) {
+                runs[l % kConsumerWarps].push_back(((uint32_t)l << 24) | ((uint32_t)q << 12) | (uint32_t)(e - q - 1));
+                tile_mask[(size_t)t * 4 + (l >> 6)] |= 1ull << (l & 63);
+            }
+            q = e;
+        }
+        prog_off[t] = (int32_t)(prog.size() / 4);
+        uint32_t hdr[kHdrWords] = {0};
+        uint32_t acc = 0;
+        for (int w = 0; w < kConsumerWarps; ++w) {
+            // sort by label, then start (runs of one label must be visited in ascending voxel order)
+            std::sort(runs[w].begin(), runs[w].end());
+            hdr[w] = acc;
+            acc += (uint32_t)runs[w].size();
+        }
+        hdr[kConsumerWarps] = acc;
+        prog.insert(prog.end(), hdr, hdr + kHdrWords);
+        for (int w = 0; w < kConsumerWarps; ++w) prog.insert(prog.end(), runs[w].begin(), runs[w].end());
+        while (prog.size() % 4) prog.push_back(0u);
+    }
+    prog_off[n_tiles] = (int32_t)(prog.size() / 4);
+    return 0;
+}
+
+// Host-only: split the (volume group x tile) space into work items and lay out
+// the partial slots each item writes and each (group, ROI) reads back.
+static void build_binding_host(const mmad_roi_plan& pl, long long n_vols, Binding& b) {
+    b.n_vols = n_vols;
+    b.n_groups = (int)((n_vols + 31) / 32);
+    int pieces = 1;
+    if (b.n_groups <= pl.sms) pieces = std::max(1, std::min(pl.sms / b.n_groups, pl.n_tiles));
+    b.n_items = b.n_groups * pieces;
+    b.grid = std::min(b.n_items, pl.sms);
+    b.h_item_group.resize(b.n_items); b.h_item_t0.resize(b.n_items); b.h_item_t1.resize(b.n_items);
+    b.h_item_slot_ptr.assign((size_t)b.n_items + 1, 0);
+    b.h_slot_label.clear();
+    // item = piece * n_groups + g : neighbouring CTAs stream the same tile range of different groups
+    std::vector<std::vector<int32_t>> per_gr((size_t)b.n_groups * pl.R);
+    for (int piece = 0; piece < pieces; ++piece) {
+        const int t0 = (int)((long long)pl.n_tiles * piece / pieces);
+        const int t1 = (int)((long long)pl.n_tiles * (piece + 1) / pieces);
+        uint64_t m[4] = {0, 0, 0, 0};
+        for (int t = t0; t < t1; ++t)
+            for (int k = 0; k < 4; ++k) m[k] |= pl.h_tile_mask[(size_t)t * 4 + k];
+        for (int g = 0; g < b.n_groups; ++g) {
+            const int item = piece * b.n_groups + g;
+            b.h_item_group[item] = g; b.h_item_t0[item] = t0; b.h_item_t1[item] = t1;
+            b.h_item_slot_ptr[item] = (int32_t)b.h_slot_label.size();
+            for (int l = 1; l <= pl.R; ++l)
+                if (m[l >> 6] >> (l & 63) & 1ull) {
+                    per_gr[(size_t)g * pl.R + (l - 1)].push_back((int32_t)b.h_slot_label.size());
+                    b.h_slot_label.push_back((uint8_t)l);
+                }
+        }
+    }
+    b.n_slots = (int)b.h_slot_label.size();
+    b.h_item_slot_ptr[b.n_items] = b.n_slots;
+    b.h_fin_ptr.assign((size_t)b.n_groups * pl.R + 1, 0);
+    b.h_fin_slots.clear();
+    for (size_t k = 0; k < per_gr.size(); ++k) {
+        b.h_fin_ptr[k] = (int32_t)b.h_fin_slots.size();
+        b.h_fin_slots.insert(b.h_fin_slots.end(), per_gr[k].begin(), per_gr[k].end());   // ascending piece => ascending tile
+    }
+    b.h_fin_ptr[per_gr.size()] = (int32_t)b.h_fin_slots.size();
+}
+
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)dptr, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int get_binding(mmad_roi_plan* pl, long long n_vols, Binding** out) {
+    auto itb = pl->bindings.find(n_vols);
+    if (itb != pl->bindings.end()) { *out = itb->second; return MMAD_OK; }
+    Binding* b = new Binding();
+    build_binding_host(*pl, n_vols, *b);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = upload(&b->d_item_group, b->h_item_group);
+    if (e == cudaSuccess) e = upload(&b->d_item_t0, b->h_item_t0);
+    if (e == cudaSuccess) e = upload(&b->d_item_t1, b->h_item_t1);
+    if (e == cudaSuccess) e = upload(&b->d_item_slot_ptr, b->h_item_slot_ptr);
+    if (e == cudaSuccess) e = upload(&b->d_slot_label, b->h_slot_label);
+    if (e == cudaSuccess) e = upload(&b->d_fin_ptr, b->h_fin_ptr);
+    if (e == cudaSuccess) e = upload(&b->d_fin_slots, b->h_fin_slots);
+    const size_t ns = std::max(b->n_slots, 1);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_sum, ns * 32 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_max, ns * 32 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_arg, ns * 32 * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        b->release();
+        delete b;
+        return fail(MMAD_ECUDA, std::string("roi binding upload: ") + cudaGetErrorString(e));
+    }
+    pl->bindings[n_vols] = b;
+    *out = b;
+    return MMAD_OK;
+}
+
+static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vols, float* mean_dev, float* max_dev,
+                       int32_t* argmax_dev, cudaStream_t st) {
+    Binding* b = nullptr;
+    int rc = get_binding(pl, n_vols, &b);
+    if (rc) return rc;
+    RoiParams p;
+    p.vols = vols_dev; p.n_vols = n_vols; p.V = pl->V; p.R = pl->R; p.ns = pl->ns; p.n_items = b->n_items;
+    p.prog = pl->d_prog; p.prog_off = pl->d_prog_off;
+    p.item_group = b->d_item_group; p.item_t0 = b->d_item_t0; p.item_t1 = b->d_item_t1;
+    p.item_slot_ptr = b->d_item_slot_ptr; p.slot_label = b->d_slot_label;
+    p.slot_sum = b->d_slot_sum; p.slot_max = b->d_slot_max; p.slot_arg = b->d_slot_arg;
+    switch (pl->tile) {
+        case 128: roi_stream_kernel<128><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
+        case 256: roi_stream_kernel<256><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
+        case 512: roi_stream_kernel<512><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
+        default: return fail(MMAD_EUNSUPPORTED, "roi tile must be 128, 256 or 512");
+    }
+    MMAD_CUDA(cudaGetLastError());
+    const int warps = b->n_groups * pl->R;
+    roi_finalize_kernel<<<(warps + 3) / 4, 128, 0, st>>>(b->d_slot_sum, b->d_slot_max, b->d_slot_arg, b->d_fin_ptr,
+                                                       b->d_fin_slots, pl->d_counts, b->n_groups, pl->R, n_vols,
+                                                       mean_dev, max_dev, argmax_dev);
+    MMAD_CUDA(cudaGetLastError());
+    count_launch(2);
+    return MMAD_OK;
+}
+
+}  // namespace mmad
+
+using namespace mmad;
+
+extern "C" {
+
+// Extended constructor used by bench.py / tests for tuning: tile in {128,256,512},
+// stages 0 = as many as fit (max 4).
+int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_t n_rois, int32_t tile,
+                            int32_t stages, int32_t host_only, mmad_roi_plan** plan_out) {
+    MMAD_CHECK_ARG(labels_host && plan_out, "roi_plan_create: null pointer");
+    MMAD_CHECK_ARG(n_voxels > 0 && n_voxels < (1ll << 31) - 4096, "roi_plan_create: n_voxels must be in (0, 2^31)");
+    MMAD_CHECK_ARG(n_rois >= 1 && n_rois <= 255, "roi_plan_create: n_rois must be 1..255");
+    MMAD_CHECK_ARG(tile == 128 || tile == 256 || tile == 512, "roi_plan_create: tile must be 128, 256 or 512");
+    mmad_roi_plan* pl = new mmad_roi_plan();
+    pl->V = n_voxels; pl->R = n_rois; pl->tile = tile;
+    if (build_programme(labels_host, n_voxels, n_rois, tile, pl->h_prog, pl->h_prog_off, pl->h_tile_mask, pl->n_tiles)) {
+        delete pl;
+        return fail(MMAD_EINVAL, "roi_plan_create: label outside [0, n_rois]");
+    }
+    const size_t bins = (((size_t)n_rois * 512) + 15) & ~(size_t)15;
+    int ns = (int)((kMaxSmem - bins - 64) / stage_bytes(tile));
+    ns = std::min(ns, 4);
+    if (stages > 0) ns = std::min(ns, (int)stages);
+    if (ns < 2) { delete pl; return fail(MMAD_EUNSUPPORTED, "roi_plan_create: shared memory too small for this tile / n_rois"); }
+    pl->ns = ns;
+    pl->smem_bytes = bins + (size_t)ns * stage_bytes(tile) + 64;
+    if (host_only) { *plan_out = pl; return MMAD_OK; }
+
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { delete pl; return fail(MMAD_ECUDA, std::string("roi_plan_create: no CUDA device: ") + cudaGetErrorString(e)); }
+    pl->device = dev; pl->sms = sms;
+    std::vector<uint8_t> lab8((size_t)n_voxels);
+    for (long long i = 0; i < n_voxels; ++i) lab8[i] = (uint8_t)labels_host[i];
+    if (e == cudaSuccess) e = upload(&pl->d_prog, pl->h_prog);
+    if (e == cudaSuccess) e = upload(&pl->d_prog_off, pl->h_prog_off);
+    if (e == cudaSuccess) e = upload(&pl->d_labels, lab8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_counts, sizeof(int32_t) * n_rois);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_counts, 0, sizeof(int32_t) * n_rois);
+    if (e == cudaSuccess) {
+        roi_count_kernel<<<std::max(1, std::min(4 * sms, (int)((n_voxels + 255) / 256))), 256>>>(pl->d_labels, n_voxels, pl->d_counts, n_rois);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    pl->h_counts.resize(n_rois);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->h_counts.data(), pl->d_counts, sizeof(int32_t) * n_rois, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("roi_plan_create: ") + cudaGetErrorString(e);
+        mmad_roi_plan_destroy(pl);
+        return fail(MMAD_ECUDA, msg);
+    }
+    *plan_out = pl;
+    return MMAD_OK;
+}
+
+int mmad_roi_plan_create(const int32_t* labels_host, int64_t n_voxels, int32_t n_rois, mmad_roi_plan** plan_out) {
+    return mmad_roi_plan_create_ex(labels_host, n_voxels, n_rois, 256, 0, 0, plan_out);
+}
+
+int mmad_roi_plan_destroy(mmad_roi_plan* pl) {
+    if (!pl) return MMAD_OK;
+    for (auto& kv : pl->bindings) { kv.second->release(); delete kv.second; }
+    cudaFree(pl->d_prog); cudaFree(pl->d_prog_off); cudaFree(pl->d_labels); cudaFree(pl->d_counts);
+    cudaFree(pl->d_stage[0]); cudaFree(pl->d_stage[1]);
+    cudaFree(pl->d_omean); cudaFree(pl->d_omax); cudaFree(pl->d_oarg);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->ev_copied[i]) cudaEventDestroy(pl->ev_copied[i]);
+        if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
+    }
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
+    delete pl;
+    return MMAD_OK;
+}
+
+int mmad_roi_plan_counts(const mmad_roi_plan* pl, int32_t* counts_host) {
+    MMAD_CHECK_ARG(pl && counts_host, "roi_plan_counts: null pointer");
+    MMAD_CHECK_ARG(!pl->h_counts.empty(), "roi_plan_counts: host-only plan has no GPU counts");
+    std::memcpy(counts_host, pl->h_counts.data(), sizeof(int32_t) * pl->R);
+    return MMAD_OK;
+}
+
+int mmad_roi_plan_counts_dev(const mmad_roi_plan* pl, const int32_t** counts_dev) {
+    MMAD_CHECK_ARG(pl && counts_dev && pl->d_counts, "roi_plan_counts_dev: null pointer / host-only plan");
+    *counts_dev = pl->d_counts;
+    return MMAD_OK;
+}
+
+int mmad_roi_pool_f32(mmad_roi_plan* pl, const float* vols_dev, int64_t n_vols, float* mean_dev, float* max_dev,
+                      int32_t* argmax_dev, void* stream) {
+    MMAD_CHECK_ARG(pl && pl->d_prog, "roi_pool: null or host-only plan");
+    MMAD_CHECK_ARG(n_vols >= 0, "roi_pool: n_vols < 0");
+    if (n_vols == 0) return MMAD_OK;
+    MMAD_CHECK_ARG(vols_dev, "roi_pool: null volumes");
+    MMAD_CHECK_ARG((reinterpret_cast<uintptr_t>(vols_dev) & 3) == 0, "roi_pool: volumes must be 4-byte aligned");
+    return launch_pool(pl, vols_dev, n_vols, mean_dev, max_dev, argmax_dev, (cudaStream_t)stream);
+}
+
+int mmad_roi_pool_mean_backward_f32(mmad_roi_plan* pl, const float* grad_mean_dev, int64_t n_vols,
+                                    float* grad_vols_dev, void* stream) {
+    MMAD_CHECK_ARG(pl && pl->d_labels, "roi_pool_mean_backward: null or host-only plan");
+    MMAD_CHECK_ARG(n_vols >= 0, "roi_pool_mean_backward: n_vols < 0");
+    if (n_vols == 0) return MMAD_OK;
+    MMAD_CHECK_ARG(grad_mean_dev && grad_vols_dev, "roi_pool_mean_backward: null pointer");
+    const long long total = (long long)n_vols * pl->V;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)pl->sms * 16);
+    roi_mean_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad_mean_dev, pl->d_labels, pl->d_counts, pl->V, pl->R,
+                                                                n_vols, grad_vols_dev);
+    MMAD_CUDA(cudaGetLastError());
+    count_launch();
+    return MMAD_OK;
+}
+
+int mmad_roi_pool_host_f32(mmad_roi_plan* pl, const float* vols_host, int64_t n_vols, float* mean_host,
+                           float* max_host, int32_t* argmax_host) {
+    MMAD_CHECK_ARG(pl && pl->d_prog, "roi_pool_host: null or host-only plan");
+    MMAD_CHECK_ARG(n_vols >= 0, "roi_pool_host: n_vols < 0");
+    if (n_vols == 0) return MMAD_OK;
+    MMAD_CHECK_ARG(vols_host, "roi_pool_host: null volumes");
+    const long long chunk = 8;   // volumes per H2D chunk: PCIe time >> kernel time, small chunks hide the kernel
+    if (!pl->s_copy) {
+        MMAD_CUDA(cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking));
+        MMAD_CUDA(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MMAD_CUDA(cudaEventCreateWithFlags(&pl->ev_copied[i], cudaEventDisableTiming));
+            MMAD_CUDA(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (pl->stage_vols < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(pl->d_stage[i]);
+            pl->d_stage[i] = nullptr;
+            MMAD_CUDA(cudaMalloc((void**)&pl->d_stage[i], sizeof(float) * chunk * pl->V));
+        }
+        pl->stage_vols = chunk;
+    }
+    if (pl->out_cap < n_vols) {
+        cudaFree(pl->d_omean); cudaFree(pl->d_omax); cudaFree(pl->d_oarg);
+        pl->d_omean = nullptr; pl->d_omax = nullptr; pl->d_oarg = nullptr;
+        MMAD_CUDA(cudaMalloc((void**)&pl->d_omean, sizeof(float) * n_vols * pl->R));
+        MMAD_CUDA(cudaMalloc((void**)&pl->d_omax, sizeof(float) * n_vols * pl->R));
+        MMAD_CUDA(cudaMalloc((void**)&pl->d_oarg, sizeof(int32_t) * n_vols * pl->R));
+        pl->out_cap = n_vols;
+    }
+    int k = 0;
+    for (long long v0 = 0; v0 < n_vols; v0 += chunk, ++k) {
+        const int buf = k & 1;
+        const long long n = std::min(chunk, (long long)n_vols - v0);
+        if (k >= 2) MMAD_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_done[buf], 0));   // buffer free again
+        MMAD_CUDA(cudaMemcpyAsync(pl->d_stage[buf], vols_host + v0 * pl->V, sizeof(float) * n * pl->V,
+                                  cudaMemcpyHostToDevice, pl->s_copy));
+        MMAD_CUDA(cudaEventRecord(pl->ev_copied[buf], pl->s_copy));
+        MMAD_CUDA(cudaStreamWaitEvent(pl->s_comp, pl->ev_copied[buf], 0));
+        int rc = launch_pool(pl, pl->d_stage[buf], n, pl->d_omean + v0 * pl->R, pl->d_omax + v0 * pl->R,
+                             pl->d_oarg + v0 * pl->R, pl->s_comp);
+        if (rc) return rc;
+        MMAD_CUDA(cudaEventRecord(pl->ev_done[buf], pl->s_comp));
+    }
+    if (mean_host) MMAD_CUDA(cudaMemcpyAsync(mean_host, pl->d_omean, sizeof(float) * n_vols * pl->R, cudaMemcpyDeviceToHost, pl->s_comp));
+    if (max_host) MMAD_CUDA(cudaMemcpyAsync(max_host, pl->d_omax, sizeof(float) * n_vols * pl->R, cudaMemcpyDeviceToHost, pl->s_comp));
+    if (argmax_host) MMAD_CUDA(cudaMemcpyAsync(argmax_host, pl->d_oarg, sizeof(int32_t) * n_vols * pl->R, cudaMemcpyDeviceToHost, pl->s_comp));
+    MMAD_CUDA(cudaStreamSynchronize(pl->s_comp));
+    return MMAD_OK;
+}
+
+int64_t mmad_roi_pool_algorithmic_bytes(const mmad_roi_plan* pl, int64_t n_vols) {
+    if (!pl || n_vols <= 0) return 0;
+    // every voxel of every volume once, the run programme once, three outputs per (volume, ROI)
+    return (int64_t)n_vols * pl->V * 4 + (int64_t)pl->h_prog.size() * 4 + (int64_t)n_vols * pl->R * 12;
+}
+
+// ---- host-only introspection for the CPU test-suite (no CUDA calls) ----------------------
+// Copies the run programme of a plan: words (may be NULL to query sizes) and 16-byte-unit offsets.
+int mmad_roi_plan_programme(const mmad_roi_plan* pl, uint32_t* words, int64_t* n_words, int32_t* offs,
+                            int32_t* n_tiles, int32_t* stages, int64_t* smem_bytes) {
+    MMAD_CHECK_ARG(pl, "roi_plan_programme: null plan");
+    if (n_words) *n_words = (int64_t)pl->h_prog.size();
+    if (n_tiles) *n_tiles = pl->n_tiles;
+    if (stages) *stages = pl->ns;
+    if (smem_bytes) *smem_bytes = (int64_t)pl->smem_bytes;
+    if (words) std::memcpy(words, pl->h_prog.data(), pl->h_prog.size() * 4);
+    if (offs) std::memcpy(offs, pl->h_prog_off.data(), pl->h_prog_off.size() * 4);
+    return MMAD_OK;
+}
+
+// Work-item / slot layout the plan would use for n_vols volumes on a GPU with `sms` SMs
+// (host-only).  Arrays may be NULL to query sizes first.
+int mmad_roi_plan_binding(mmad_roi_plan* pl, int64_t n_vols, int32_t sms, int32_t* n_items, int32_t* n_slots,
+                          int32_t* grid, int32_t* item_group, int32_t* item_t0, int32_t* item_t1,
+                          int32_t* item_slot_ptr, uint8_t* slot_label, int32_t* fin_ptr, int32_t* fin_slots,
+                          int64_t* n_fin) {
+    MMAD_CHECK_ARG(pl && n_vols > 0 && sms > 0, "roi_plan_binding: bad argument");
+    const int keep = pl->sms;
+    pl->sms = sms;
+    Binding b;
+    build_binding_host(*pl, n_vols, b);
+    pl->sms = keep;
+    if (n_items) *n_items = b.n_items;
+    if (n_slots) *n_slots = b.n_slots;
+    if (grid) *grid = b.grid;
+    if (n_fin) *n_fin = (int64_t)b.h_fin_slots.size();
+    if (item_group) std::memcpy(item_group, b.h_item_group.data(), b.h_item_group.size() * 4);
+    if (item_t0) std::memcpy(item_t0, b.h_item_t0.data(), b.h_item_t0.size() * 4);
+    if (item_t1) std::memcpy(item_t1, b.h_item_t1.data(), b.h_item_t1.size() * 4);
+    if (item_slot_ptr) std::memcpy(item_slot_ptr, b.h_item_slot_ptr.data(), b.h_item_slot_ptr.size() * 4);
+    if (slot_label) std::memcpy(slot_label, b.h_slot_label.data(), b.h_slot_label.size());
+    if (fin_ptr) std::memcpy(fin_ptr, b.h_fin_ptr.data(), b.h_fin_ptr.size() * 4);
+    if (fin_slots) std::memcpy(fin_slots, b.h_fin_slots.data(), b.h_fin_slots.size() * 4);
+    return MMAD_OK;
+}
+
+}  // extern "C"
