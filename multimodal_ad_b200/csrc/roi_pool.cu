@@ -28,7 +28,9 @@ namespace mmad {
 
 constexpr int kConsumerWarps = 8;                 // NW
 constexpr int kHdrWords = 12;                     // per-tile programme header (NW+1 offsets, padded)
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kProducerWarps = 4;                 // NP: bulk-copy issue is serialised per warp (UBLKCP takes uniform regs)
+constexpr int kRowsPerProducer = 32 / kProducerWarps;
+constexpr int kThreads = (kConsumerWarps + kProducerWarps) * 32;
 constexpr int kMaxSmem = 227 * 1024;
 
 __host__ __device__ constexpr int row_pitch(int tile) { return tile + 4; }                 // floats; == 4 (mod 32)
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < ns; ++s) {
-            mbar_init(full0 + 8 * s, 1);
+            mbar_init(full0 + 8 * s, kProducerWarps);
             mbar_init(empty0 + 8 * s, kConsumerWarps);
         }
         mbar_fence_init();
@@ -91,19 +93,22 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
     const int rho = stage_row(lane);
     uint32_t it = 0;   // tiles consumed/produced so far by this CTA (ring position)
 
-    if (warp == kConsumerWarps) {
-        // ===================== producer warp: one bulk copy per volume row =====================
+    if (warp >= kConsumerWarps) {
+        // ===================== producer warps: one bulk copy per volume row, 8 rows per warp =====================
+        const int pw = warp - kConsumerWarps;
+        const int prow = pw * kRowsPerProducer + lane;          // volume (row) this lane copies; lanes >= 8 idle
+        const int prho = stage_row(prow & 31);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const int g = p.item_group[item];
             const int t0 = p.item_t0[item], t1 = p.item_t1[item];
-            const long long vol = (long long)g * 32 + lane;
-            const bool act = vol < p.n_vols;
+            const long long vol = (long long)g * 32 + prow;
+            const bool act = lane < kRowsPerProducer && vol < p.n_vols;
             const float* vbase = p.vols + (act ? vol : 0) * p.V;
             const uint32_t sb = (uint32_t)((reinterpret_cast<uintptr_t>(vbase) >> 2) & 3);
             for (int tb = t0; tb < t1; tb += 32) {
                 const int tt = tb + lane;
-                const int o0 = tt < t1 ? p.prog_off[tt] : 0;
-                const int o1 = tt < t1 ? p.prog_off[tt + 1] : 0;
+                const int o0 = (pw == 0 && tt < t1) ? p.prog_off[tt] : 0;
+                const int o1 = (pw == 0 && tt < t1) ? p.prog_off[tt + 1] : 0;
                 const int nt = min(32, t1 - tb);
                 for (int k = 0; k < nt; ++k, ++it) {
                     const int t = tb + k;
@@ -115,15 +120,15 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
                     const long long v0 = (long long)t * TILE;
                     const int L = (int)min((long long)TILE, p.V - v0);
                     const uint32_t bytes = act ? ((sb + (uint32_t)L + 3u) & ~3u) * 4u : 0u;
-                    const uint32_t pbytes = (uint32_t)(po1 - po0) * 16u;
+                    const uint32_t pbytes = (uint32_t)(po1 - po0) * 16u;      // 0 unless pw == 0
                     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes) + pbytes;
                     if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * s, total);
                     __syncwarp();
                     const uint32_t sbase = smem_u32(stages + (size_t)s * STAGE);
                     if (act)
-                        bulk_g2s(sbase + (uint32_t)rho * P * 4u,
+                        bulk_g2s(sbase + (uint32_t)prho * P * 4u,
                                  reinterpret_cast<const char*>(vbase + v0) - sb * 4u, bytes, full0 + 8 * s);
-                    if (lane == 0)
+                    if (pw == 0 && lane == 0)
                         bulk_g2s(sbase + 32u * P * 4u, p.prog + (size_t)po0 * 4, pbytes, full0 + 8 * s);
                 }
             }
