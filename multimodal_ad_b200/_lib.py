@@ -42,7 +42,7 @@ def load() -> ctypes.CDLL:
 
     P = c_void_p
     lib.mmad_roi_plan_create.argtypes = [P, c_int64, c_int32, POINTER(P)]
-    lib.mmad_roi_plan_create_ex.argtypes = [P, c_int64, c_int32, c_int32, c_int32, c_int32, POINTER(P)]
+    lib.mmad_roi_plan_create_ex.argtypes = [P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(P)]
     lib.mmad_roi_plan_destroy.argtypes = [P]
     lib.mmad_roi_plan_counts.argtypes = [P, P]
     lib.mmad_roi_plan_counts_dev.argtypes = [P, POINTER(P)]
@@ -52,7 +52,7 @@ def load() -> ctypes.CDLL:
     lib.mmad_roi_pool_algorithmic_bytes.argtypes = [P, c_int64]
     lib.mmad_roi_pool_algorithmic_bytes.restype = c_int64
     lib.mmad_roi_plan_programme.argtypes = [P, P, POINTER(c_int64), P, POINTER(c_int32), POINTER(c_int32),
-                                            POINTER(c_int64)]
+                                            POINTER(c_int64), POINTER(c_int32)]
     lib.mmad_roi_plan_binding.argtypes = [P, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                           P, P, P, P, P, P, P, POINTER(c_int64)]
     for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",

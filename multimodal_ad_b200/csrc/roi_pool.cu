@@ -6,8 +6,8 @@
 //  * The atlas is the same for every volume of a batch, so the label map is
 //    run-length encoded ONCE on the host into a per-tile "run programme"; the
 //    kernel never touches per-voxel labels.
-//  * A CTA owns 32 volumes x a contiguous range of voxel tiles.  A producer
-//    warp stages each tile (32 rows of TILE voxels, one row per volume) into
+//  * A CTA owns 32 volumes x a contiguous range of voxel tiles.  Four producer
+//    warps stage each tile (32 rows of TILE voxels, one row per volume) into
 //    shared memory with 1-D bulk async copies (TMA engine) through an mbarrier
 //    ring; the tile's run programme rides along on the same barrier.
 //  * Consumer warps run with lane = volume.  Every lane sees the same labels,
@@ -26,16 +26,16 @@
 
 namespace mmad {
 
-constexpr int kConsumerWarps = 8;                 // NW
-constexpr int kHdrWords = 12;                     // per-tile programme header (NW+1 offsets, padded)
 constexpr int kProducerWarps = 4;                 // NP: bulk-copy issue is serialised per warp (UBLKCP takes uniform regs)
 constexpr int kRowsPerProducer = 32 / kProducerWarps;
-constexpr int kThreads = (kConsumerWarps + kProducerWarps) * 32;
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kRecLen = 8;                        // a run record covers at most 8 consecutive voxels
 
-__host__ __device__ constexpr int row_pitch(int tile) { return tile + 4; }                 // floats; == 4 (mod 32)
-__host__ __device__ constexpr int prog_words(int tile) { return (kHdrWords + tile + 3) / 4 * 4; }
-__host__ __device__ constexpr int stage_bytes(int tile) { return 32 * row_pitch(tile) * 4 + prog_words(tile) * 4; }
+// NW = consumer warps (8 or 16).  Per-tile programme: header of NW+1 record offsets padded to 4 words, then records.
+__host__ __device__ constexpr int hdr_words(int nw) { return (nw + 1 + 3) / 4 * 4; }
+__host__ __device__ constexpr int row_pitch(int tile) { return tile + 12; }                // floats; == 12 (mod 32): 4 | pitch, slack for 8-wide over-read
+__host__ __device__ constexpr int prog_words(int tile, int nw) { return (hdr_words(nw) + tile + 3) / 4 * 4; }
+__host__ __device__ constexpr int stage_bytes(int tile, int nw) { return 32 * row_pitch(tile) * 4 + prog_words(tile, nw) * 4; }
 
 struct RoiParams {
     const float* vols;
@@ -62,10 +62,51 @@ struct RoiParams {
 // read 32 different banks.
 __device__ __forceinline__ int stage_row(int lane) { return (lane >> 2) + 8 * (lane & 3); }
 
-template <int TILE>
-__global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams p) {
+// One record of n <= 8 consecutive voxels of one ROI, for the 32 volumes of the warp (lane = volume).
+// `a` holds the 8 values at the record's start (values past n are never used).  Straight-line tree per n:
+// pairwise fp32 sum -> one double add; first-occurrence argmax tree (ties keep the lower index).
+template <int N>
+__device__ __forceinline__ void roi_record(const float (&a)[kRecLen], int gidx, double& ds, float& mx, int& arg) {
+    float t;
+    if constexpr (N == 1) t = a[0];
+    else if constexpr (N == 2) t = a[0] + a[1];
+    else if constexpr (N == 3) t = (a[0] + a[1]) + a[2];
+    else if constexpr (N == 4) t = (a[0] + a[1]) + (a[2] + a[3]);
+    else if constexpr (N == 5) t = ((a[0] + a[1]) + (a[2] + a[3])) + a[4];
+    else if constexpr (N == 6) t = ((a[0] + a[1]) + (a[2] + a[3])) + (a[4] + a[5]);
+    else if constexpr (N == 7) t = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + a[6]);
+    else t = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    ds += (double)t;
+    // level 1
+    float v[4];
+    int ix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (2 * k + 1 < N) {
+            const bool g = a[2 * k + 1] > a[2 * k];
+            v[k] = g ? a[2 * k + 1] : a[2 * k];
+            ix[k] = g ? 2 * k + 1 : 2 * k;
+        } else if (2 * k < N) {
+            v[k] = a[2 * k];
+            ix[k] = 2 * k;
+        }
+    }
+    // level 2
+    float w0 = v[0], w1 = 0.f;
+    int j0 = ix[0], j1 = 0;
+    if (N > 2) { const bool g = v[1] > v[0]; w0 = g ? v[1] : v[0]; j0 = g ? ix[1] : ix[0]; }
+    if (N > 6) { const bool g = v[3] > v[2]; w1 = g ? v[3] : v[2]; j1 = g ? ix[3] : ix[2]; }
+    else if (N > 4) { w1 = v[2]; j1 = ix[2]; }
+    // level 3
+    if (N > 4) { const bool g = w1 > w0; w0 = g ? w1 : w0; j0 = g ? j1 : j0; }
+    if (w0 > mx || arg < 0) { mx = w0; arg = gidx + j0; }
+}
+
+template <int TILE, int NW>
+__global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kernel(const RoiParams p) {
     constexpr int P = row_pitch(TILE);
-    constexpr int STAGE = stage_bytes(TILE);
+    constexpr int STAGE = stage_bytes(TILE, NW);
+    constexpr int HDR = hdr_words(NW);
     extern __shared__ __align__(16) unsigned char smem[];
 
     const int R = p.R;
@@ -84,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
     if (threadIdx.x == 0) {
         for (int s = 0; s < ns; ++s) {
             mbar_init(full0 + 8 * s, kProducerWarps);
-            mbar_init(empty0 + 8 * s, kConsumerWarps);
+            mbar_init(empty0 + 8 * s, NW);
         }
         mbar_fence_init();
     }
@@ -93,9 +134,9 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
     const int rho = stage_row(lane);
     uint32_t it = 0;   // tiles consumed/produced so far by this CTA (ring position)
 
-    if (warp >= kConsumerWarps) {
+    if (warp >= NW) {
         // ===================== producer warps: one bulk copy per volume row, 8 rows per warp =====================
-        const int pw = warp - kConsumerWarps;
+        const int pw = warp - NW;
         const int prow = pw * kRowsPerProducer + lane;          // volume (row) this lane copies; lanes >= 8 idle
         const int prho = stage_row(prow & 31);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -137,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
     }
 
     // ===================== consumer warps: lane = volume, warp owns labels l % NW == warp =====================
-    constexpr int NCT = kConsumerWarps * 32;
+    constexpr int NCT = NW * 32;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int g = p.item_group[item];
         const int t0 = p.item_t0[item], t1 = p.item_t1[item];
@@ -153,6 +194,12 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
         }
         named_bar_sync(1, NCT);
 
+        // accumulators of the label this warp is currently on; they live in registers across tiles
+        int cur = 0;
+        double ds = 0.0;
+        float mx = -INFINITY;
+        int arg = -1;
+
         for (int t = t0; t < t1; ++t, ++it) {
             const uint32_t s = it % ns;
             const uint32_t ph = (it / ns) & 1;
@@ -163,64 +210,59 @@ __global__ void __launch_bounds__(kThreads, 1) roi_stream_kernel(const RoiParams
             const uint32_t r0 = prog[warp], r1 = prog[warp + 1];
             const int gbase = t * TILE;
 
-            int cur = 0;
-            double ds = 0.0;
-            float mx = -INFINITY;
-            int arg = -1;
-            for (uint32_t i = r0; i < r1; ++i) {
-                const uint32_t run = prog[kHdrWords + i];
-                const int label = (int)(run >> 24);
-                int q = (int)((run >> 12) & 0xfffu);
-                const int e = q + (int)(run & 0xfffu) + 1;
-                if (label != cur) {
-                    if (cur) {
+            if (r0 < r1 && act) {
+                uint32_t rec = prog[HDR + r0];
+                float a[kRecLen];
+                {
+                    const float* src = rowp + ((rec >> 12) & 0xfffu);
+#pragma unroll
+                    for (int k = 0; k < kRecLen; ++k) a[k] = src[k];
+                }
+                for (uint32_t i = r0; i < r1; ++i) {
+                    const uint32_t crec = rec;
+                    float c[kRecLen];
+#pragma unroll
+                    for (int k = 0; k < kRecLen; ++k) c[k] = a[k];
+                    if (i + 1 < r1) {                               // prefetch the next record while this one is reduced
+                        rec = prog[HDR + i + 1];
+                        const float* src = rowp + ((rec >> 12) & 0xfffu);
+#pragma unroll
+                        for (int k = 0; k < kRecLen; ++k) a[k] = src[k];
+                    }
+                    const int label = (int)(crec >> 24);
+                    const int gidx = gbase + (int)((crec >> 12) & 0xfffu);
+                    if (label != cur) {
+                        if (cur) {
+                            const int b = (cur - 1) * 32 + lane;
+                            bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
+                        }
+                        cur = label;
                         const int b = (cur - 1) * 32 + lane;
-                        bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
+                        ds = bins_sum[b]; mx = bins_max[b]; arg = bins_arg[b];
                     }
-                    cur = label;
-                    const int b = (cur - 1) * 32 + lane;
-                    ds = bins_sum[b]; mx = bins_max[b]; arg = bins_arg[b];
+                    switch (crec & 7u) {
+                        case 0: roi_record<1>(c, gidx, ds, mx, arg); break;
+                        case 1: roi_record<2>(c, gidx, ds, mx, arg); break;
+                        case 2: roi_record<3>(c, gidx, ds, mx, arg); break;
+                        case 3: roi_record<4>(c, gidx, ds, mx, arg); break;
+                        case 4: roi_record<5>(c, gidx, ds, mx, arg); break;
+                        case 5: roi_record<6>(c, gidx, ds, mx, arg); break;
+                        case 6: roi_record<7>(c, gidx, ds, mx, arg); break;
+                        default: roi_record<8>(c, gidx, ds, mx, arg); break;
+                    }
                 }
-                if (act) {
-#define MMAD_UPD(v, idx) if ((v) > mx || arg < 0) { mx = (v); arg = gbase + (idx); }
-                    for (; q + 8 <= e; q += 8) {
-                        const float a0 = rowp[q], a1 = rowp[q + 1], a2 = rowp[q + 2], a3 = rowp[q + 3];
-                        const float a4 = rowp[q + 4], a5 = rowp[q + 5], a6 = rowp[q + 6], a7 = rowp[q + 7];
-                        ds += (double)(((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)));
-                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1) MMAD_UPD(a2, q + 2) MMAD_UPD(a3, q + 3)
-                        MMAD_UPD(a4, q + 4) MMAD_UPD(a5, q + 5) MMAD_UPD(a6, q + 6) MMAD_UPD(a7, q + 7)
-                    }
-                    if (q + 4 <= e) {
-                        const float a0 = rowp[q], a1 = rowp[q + 1], a2 = rowp[q + 2], a3 = rowp[q + 3];
-                        ds += (double)((a0 + a1) + (a2 + a3));
-                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1) MMAD_UPD(a2, q + 2) MMAD_UPD(a3, q + 3)
-                        q += 4;
-                    }
-                    if (q + 2 <= e) {
-                        const float a0 = rowp[q], a1 = rowp[q + 1];
-                        ds += (double)(a0 + a1);
-                        MMAD_UPD(a0, q) MMAD_UPD(a1, q + 1)
-                        q += 2;
-                    }
-                    if (q < e) {
-                        const float a0 = rowp[q];
-                        ds += (double)a0;
-                        MMAD_UPD(a0, q)
-                    }
-#undef MMAD_UPD
-                }
-            }
-            if (cur) {
-                const int b = (cur - 1) * 32 + lane;
-                bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
         }
+        if (cur) {
+            const int b = (cur - 1) * 32 + lane;
+            bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
+        }
 
         named_bar_sync(1, NCT);
         const int sp0 = p.item_slot_ptr[item], sp1 = p.item_slot_ptr[item + 1];
-        for (int j = sp0 + warp; j < sp1; j += kConsumerWarps) {
+        for (int j = sp0 + warp; j < sp1; j += NW) {
             const int b = ((int)p.slot_label[j] - 1) * 32 + lane;
             p.slot_sum[(size_t)j * 32 + lane] = bins_sum[b];
             p.slot_max[(size_t)j * 32 + lane] = bins_max[b];
@@ -320,7 +362,7 @@ struct Binding {
 
 struct mmad_roi_plan {
     long long V = 0;
-    int R = 0, tile = 256, n_tiles = 0, ns = 0, sms = 148, device = 0;
+    int R = 0, tile = 256, nw = 8, n_tiles = 0, ns = 0, sms = 148, device = 0;
     size_t smem_bytes = 0;
     std::vector<uint32_t> h_prog;         // words
     std::vector<int32_t> h_prog_off;      // 16-byte units, n_tiles + 1
@@ -344,13 +386,14 @@ namespace mmad {
 
 // Host-only: run-length encode the label map into the per-tile programme.
 // Exposed through mmad_roi_plan_host_debug for the CPU tests.
-static int build_programme(const int32_t* labels, long long V, int R, int tile, std::vector<uint32_t>& prog,
+static int build_programme(const int32_t* labels, long long V, int R, int tile, int nw, std::vector<uint32_t>& prog,
                            std::vector<int32_t>& prog_off, std::vector<uint64_t>& tile_mask, int& n_tiles) {
     n_tiles = (int)((V + tile - 1) / tile);
     prog.clear();
     prog_off.assign((size_t)n_tiles + 1, 0);
     tile_mask.assign((size_t)n_tiles * 4, 0ull);
-    std::vector<uint32_t> runs[kConsumerWarps];
+    std::vector<std::vector<uint32_t>> runs((size_t)nw);
+    const int hdrw = hdr_words(nw);
     for (int t = 0; t < n_tiles; ++t) {
         for (auto& r : runs) r.clear();
         const long long v0 = (long long)t * tile;
@@ -362,23 +405,24 @@ static int build_programme(const int32_t* labels, long long V, int R, int tile, 
             int e = q + 1;
             while (e < L && labels[v0 + e] == l) ++e;
             if (l) {
-                runs[l % kConsumerWarps].push_back(((uint32_t)l << 24) | ((uint32_t)q << 12) | (uint32_t)(e - q - 1));
+                for (int a = q; a < e; a += kRecLen)            // records of <= 8 voxels
+                    runs[l % nw].push_back(((uint32_t)l << 24) | ((uint32_t)a << 12) | (uint32_t)(std::min(kRecLen, e - a) - 1));
                 tile_mask[(size_t)t * 4 + (l >> 6)] |= 1ull << (l & 63);
             }
             q = e;
         }
         prog_off[t] = (int32_t)(prog.size() / 4);
-        uint32_t hdr[kHdrWords] = {0};
+        std::vector<uint32_t> hdr((size_t)hdrw, 0u);
         uint32_t acc = 0;
-        for (int w = 0; w < kConsumerWarps; ++w) {
+        for (int w = 0; w < nw; ++w) {
             // sort by label, then start (runs of one label must be visited in ascending voxel order)
             std::sort(runs[w].begin(), runs[w].end());
             hdr[w] = acc;
             acc += (uint32_t)runs[w].size();
         }
-        hdr[kConsumerWarps] = acc;
-        prog.insert(prog.end(), hdr, hdr + kHdrWords);
-        for (int w = 0; w < kConsumerWarps; ++w) prog.insert(prog.end(), runs[w].begin(), runs[w].end());
+        hdr[nw] = acc;
+        prog.insert(prog.end(), hdr.begin(), hdr.end());
+        for (int w = 0; w < nw; ++w) prog.insert(prog.end(), runs[w].begin(), runs[w].end());
         while (prog.size() % 4) prog.push_back(0u);
     }
     prog_off[n_tiles] = (int32_t)(prog.size() / 4);
@@ -474,12 +518,18 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
     p.item_group = b->d_item_group; p.item_t0 = b->d_item_t0; p.item_t1 = b->d_item_t1;
     p.item_slot_ptr = b->d_item_slot_ptr; p.slot_label = b->d_slot_label;
     p.slot_sum = b->d_slot_sum; p.slot_max = b->d_slot_max; p.slot_arg = b->d_slot_arg;
-    switch (pl->tile) {
-        case 128: roi_stream_kernel<128><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
-        case 256: roi_stream_kernel<256><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
-        case 512: roi_stream_kernel<512><<<b->grid, kThreads, pl->smem_bytes, st>>>(p); break;
-        default: return fail(MMAD_EUNSUPPORTED, "roi tile must be 128, 256 or 512");
+#define MMAD_ROI_LAUNCH(T, W) roi_stream_kernel<T, W><<<b->grid, (W + kProducerWarps) * 32, pl->smem_bytes, st>>>(p)
+    const int key = pl->tile * 100 + pl->nw;
+    switch (key) {
+        case 12808: MMAD_ROI_LAUNCH(128, 8); break;
+        case 25608: MMAD_ROI_LAUNCH(256, 8); break;
+        case 51208: MMAD_ROI_LAUNCH(512, 8); break;
+        case 12816: MMAD_ROI_LAUNCH(128, 16); break;
+        case 25616: MMAD_ROI_LAUNCH(256, 16); break;
+        case 51216: MMAD_ROI_LAUNCH(512, 16); break;
+        default: return fail(MMAD_EUNSUPPORTED, "roi tile must be 128, 256 or 512 and consumer warps 8 or 16");
     }
+#undef MMAD_ROI_LAUNCH
     MMAD_CUDA(cudaGetLastError());
     const int warps = b->n_groups * pl->R;
     roi_finalize_kernel<<<(warps + 3) / 4, 128, 0, st>>>(b->d_slot_sum, b->d_slot_max, b->d_slot_arg, b->d_fin_ptr,
@@ -499,24 +549,26 @@ extern "C" {
 // Extended constructor used by bench.py / tests for tuning: tile in {128,256,512},
 // stages 0 = as many as fit (max 4).
 int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_t n_rois, int32_t tile,
-                            int32_t stages, int32_t host_only, mmad_roi_plan** plan_out) {
+                            int32_t stages, int32_t consumer_warps, int32_t host_only, mmad_roi_plan** plan_out) {
     MMAD_CHECK_ARG(labels_host && plan_out, "roi_plan_create: null pointer");
     MMAD_CHECK_ARG(n_voxels > 0 && n_voxels < (1ll << 31) - 4096, "roi_plan_create: n_voxels must be in (0, 2^31)");
     MMAD_CHECK_ARG(n_rois >= 1 && n_rois <= 255, "roi_plan_create: n_rois must be 1..255");
     MMAD_CHECK_ARG(tile == 128 || tile == 256 || tile == 512, "roi_plan_create: tile must be 128, 256 or 512");
+    if (consumer_warps == 0) consumer_warps = 8;
+    MMAD_CHECK_ARG(consumer_warps == 8 || consumer_warps == 16, "roi_plan_create: consumer_warps must be 8 or 16");
     mmad_roi_plan* pl = new mmad_roi_plan();
-    pl->V = n_voxels; pl->R = n_rois; pl->tile = tile;
-    if (build_programme(labels_host, n_voxels, n_rois, tile, pl->h_prog, pl->h_prog_off, pl->h_tile_mask, pl->n_tiles)) {
+    pl->V = n_voxels; pl->R = n_rois; pl->tile = tile; pl->nw = consumer_warps;
+    if (build_programme(labels_host, n_voxels, n_rois, tile, pl->nw, pl->h_prog, pl->h_prog_off, pl->h_tile_mask, pl->n_tiles)) {
         delete pl;
         return fail(MMAD_EINVAL, "roi_plan_create: label outside [0, n_rois]");
     }
     const size_t bins = (((size_t)n_rois * 512) + 15) & ~(size_t)15;
-    int ns = (int)((kMaxSmem - bins - 64) / stage_bytes(tile));
+    int ns = (int)((kMaxSmem - bins - 64) / stage_bytes(tile, pl->nw));
     ns = std::min(ns, 4);
     if (stages > 0) ns = std::min(ns, (int)stages);
     if (ns < 2) { delete pl; return fail(MMAD_EUNSUPPORTED, "roi_plan_create: shared memory too small for this tile / n_rois"); }
     pl->ns = ns;
-    pl->smem_bytes = bins + (size_t)ns * stage_bytes(tile) + 64;
+    pl->smem_bytes = bins + (size_t)ns * stage_bytes(tile, pl->nw) + 64;
     if (host_only) { *plan_out = pl; return MMAD_OK; }
 
     int dev = 0;
@@ -539,9 +591,10 @@ int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_
     }
     pl->h_counts.resize(n_rois);
     if (e == cudaSuccess) e = cudaMemcpy(pl->h_counts.data(), pl->d_counts, sizeof(int32_t) * n_rois, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+#define MMAD_ROI_ATTR(T, W) if (e == cudaSuccess) e = cudaFuncSetAttribute(roi_stream_kernel<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+    MMAD_ROI_ATTR(128, 8); MMAD_ROI_ATTR(256, 8); MMAD_ROI_ATTR(512, 8);
+    MMAD_ROI_ATTR(128, 16); MMAD_ROI_ATTR(256, 16); MMAD_ROI_ATTR(512, 16);
+#undef MMAD_ROI_ATTR
     if (e != cudaSuccess) {
         std::string msg = std::string("roi_plan_create: ") + cudaGetErrorString(e);
         mmad_roi_plan_destroy(pl);
@@ -552,7 +605,7 @@ int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_
 }
 
 int mmad_roi_plan_create(const int32_t* labels_host, int64_t n_voxels, int32_t n_rois, mmad_roi_plan** plan_out) {
-    return mmad_roi_plan_create_ex(labels_host, n_voxels, n_rois, 256, 0, 0, plan_out);
+    return mmad_roi_plan_create_ex(labels_host, n_voxels, n_rois, 256, 0, 0, 0, plan_out);
 }
 
 int mmad_roi_plan_destroy(mmad_roi_plan* pl) {
@@ -670,12 +723,13 @@ int64_t mmad_roi_pool_algorithmic_bytes(const mmad_roi_plan* pl, int64_t n_vols)
 // ---- host-only introspection for the CPU test-suite (no CUDA calls) ----------------------
 // Copies the run programme of a plan: words (may be NULL to query sizes) and 16-byte-unit offsets.
 int mmad_roi_plan_programme(const mmad_roi_plan* pl, uint32_t* words, int64_t* n_words, int32_t* offs,
-                            int32_t* n_tiles, int32_t* stages, int64_t* smem_bytes) {
+                            int32_t* n_tiles, int32_t* stages, int64_t* smem_bytes, int32_t* consumer_warps) {
     MMAD_CHECK_ARG(pl, "roi_plan_programme: null plan");
     if (n_words) *n_words = (int64_t)pl->h_prog.size();
     if (n_tiles) *n_tiles = pl->n_tiles;
     if (stages) *stages = pl->ns;
     if (smem_bytes) *smem_bytes = (int64_t)pl->smem_bytes;
+    if (consumer_warps) *consumer_warps = pl->nw;
     if (words) std::memcpy(words, pl->h_prog.data(), pl->h_prog.size() * 4);
     if (offs) std::memcpy(offs, pl->h_prog_off.data(), pl->h_prog_off.size() * 4);
     return MMAD_OK;

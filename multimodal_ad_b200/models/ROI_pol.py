@@ -40,7 +40,7 @@ class RoiPlan:
     """
 
     def __init__(self, labels, n_rois: Optional[int] = None, *, tile: int = 256, stages: int = 0,
-                 host_only: bool = False, device: Optional[torch.device] = None):
+                 consumer_warps: int = 0, host_only: bool = False, device: Optional[torch.device] = None):
         lab = _np_labels(labels)
         if lab.size == 0:
             raise ValueError("empty label map")
@@ -54,15 +54,15 @@ class RoiPlan:
         self._h = c_void_p()
         lib = _lib.load()
         if host_only:
-            rc = lib.mmad_roi_plan_create_ex(lab.ctypes.data, self.n_voxels, self.n_rois, tile, stages, 1,
-                                             byref(self._h))
+            rc = lib.mmad_roi_plan_create_ex(lab.ctypes.data, self.n_voxels, self.n_rois, tile, stages,
+                                             consumer_warps, 1, byref(self._h))
         else:
             if not torch.cuda.is_available():
                 raise _lib.MmadError("RoiPlan needs a CUDA device (no CPU fallback)")
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             with torch.cuda.device(self.device):
-                rc = lib.mmad_roi_plan_create_ex(lab.ctypes.data, self.n_voxels, self.n_rois, tile, stages, 0,
-                                                 byref(self._h))
+                rc = lib.mmad_roi_plan_create_ex(lab.ctypes.data, self.n_voxels, self.n_rois, tile, stages,
+                                                 consumer_warps, 0, byref(self._h))
         _lib.check(rc, "mmad_roi_plan_create")
         self._counts = None
 
@@ -91,13 +91,14 @@ class RoiPlan:
     def programme(self):
         """(words uint32[], offsets int32[n_tiles+1] in 16-byte units, stages, smem_bytes) — host-side, for tests."""
         lib = _lib.load()
-        nw, nt, ns, sm = c_int64(), c_int32(), c_int32(), c_int64()
-        _lib.check(lib.mmad_roi_plan_programme(self._h, None, byref(nw), None, byref(nt), byref(ns), byref(sm)),
-                   "mmad_roi_plan_programme")
+        nw, nt, ns, sm, cw = c_int64(), c_int32(), c_int32(), c_int64(), c_int32()
+        _lib.check(lib.mmad_roi_plan_programme(self._h, None, byref(nw), None, byref(nt), byref(ns), byref(sm),
+                                               byref(cw)), "mmad_roi_plan_programme")
+        self.consumer_warps = cw.value
         words = np.empty(nw.value, np.uint32)
         offs = np.empty(nt.value + 1, np.int32)
-        _lib.check(lib.mmad_roi_plan_programme(self._h, words.ctypes.data, None, offs.ctypes.data, None, None, None),
-                   "mmad_roi_plan_programme")
+        _lib.check(lib.mmad_roi_plan_programme(self._h, words.ctypes.data, None, offs.ctypes.data, None, None, None,
+                                               None), "mmad_roi_plan_programme")
         return words, offs, ns.value, sm.value
 
     def binding(self, n_vols: int, sms: int = 148) -> dict:

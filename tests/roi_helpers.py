@@ -37,7 +37,8 @@ def emulate_kernel(plan, feats2d, sms=148):
     with the GPU."""
     words, offs, _, _ = plan.programme()
     n, V = feats2d.shape
-    R, T, NW, HDR = plan.n_rois, plan.tile, 8, 12
+    R, T, NW = plan.n_rois, plan.tile, plan.consumer_warps
+    HDR = (NW + 1 + 3) // 4 * 4
     b = plan.binding(n, sms)
     ssum = np.zeros((b["n_slots"], 32))
     smax = np.full((b["n_slots"], 32), -np.inf, np.float32)
@@ -55,12 +56,10 @@ def emulate_kernel(plan, feats2d, sms=148):
                 prev = -1
                 for run in runs[hdr[w]:hdr[w + 1]]:
                     label, q, ln = int(run >> 24), int((run >> 12) & 0xfff), int(run & 0xfff) + 1
-                    assert label % NW == w and 1 <= label <= R
-                    assert (label, q) > (prev >> 12 >> 12, (prev >> 12) & 0xfff) if prev >= 0 else True
+                    assert label % NW == w and 1 <= label <= R and 1 <= ln <= 8
+                    assert int(run) > prev                      # sorted by (label, start)
                     prev = int(run)
                     seg = feats2d[vols, t * T + q: t * T + q + ln]
-                    if item % b["n_groups"] == 0 or b["n_groups"] == 1:
-                        pass
                     bins_s[label - 1, :len(vols)] += seg.astype(np.float64).sum(1)
                     for j in range(ln):
                         v = seg[:, j]

@@ -48,15 +48,16 @@ def test_golden_fixture_through_module(case, built_lib):
     assert np.array_equal(out["counts"].numpy(), cnt), "voxel counts must be bit-exact"
 
 
+@pytest.mark.parametrize("cw", [8, 16])
 @pytest.mark.parametrize("tile", [128, 256, 512])
 @pytest.mark.parametrize("n_vols", [1, 5, 33, 64, 70])
-def test_aal_sized_atlas_vs_c_oracle(n_vols, tile, built_lib, c_oracle):
+def test_aal_sized_atlas_vs_c_oracle(n_vols, tile, cw, built_lib, c_oracle):
     from multimodal_ad_b200 import RoiPlan
 
-    if tile != 256 and n_vols not in (5, 64):
-        pytest.skip("tile sweep on two batch sizes only")
+    if (tile != 256 or cw != 8) and n_vols not in (5, 64):
+        pytest.skip("tile / warp sweep on two batch sizes only")
     lab = synthetic_atlas()
-    plan = RoiPlan(lab, 170, tile=tile)
+    plan = RoiPlan(lab, 170, tile=tile, consumer_warps=cw)
     g = torch.Generator(device="cuda").manual_seed(n_vols)
     x = torch.rand((n_vols, lab.size), device="cuda", generator=g)       # ScaleIntensityd range (ADNI.py:148)
     mean, mx, arg = plan.pool(x)
@@ -74,8 +75,8 @@ def test_ragged_sizes_and_alignments(v, built_lib):
     from multimodal_ad_b200 import RoiPlan
 
     rng = np.random.default_rng(v)
-    lab = np.repeat(rng.integers(0, 9, size=(v + 6) // 7), 7)[:v].astype(np.int32)
-    plan = RoiPlan(lab, 8, tile=128)
+    lab = np.repeat(rng.integers(0, 9, size=(v + 10) // 11), 11)[:v].astype(np.int32)   # runs of 11: records of 8 + 3
+    plan = RoiPlan(lab, 8, tile=128, consumer_warps=16 if v % 2 else 8)
     for n, off in [(3, 0), (37, 1), (4, 3)]:
         buf = torch.randn(n * v + 4, device="cuda")
         x = buf[off:off + n * v].view(n, v)

@@ -7,42 +7,45 @@ from oracle.roi_oracle import roi_pool_oracle, synthetic_atlas
 from roi_helpers import emulate_kernel, mean_tolerance
 
 
-def _plan(lab, r, tile=128):
+def _plan(lab, r, tile=128, cw=0):
     from multimodal_ad_b200.models.ROI_pol import RoiPlan
 
-    return RoiPlan(lab, r, tile=tile, host_only=True)
+    return RoiPlan(lab, r, tile=tile, consumer_warps=cw, host_only=True)
 
 
 def test_programme_reconstructs_the_label_map(built_lib):
     lab = synthetic_atlas((17, 13, 19), 40, seed=5, empty=(7, 8))
-    for tile in (128, 256, 512):
-        plan = _plan(lab, 40, tile)
+    for tile, cw in ((128, 8), (256, 8), (512, 8), (256, 16)):
+        plan = _plan(lab, 40, tile, cw)
         words, offs, ns, smem = plan.programme()
-        assert 2 <= ns <= 4 and smem <= 227 * 1024
+        nw = plan.consumer_warps
+        H = (nw + 1 + 3) // 4 * 4
+        assert nw == cw and 2 <= ns <= 4 and smem <= 227 * 1024
         flat = lab.reshape(-1)
         rec = np.zeros_like(flat)
         n_tiles = len(offs) - 1
         assert n_tiles == (flat.size + tile - 1) // tile
         for t in range(n_tiles):
             w0 = offs[t] * 4
-            hdr = words[w0:w0 + 12]
-            assert hdr[0] == 0 and np.all(np.diff(hdr[:9].astype(np.int64)) >= 0)
-            runs = words[w0 + 12: w0 + 12 + hdr[8]]
-            assert (offs[t + 1] - offs[t]) * 4 >= 12 + hdr[8] and (offs[t + 1] - offs[t]) * 4 - (12 + hdr[8]) < 4
+            hdr = words[w0:w0 + H]
+            assert hdr[0] == 0 and np.all(np.diff(hdr[:nw + 1].astype(np.int64)) >= 0)
+            runs = words[w0 + H: w0 + H + hdr[nw]]
+            assert (offs[t + 1] - offs[t]) * 4 >= H + hdr[nw] and (offs[t + 1] - offs[t]) * 4 - (H + hdr[nw]) < 4
             for run in runs:
                 l, q, ln = int(run >> 24), int((run >> 12) & 0xfff), int(run & 0xfff) + 1
-                assert q + ln <= tile
+                assert q + ln <= tile and ln <= 8
                 assert np.all(rec[t * tile + q: t * tile + q + ln] == 0)
                 rec[t * tile + q: t * tile + q + ln] = l
         assert np.array_equal(rec, flat)
 
 
-@pytest.mark.parametrize("n_vols,sms", [(1, 148), (5, 148), (33, 148), (64, 148), (70, 4), (200, 3)])
-def test_emulated_kernel_matches_oracle(built_lib, n_vols, sms):
+@pytest.mark.parametrize("n_vols,sms,cw", [(1, 148, 8), (5, 148, 16), (33, 148, 8), (64, 148, 16), (70, 4, 8),
+                                           (200, 3, 16)])
+def test_emulated_kernel_matches_oracle(built_lib, n_vols, sms, cw):
     rng = np.random.default_rng(n_vols)
     lab = synthetic_atlas((9, 11, 13), 21, seed=n_vols, empty=(3,))
     feats = rng.standard_normal((n_vols, lab.size)).astype(np.float32)
-    plan = _plan(lab, 21)
+    plan = _plan(lab, 21, cw=cw)
     mean, mx, arg, cnt = emulate_kernel(plan, feats, sms)
     omean, omx, oarg, ocnt = roi_pool_oracle(feats, lab, 21)
     assert np.array_equal(cnt, ocnt)

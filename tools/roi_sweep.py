@@ -12,10 +12,10 @@ def main():
     batches = [int(a) for a in sys.argv[1:]] or [64]
     for B in batches:
         bufs = [torch.rand((B, V), device="cuda") for _ in range(3)]
-        for tile in (128, 256, 512):
-            for stages in (2, 3, 4):
+        for tile, stages, cw in [(t, st, c) for c in (8, 16) for t in (128, 256, 512) for st in (2, 3, 4)]:
+            if True:
                 try:
-                    plan = RoiPlan(lab, 170, tile=tile, stages=stages)
+                    plan = RoiPlan(lab, 170, tile=tile, stages=stages, consumer_warps=cw)
                 except Exception as e:
                     print("skip", tile, stages, e); continue
                 _, _, ns, smem = plan.programme()
@@ -29,7 +29,7 @@ def main():
                 b.record(); b.synchronize()
                 us = a.elapsed_time(b) * 1e3 / K
                 gbs = plan.algorithmic_bytes(B) / (us * 1e-6) / 1e9
-                print(json.dumps(dict(batch=B, tile=tile, stages=ns, smem=smem, us=round(us, 2), gbs=round(gbs, 1))), flush=True)
+                print(json.dumps(dict(batch=B, tile=tile, cw=cw, stages=ns, smem=smem, us=round(us, 2), gbs=round(gbs, 1))), flush=True)
                 del plan
 
 if __name__ == "__main__":
