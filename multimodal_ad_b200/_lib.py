@@ -54,7 +54,7 @@ def load() -> ctypes.CDLL:
     lib.mmad_roi_plan_programme.argtypes = [P, P, POINTER(c_int64), P, POINTER(c_int32), POINTER(c_int32),
                                             POINTER(c_int64), POINTER(c_int32)]
     lib.mmad_roi_plan_binding.argtypes = [P, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
-                                          P, P, P, P, P, P, P, POINTER(c_int64)]
+                                          P, P, P, P, P, P, P]
     for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",
                  "mmad_roi_plan_counts_dev", "mmad_roi_pool_f32", "mmad_roi_pool_host_f32",
                  "mmad_roi_pool_mean_backward_f32", "mmad_roi_plan_programme", "mmad_roi_plan_binding"):

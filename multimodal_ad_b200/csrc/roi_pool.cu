@@ -11,12 +11,15 @@
 //    shared memory with 1-D bulk async copies (TMA engine) through an mbarrier
 //    ring; the tile's run programme rides along on the same barrier.
 //  * Consumer warps run with lane = volume.  Every lane sees the same labels,
-//    so control flow is warp-uniform, and lane-private accumulator columns
-//    need no atomics.  Labels are partitioned across the consumer warps, so no
-//    two warps ever touch the same accumulator either.
-//  * Sums are carried in double per (ROI, volume); partials leave the CTA once
-//    per work item and a small second kernel reduces them in a fixed order:
-//    results are bit-reproducible run to run.
+//    so control flow is warp-uniform and lanes never collide.  A tile's records
+//    (<= 8 voxels of one ROI each, sorted by ROI) are split evenly over the
+//    consumer warps; a warp keeps the ROI it is on in registers and, when the ROI
+//    changes, folds its partial into the CTA's shared accumulators with
+//    shared-memory CAS atomics (rare: once per ROI change).
+//  * Sums are carried in double per (ROI, volume); max and argmax travel as one
+//    64-bit key (ordered value bits, inverted voxel index), so the first maximal
+//    voxel wins whatever the order of the merges.  Partials leave the CTA once
+//    per work item; a small second kernel reduces them in a fixed order.
 #include "common.cuh"
 
 #include <algorithm>
@@ -31,11 +34,31 @@ constexpr int kRowsPerProducer = 32 / kProducerWarps;
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kRecLen = 8;                        // a run record covers at most 8 consecutive voxels
 
-// NW = consumer warps (8 or 16).  Per-tile programme: header of NW+1 record offsets padded to 4 words, then records.
-__host__ __device__ constexpr int hdr_words(int nw) { return (nw + 1 + 3) / 4 * 4; }
+// Per-tile programme: 4 header words (record count, 0, 0, 0), then the records sorted by (ROI, start).
+constexpr int kHdrWords = 4;
 __host__ __device__ constexpr int row_pitch(int tile) { return tile + 12; }                // floats; == 12 (mod 32): 4 | pitch, slack for 8-wide over-read
-__host__ __device__ constexpr int prog_words(int tile, int nw) { return (hdr_words(nw) + tile + 3) / 4 * 4; }
-__host__ __device__ constexpr int stage_bytes(int tile, int nw) { return 32 * row_pitch(tile) * 4 + prog_words(tile, nw) * 4; }
+__host__ __device__ constexpr int prog_words(int tile) { return (kHdrWords + tile + 3) / 4 * 4; }
+__host__ __device__ constexpr int stage_bytes(int tile) { return 32 * row_pitch(tile) * 4 + prog_words(tile) * 4; }
+
+// max/argmax key: high word = float bits mapped to an order-preserving unsigned (with -0 folded into +0),
+// low word = ~voxel index, so that of two equal values the LOWER index gives the larger key.  0 = "no voxel yet".
+__host__ __device__ __forceinline__ unsigned long long roi_pack_key(float v, int idx) {
+    v = v + 0.0f;
+    unsigned int u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(v);
+#else
+    std::memcpy(&u, &v, 4);
+#endif
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned int)idx);
+}
+__device__ __forceinline__ void roi_unpack_key(unsigned long long key, float& v, int& idx) {
+    unsigned int u = (unsigned int)(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    v = __uint_as_float(u);
+    idx = (int)(0xffffffffu - (unsigned int)(key & 0xffffffffu));
+}
 
 struct RoiParams {
     const float* vols;
@@ -50,10 +73,10 @@ struct RoiParams {
     const int32_t* item_t0;      // [n_items]
     const int32_t* item_t1;      // [n_items]
     const int32_t* item_slot_ptr;  // [n_items + 1]
-    const uint8_t* slot_label;     // [n_slots], label 1..R of every partial slot
+    const uint8_t* slot_label;     // [n_slots] in item order: label 1..R of every partial the item writes
+    const int32_t* slot_dst;       // [n_slots] in item order: destination slot (slots of one (group, ROI) are contiguous)
     double* slot_sum;              // [n_slots][32]
-    float* slot_max;               // [n_slots][32]
-    int32_t* slot_arg;             // [n_slots][32]
+    unsigned long long* slot_key;  // [n_slots][32]
 };
 
 // Row of volume `lane` inside a stage.  Rows of the four volumes of a quad land
@@ -105,15 +128,13 @@ __device__ __forceinline__ void roi_record(const float (&a)[kRecLen], int gidx, 
 template <int TILE, int NW>
 __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kernel(const RoiParams p) {
     constexpr int P = row_pitch(TILE);
-    constexpr int STAGE = stage_bytes(TILE, NW);
-    constexpr int HDR = hdr_words(NW);
+    constexpr int STAGE = stage_bytes(TILE);
     extern __shared__ __align__(16) unsigned char smem[];
 
     const int R = p.R;
     double* bins_sum = reinterpret_cast<double*>(smem);
-    float* bins_max = reinterpret_cast<float*>(smem + (size_t)R * 256);
-    int* bins_arg = reinterpret_cast<int*>(smem + (size_t)R * 384);
-    unsigned char* stages = smem + (((size_t)R * 512 + 15) & ~(size_t)15);
+    unsigned long long* bins_key = reinterpret_cast<unsigned long long*>(smem + (size_t)R * 256);
+    unsigned char* stages = smem + (size_t)R * 512;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)p.ns * STAGE);
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = smem_u32(bars + p.ns);
@@ -132,7 +153,7 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
     __syncthreads();
 
     const int rho = stage_row(lane);
-    uint32_t it = 0;   // tiles consumed/produced so far by this CTA (ring position)
+    uint32_t s = 0, ph = 0;   // ring position: stage and phase parity of the next tile
 
     if (warp >= NW) {
         // ===================== producer warps: one bulk copy per volume row, 8 rows per warp =====================
@@ -151,10 +172,8 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
                 const int o0 = (pw == 0 && tt < t1) ? p.prog_off[tt] : 0;
                 const int o1 = (pw == 0 && tt < t1) ? p.prog_off[tt + 1] : 0;
                 const int nt = min(32, t1 - tb);
-                for (int k = 0; k < nt; ++k, ++it) {
+                for (int k = 0; k < nt; ++k) {
                     const int t = tb + k;
-                    const uint32_t s = it % ns;
-                    const uint32_t ph = (it / ns) & 1;
                     const int po0 = __shfl_sync(0xffffffffu, o0, k);
                     const int po1 = __shfl_sync(0xffffffffu, o1, k);
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -171,13 +190,14 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
                                  reinterpret_cast<const char*>(vbase + v0) - sb * 4u, bytes, full0 + 8 * s);
                     if (pw == 0 && lane == 0)
                         bulk_g2s(sbase + 32u * P * 4u, p.prog + (size_t)po0 * 4, pbytes, full0 + 8 * s);
+                    if (++s == (uint32_t)ns) { s = 0; ph ^= 1; }
                 }
             }
         }
         return;
     }
 
-    // ===================== consumer warps: lane = volume, warp owns labels l % NW == warp =====================
+    // ===================== consumer warps: lane = volume; a tile's records are split evenly over the warps =====================
     constexpr int NCT = NW * 32;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int g = p.item_group[item];
@@ -189,29 +209,34 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
 
         for (int i = threadIdx.x; i < R * 32; i += NCT) {
             bins_sum[i] = 0.0;
-            bins_max[i] = -INFINITY;
-            bins_arg[i] = -1;
+            bins_key[i] = 0ull;
         }
         named_bar_sync(1, NCT);
 
-        // accumulators of the label this warp is currently on; they live in registers across tiles
+        // partial of the ROI this warp is currently on (registers; survives tile boundaries)
         int cur = 0;
         double ds = 0.0;
         float mx = -INFINITY;
         int arg = -1;
+        auto flush = [&]() {
+            if (cur && arg >= 0) {
+                const int b = (cur - 1) * 32 + lane;
+                atomicAdd(&bins_sum[b], ds);
+                atomicMax(&bins_key[b], roi_pack_key(mx, arg));
+            }
+        };
 
-        for (int t = t0; t < t1; ++t, ++it) {
-            const uint32_t s = it % ns;
-            const uint32_t ph = (it / ns) & 1;
+        for (int t = t0; t < t1; ++t) {
             mbar_wait(full0 + 8 * s, ph);
             const unsigned char* sbase = stages + (size_t)s * STAGE;
             const float* rowp = reinterpret_cast<const float*>(sbase) + rho * P + sb;
             const uint32_t* prog = reinterpret_cast<const uint32_t*>(sbase + 32 * P * 4);
-            const uint32_t r0 = prog[warp], r1 = prog[warp + 1];
+            const uint32_t cnt = prog[0];
+            const uint32_t r0 = cnt * (uint32_t)warp / NW, r1 = cnt * (uint32_t)(warp + 1) / NW;
             const int gbase = t * TILE;
 
             if (r0 < r1 && act) {
-                uint32_t rec = prog[HDR + r0];
+                uint32_t rec = prog[kHdrWords + r0];
                 float a[kRecLen];
                 {
                     const float* src = rowp + ((rec >> 12) & 0xfffu);
@@ -224,7 +249,7 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
 #pragma unroll
                     for (int k = 0; k < kRecLen; ++k) c[k] = a[k];
                     if (i + 1 < r1) {                               // prefetch the next record while this one is reduced
-                        rec = prog[HDR + i + 1];
+                        rec = prog[kHdrWords + i + 1];
                         const float* src = rowp + ((rec >> 12) & 0xfffu);
 #pragma unroll
                         for (int k = 0; k < kRecLen; ++k) a[k] = src[k];
@@ -232,13 +257,8 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
                     const int label = (int)(crec >> 24);
                     const int gidx = gbase + (int)((crec >> 12) & 0xfffu);
                     if (label != cur) {
-                        if (cur) {
-                            const int b = (cur - 1) * 32 + lane;
-                            bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
-                        }
-                        cur = label;
-                        const int b = (cur - 1) * 32 + lane;
-                        ds = bins_sum[b]; mx = bins_max[b]; arg = bins_arg[b];
+                        flush();
+                        cur = label; ds = 0.0; mx = -INFINITY; arg = -1;
                     }
                     switch (crec & 7u) {
                         case 0: roi_record<1>(c, gidx, ds, mx, arg); break;
@@ -254,31 +274,27 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if (++s == (uint32_t)ns) { s = 0; ph ^= 1; }
         }
-        if (cur) {
-            const int b = (cur - 1) * 32 + lane;
-            bins_sum[b] = ds; bins_max[b] = mx; bins_arg[b] = arg;
-        }
+        flush();
 
         named_bar_sync(1, NCT);
         const int sp0 = p.item_slot_ptr[item], sp1 = p.item_slot_ptr[item + 1];
         for (int j = sp0 + warp; j < sp1; j += NW) {
             const int b = ((int)p.slot_label[j] - 1) * 32 + lane;
-            p.slot_sum[(size_t)j * 32 + lane] = bins_sum[b];
-            p.slot_max[(size_t)j * 32 + lane] = bins_max[b];
-            p.slot_arg[(size_t)j * 32 + lane] = bins_arg[b];
+            const size_t o = (size_t)p.slot_dst[j] * 32 + lane;
+            p.slot_sum[o] = bins_sum[b];
+            p.slot_key[o] = bins_key[b];
         }
         named_bar_sync(1, NCT);
     }
 }
 
-// Second pass: one warp per (volume group, ROI) walks that ROI's partial slots in
-// ascending tile order (fixed order => reproducible; strict '>' keeps the first max).
+// Second pass: one warp per (volume group, ROI), lane = volume.  The ROI's partial slots are contiguous and in
+// ascending tile order; sums are added in that fixed order, keys are max-reduced (order independent).
 __global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restrict__ slot_sum,
-                                                           const float* __restrict__ slot_max,
-                                                           const int32_t* __restrict__ slot_arg,
+                                                           const unsigned long long* __restrict__ slot_key,
                                                            const int32_t* __restrict__ fin_ptr,
-                                                           const int32_t* __restrict__ fin_slots,
                                                            const int32_t* __restrict__ counts, int n_groups, int R,
                                                            long long n_vols, float* __restrict__ mean,
                                                            float* __restrict__ mx_out, int32_t* __restrict__ arg_out) {
@@ -287,24 +303,39 @@ __global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restr
     if (w >= n_groups * R) return;
     const int g = w / R, r = w - g * R;
     double s = 0.0;
-    float mx = -INFINITY;
-    int arg = -1;
+    unsigned long long key = 0ull;
     const int k0 = fin_ptr[w], k1 = fin_ptr[w + 1];
-    for (int k = k0; k < k1; ++k) {
-        const size_t o = (size_t)fin_slots[k] * 32 + lane;
-        s += slot_sum[o];
-        const float m = slot_max[o];
-        const int a = slot_arg[o];
-        if (a >= 0 && (arg < 0 || m > mx)) { mx = m; arg = a; }
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        double sv[4];
+        unsigned long long kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            sv[u] = slot_sum[(size_t)(k + u) * 32 + lane];
+            kv[u] = slot_key[(size_t)(k + u) * 32 + lane];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s += sv[u];
+            key = kv[u] > key ? kv[u] : key;
+        }
+    }
+    for (; k < k1; ++k) {
+        s += slot_sum[(size_t)k * 32 + lane];
+        const unsigned long long kk = slot_key[(size_t)k * 32 + lane];
+        key = kk > key ? kk : key;
     }
     const long long vol = (long long)g * 32 + lane;
     if (vol >= n_vols) return;
     const int cnt = counts[r];
     const float den = fmaxf((float)cnt, 1e-6f);
+    float mx = 0.0f;
+    int arg = -1;
+    if (cnt && key) roi_unpack_key(key, mx, arg);
     const size_t o = (size_t)vol * R + r;
     if (mean) mean[o] = (float)s / den;
-    if (mx_out) mx_out[o] = cnt ? mx : 0.0f;
-    if (arg_out) arg_out[o] = cnt ? arg : -1;
+    if (mx_out) mx_out[o] = mx;
+    if (arg_out) arg_out[o] = arg;
 }
 
 // Per-ROI voxel counts of the uint8 label map (plan creation, once per atlas).
@@ -343,18 +374,17 @@ __global__ void __launch_bounds__(256) roi_mean_bwd_kernel(const float* __restri
 struct Binding {
     long long n_vols = 0;
     int n_groups = 0, n_items = 0, grid = 0, n_slots = 0;
-    std::vector<int32_t> h_item_group, h_item_t0, h_item_t1, h_item_slot_ptr, h_fin_ptr, h_fin_slots;
+    std::vector<int32_t> h_item_group, h_item_t0, h_item_t1, h_item_slot_ptr, h_slot_dst, h_fin_ptr;
     std::vector<uint8_t> h_slot_label;
     int32_t *d_item_group = nullptr, *d_item_t0 = nullptr, *d_item_t1 = nullptr, *d_item_slot_ptr = nullptr;
-    int32_t *d_fin_ptr = nullptr, *d_fin_slots = nullptr;
+    int32_t *d_slot_dst = nullptr, *d_fin_ptr = nullptr;
     uint8_t* d_slot_label = nullptr;
     double* d_slot_sum = nullptr;
-    float* d_slot_max = nullptr;
-    int32_t* d_slot_arg = nullptr;
+    unsigned long long* d_slot_key = nullptr;
     void release() {
         cudaFree(d_item_group); cudaFree(d_item_t0); cudaFree(d_item_t1); cudaFree(d_item_slot_ptr);
-        cudaFree(d_fin_ptr); cudaFree(d_fin_slots); cudaFree(d_slot_label);
-        cudaFree(d_slot_sum); cudaFree(d_slot_max); cudaFree(d_slot_arg);
+        cudaFree(d_slot_dst); cudaFree(d_fin_ptr); cudaFree(d_slot_label);
+        cudaFree(d_slot_sum); cudaFree(d_slot_key);
     }
 };
 
@@ -384,18 +414,17 @@ struct mmad_roi_plan {
 
 namespace mmad {
 
-// Host-only: run-length encode the label map into the per-tile programme.
-// Exposed through mmad_roi_plan_host_debug for the CPU tests.
-static int build_programme(const int32_t* labels, long long V, int R, int tile, int nw, std::vector<uint32_t>& prog,
+// Host-only: run-length encode the label map into the per-tile programme (records of <= 8 voxels,
+// sorted by (ROI, start) inside a tile).
+static int build_programme(const int32_t* labels, long long V, int R, int tile, std::vector<uint32_t>& prog,
                            std::vector<int32_t>& prog_off, std::vector<uint64_t>& tile_mask, int& n_tiles) {
     n_tiles = (int)((V + tile - 1) / tile);
     prog.clear();
     prog_off.assign((size_t)n_tiles + 1, 0);
     tile_mask.assign((size_t)n_tiles * 4, 0ull);
-    std::vector<std::vector<uint32_t>> runs((size_t)nw);
-    const int hdrw = hdr_words(nw);
+    std::vector<uint32_t> recs;
     for (int t = 0; t < n_tiles; ++t) {
-        for (auto& r : runs) r.clear();
+        recs.clear();
         const long long v0 = (long long)t * tile;
         const int L = (int)std::min<long long>(tile, V - v0);
         int q = 0;
@@ -405,32 +434,25 @@ static int build_programme(const int32_t* labels, long long V, int R, int tile, 
             int e = q + 1;
             while (e < L && labels[v0 + e] == l) ++e;
             if (l) {
-                for (int a = q; a < e; a += kRecLen)            // records of <= 8 voxels
-                    runs[l % nw].push_back(((uint32_t)l << 24) | ((uint32_t)a << 12) | (uint32_t)(std::min(kRecLen, e - a) - 1));
+                for (int a = q; a < e; a += kRecLen)
+                    recs.push_back(((uint32_t)l << 24) | ((uint32_t)a << 12) | (uint32_t)(std::min(kRecLen, e - a) - 1));
                 tile_mask[(size_t)t * 4 + (l >> 6)] |= 1ull << (l & 63);
             }
             q = e;
         }
+        std::sort(recs.begin(), recs.end());
         prog_off[t] = (int32_t)(prog.size() / 4);
-        std::vector<uint32_t> hdr((size_t)hdrw, 0u);
-        uint32_t acc = 0;
-        for (int w = 0; w < nw; ++w) {
-            // sort by label, then start (runs of one label must be visited in ascending voxel order)
-            std::sort(runs[w].begin(), runs[w].end());
-            hdr[w] = acc;
-            acc += (uint32_t)runs[w].size();
-        }
-        hdr[nw] = acc;
-        prog.insert(prog.end(), hdr.begin(), hdr.end());
-        for (int w = 0; w < nw; ++w) prog.insert(prog.end(), runs[w].begin(), runs[w].end());
+        prog.push_back((uint32_t)recs.size());
+        for (int k = 1; k < kHdrWords; ++k) prog.push_back(0u);
+        prog.insert(prog.end(), recs.begin(), recs.end());
         while (prog.size() % 4) prog.push_back(0u);
     }
     prog_off[n_tiles] = (int32_t)(prog.size() / 4);
     return 0;
 }
 
-// Host-only: split the (volume group x tile) space into work items and lay out
-// the partial slots each item writes and each (group, ROI) reads back.
+// Host-only: split the (volume group x tile) space into work items and lay out the partial slots.
+// Slots of one (group, ROI) are contiguous and ordered by tile range, so the second pass reads them linearly.
 static void build_binding_host(const mmad_roi_plan& pl, long long n_vols, Binding& b) {
     b.n_vols = n_vols;
     b.n_groups = (int)((n_vols + 31) / 32);
@@ -441,34 +463,40 @@ static void build_binding_host(const mmad_roi_plan& pl, long long n_vols, Bindin
     b.h_item_group.resize(b.n_items); b.h_item_t0.resize(b.n_items); b.h_item_t1.resize(b.n_items);
     b.h_item_slot_ptr.assign((size_t)b.n_items + 1, 0);
     b.h_slot_label.clear();
-    // item = piece * n_groups + g : neighbouring CTAs stream the same tile range of different groups
-    std::vector<std::vector<int32_t>> per_gr((size_t)b.n_groups * pl.R);
+    b.h_slot_dst.clear();
+    // pass 1: which ROIs each piece touches; count slots per (group, ROI)
+    std::vector<std::vector<uint8_t>> piece_labels((size_t)pieces);
+    std::vector<int32_t> per_roi((size_t)pl.R, 0);
     for (int piece = 0; piece < pieces; ++piece) {
         const int t0 = (int)((long long)pl.n_tiles * piece / pieces);
         const int t1 = (int)((long long)pl.n_tiles * (piece + 1) / pieces);
         uint64_t m[4] = {0, 0, 0, 0};
         for (int t = t0; t < t1; ++t)
             for (int k = 0; k < 4; ++k) m[k] |= pl.h_tile_mask[(size_t)t * 4 + k];
+        for (int l = 1; l <= pl.R; ++l)
+            if (m[l >> 6] >> (l & 63) & 1ull) { piece_labels[piece].push_back((uint8_t)l); per_roi[l - 1]++; }
+    }
+    b.h_fin_ptr.assign((size_t)b.n_groups * pl.R + 1, 0);
+    for (int g = 0; g < b.n_groups; ++g)
+        for (int r = 0; r < pl.R; ++r)
+            b.h_fin_ptr[(size_t)g * pl.R + r + 1] = b.h_fin_ptr[(size_t)g * pl.R + r] + per_roi[r];
+    b.n_slots = b.h_fin_ptr.back();
+    // pass 2: items (item = piece * n_groups + g: neighbouring CTAs stream the same tile range of different groups)
+    std::vector<int32_t> next(b.h_fin_ptr.begin(), b.h_fin_ptr.end() - 1);
+    for (int piece = 0; piece < pieces; ++piece) {
+        const int t0 = (int)((long long)pl.n_tiles * piece / pieces);
+        const int t1 = (int)((long long)pl.n_tiles * (piece + 1) / pieces);
         for (int g = 0; g < b.n_groups; ++g) {
             const int item = piece * b.n_groups + g;
             b.h_item_group[item] = g; b.h_item_t0[item] = t0; b.h_item_t1[item] = t1;
             b.h_item_slot_ptr[item] = (int32_t)b.h_slot_label.size();
-            for (int l = 1; l <= pl.R; ++l)
-                if (m[l >> 6] >> (l & 63) & 1ull) {
-                    per_gr[(size_t)g * pl.R + (l - 1)].push_back((int32_t)b.h_slot_label.size());
-                    b.h_slot_label.push_back((uint8_t)l);
-                }
+            for (uint8_t l : piece_labels[piece]) {
+                b.h_slot_label.push_back(l);
+                b.h_slot_dst.push_back(next[(size_t)g * pl.R + (l - 1)]++);      // ascending piece => ascending tile
+            }
         }
     }
-    b.n_slots = (int)b.h_slot_label.size();
-    b.h_item_slot_ptr[b.n_items] = b.n_slots;
-    b.h_fin_ptr.assign((size_t)b.n_groups * pl.R + 1, 0);
-    b.h_fin_slots.clear();
-    for (size_t k = 0; k < per_gr.size(); ++k) {
-        b.h_fin_ptr[k] = (int32_t)b.h_fin_slots.size();
-        b.h_fin_slots.insert(b.h_fin_slots.end(), per_gr[k].begin(), per_gr[k].end());   // ascending piece => ascending tile
-    }
-    b.h_fin_ptr[per_gr.size()] = (int32_t)b.h_fin_slots.size();
+    b.h_item_slot_ptr[b.n_items] = (int32_t)b.h_slot_label.size();
 }
 
 template <typename T>
@@ -491,12 +519,11 @@ static int get_binding(mmad_roi_plan* pl, long long n_vols, Binding** out) {
     if (e == cudaSuccess) e = upload(&b->d_item_t1, b->h_item_t1);
     if (e == cudaSuccess) e = upload(&b->d_item_slot_ptr, b->h_item_slot_ptr);
     if (e == cudaSuccess) e = upload(&b->d_slot_label, b->h_slot_label);
+    if (e == cudaSuccess) e = upload(&b->d_slot_dst, b->h_slot_dst);
     if (e == cudaSuccess) e = upload(&b->d_fin_ptr, b->h_fin_ptr);
-    if (e == cudaSuccess) e = upload(&b->d_fin_slots, b->h_fin_slots);
     const size_t ns = std::max(b->n_slots, 1);
     if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_sum, ns * 32 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_max, ns * 32 * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_arg, ns * 32 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_slot_key, ns * 32 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         b->release();
         delete b;
@@ -517,7 +544,7 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
     p.prog = pl->d_prog; p.prog_off = pl->d_prog_off;
     p.item_group = b->d_item_group; p.item_t0 = b->d_item_t0; p.item_t1 = b->d_item_t1;
     p.item_slot_ptr = b->d_item_slot_ptr; p.slot_label = b->d_slot_label;
-    p.slot_sum = b->d_slot_sum; p.slot_max = b->d_slot_max; p.slot_arg = b->d_slot_arg;
+    p.slot_dst = b->d_slot_dst; p.slot_sum = b->d_slot_sum; p.slot_key = b->d_slot_key;
 #define MMAD_ROI_LAUNCH(T, W) roi_stream_kernel<T, W><<<b->grid, (W + kProducerWarps) * 32, pl->smem_bytes, st>>>(p)
     const int key = pl->tile * 100 + pl->nw;
     switch (key) {
@@ -532,9 +559,8 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
 #undef MMAD_ROI_LAUNCH
     MMAD_CUDA(cudaGetLastError());
     const int warps = b->n_groups * pl->R;
-    roi_finalize_kernel<<<(warps + 3) / 4, 128, 0, st>>>(b->d_slot_sum, b->d_slot_max, b->d_slot_arg, b->d_fin_ptr,
-                                                       b->d_fin_slots, pl->d_counts, b->n_groups, pl->R, n_vols,
-                                                       mean_dev, max_dev, argmax_dev);
+    roi_finalize_kernel<<<(warps + 3) / 4, 128, 0, st>>>(b->d_slot_sum, b->d_slot_key, b->d_fin_ptr, pl->d_counts,
+                                                       b->n_groups, pl->R, n_vols, mean_dev, max_dev, argmax_dev);
     MMAD_CUDA(cudaGetLastError());
     count_launch(2);
     return MMAD_OK;
@@ -558,17 +584,17 @@ int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_
     MMAD_CHECK_ARG(consumer_warps == 8 || consumer_warps == 16, "roi_plan_create: consumer_warps must be 8 or 16");
     mmad_roi_plan* pl = new mmad_roi_plan();
     pl->V = n_voxels; pl->R = n_rois; pl->tile = tile; pl->nw = consumer_warps;
-    if (build_programme(labels_host, n_voxels, n_rois, tile, pl->nw, pl->h_prog, pl->h_prog_off, pl->h_tile_mask, pl->n_tiles)) {
+    if (build_programme(labels_host, n_voxels, n_rois, tile, pl->h_prog, pl->h_prog_off, pl->h_tile_mask, pl->n_tiles)) {
         delete pl;
         return fail(MMAD_EINVAL, "roi_plan_create: label outside [0, n_rois]");
     }
-    const size_t bins = (((size_t)n_rois * 512) + 15) & ~(size_t)15;
-    int ns = (int)((kMaxSmem - bins - 64) / stage_bytes(tile, pl->nw));
+    const size_t bins = (size_t)n_rois * 512;
+    int ns = (int)((kMaxSmem - bins - 64) / stage_bytes(tile));
     ns = std::min(ns, 4);
     if (stages > 0) ns = std::min(ns, (int)stages);
     if (ns < 2) { delete pl; return fail(MMAD_EUNSUPPORTED, "roi_plan_create: shared memory too small for this tile / n_rois"); }
     pl->ns = ns;
-    pl->smem_bytes = bins + (size_t)ns * stage_bytes(tile, pl->nw) + 64;
+    pl->smem_bytes = bins + (size_t)ns * stage_bytes(tile) + 64;
     if (host_only) { *plan_out = pl; return MMAD_OK; }
 
     int dev = 0;
@@ -739,8 +765,7 @@ int mmad_roi_plan_programme(const mmad_roi_plan* pl, uint32_t* words, int64_t* n
 // (host-only).  Arrays may be NULL to query sizes first.
 int mmad_roi_plan_binding(mmad_roi_plan* pl, int64_t n_vols, int32_t sms, int32_t* n_items, int32_t* n_slots,
                           int32_t* grid, int32_t* item_group, int32_t* item_t0, int32_t* item_t1,
-                          int32_t* item_slot_ptr, uint8_t* slot_label, int32_t* fin_ptr, int32_t* fin_slots,
-                          int64_t* n_fin) {
+                          int32_t* item_slot_ptr, uint8_t* slot_label, int32_t* slot_dst, int32_t* fin_ptr) {
     MMAD_CHECK_ARG(pl && n_vols > 0 && sms > 0, "roi_plan_binding: bad argument");
     const int keep = pl->sms;
     pl->sms = sms;
@@ -750,14 +775,13 @@ int mmad_roi_plan_binding(mmad_roi_plan* pl, int64_t n_vols, int32_t sms, int32_
     if (n_items) *n_items = b.n_items;
     if (n_slots) *n_slots = b.n_slots;
     if (grid) *grid = b.grid;
-    if (n_fin) *n_fin = (int64_t)b.h_fin_slots.size();
     if (item_group) std::memcpy(item_group, b.h_item_group.data(), b.h_item_group.size() * 4);
     if (item_t0) std::memcpy(item_t0, b.h_item_t0.data(), b.h_item_t0.size() * 4);
     if (item_t1) std::memcpy(item_t1, b.h_item_t1.data(), b.h_item_t1.size() * 4);
     if (item_slot_ptr) std::memcpy(item_slot_ptr, b.h_item_slot_ptr.data(), b.h_item_slot_ptr.size() * 4);
     if (slot_label) std::memcpy(slot_label, b.h_slot_label.data(), b.h_slot_label.size());
+    if (slot_dst) std::memcpy(slot_dst, b.h_slot_dst.data(), b.h_slot_dst.size() * 4);
     if (fin_ptr) std::memcpy(fin_ptr, b.h_fin_ptr.data(), b.h_fin_ptr.size() * 4);
-    if (fin_slots) std::memcpy(fin_slots, b.h_fin_slots.data(), b.h_fin_slots.size() * 4);
     return MMAD_OK;
 }
 

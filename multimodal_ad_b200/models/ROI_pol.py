@@ -104,25 +104,22 @@ class RoiPlan:
     def binding(self, n_vols: int, sms: int = 148) -> dict:
         """Work-item / partial-slot layout for n_vols volumes on `sms` SMs — host-side, for tests."""
         lib = _lib.load()
-        ni, nsl, grid, nf = c_int32(), c_int32(), c_int32(), c_int64()
+        ni, nsl, grid = c_int32(), c_int32(), c_int32()
         _lib.check(lib.mmad_roi_plan_binding(self._h, n_vols, sms, byref(ni), byref(nsl), byref(grid), None, None,
-                                             None, None, None, None, None, byref(nf)), "mmad_roi_plan_binding")
+                                             None, None, None, None, None), "mmad_roi_plan_binding")
         n_groups = (n_vols + 31) // 32
         out = dict(n_items=ni.value, n_slots=nsl.value, grid=grid.value, n_groups=n_groups,
                    item_group=np.empty(ni.value, np.int32), item_t0=np.empty(ni.value, np.int32),
                    item_t1=np.empty(ni.value, np.int32), item_slot_ptr=np.empty(ni.value + 1, np.int32),
-                   slot_label=np.empty(max(nsl.value, 1), np.uint8)[:nsl.value],
-                   fin_ptr=np.empty(n_groups * self.n_rois + 1, np.int32),
-                   fin_slots=np.empty(max(nf.value, 1), np.int32)[:nf.value])
+                   fin_ptr=np.empty(n_groups * self.n_rois + 1, np.int32))
         sl = np.empty(max(nsl.value, 1), np.uint8)
-        fs = np.empty(max(nf.value, 1), np.int32)
+        sd = np.empty(max(nsl.value, 1), np.int32)
         _lib.check(lib.mmad_roi_plan_binding(self._h, n_vols, sms, None, None, None, out["item_group"].ctypes.data,
                                              out["item_t0"].ctypes.data, out["item_t1"].ctypes.data,
-                                             out["item_slot_ptr"].ctypes.data, sl.ctypes.data,
-                                             out["fin_ptr"].ctypes.data, fs.ctypes.data, None),
-                   "mmad_roi_plan_binding")
+                                             out["item_slot_ptr"].ctypes.data, sl.ctypes.data, sd.ctypes.data,
+                                             out["fin_ptr"].ctypes.data), "mmad_roi_plan_binding")
         out["slot_label"] = sl[:nsl.value]
-        out["fin_slots"] = fs[:nf.value]
+        out["slot_dst"] = sd[:nsl.value]
         return out
 
     # -- compute ----------------------------------------------------------------------

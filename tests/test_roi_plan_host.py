@@ -18,20 +18,17 @@ def test_programme_reconstructs_the_label_map(built_lib):
     for tile, cw in ((128, 8), (256, 8), (512, 8), (256, 16)):
         plan = _plan(lab, 40, tile, cw)
         words, offs, ns, smem = plan.programme()
-        nw = plan.consumer_warps
-        H = (nw + 1 + 3) // 4 * 4
-        assert nw == cw and 2 <= ns <= 4 and smem <= 227 * 1024
+        assert plan.consumer_warps == cw and 2 <= ns <= 4 and smem <= 227 * 1024
         flat = lab.reshape(-1)
         rec = np.zeros_like(flat)
         n_tiles = len(offs) - 1
         assert n_tiles == (flat.size + tile - 1) // tile
         for t in range(n_tiles):
             w0 = offs[t] * 4
-            hdr = words[w0:w0 + H]
-            assert hdr[0] == 0 and np.all(np.diff(hdr[:nw + 1].astype(np.int64)) >= 0)
-            runs = words[w0 + H: w0 + H + hdr[nw]]
-            assert (offs[t + 1] - offs[t]) * 4 >= H + hdr[nw] and (offs[t + 1] - offs[t]) * 4 - (H + hdr[nw]) < 4
-            for run in runs:
+            cnt = int(words[w0])
+            assert np.all(words[w0 + 1:w0 + 4] == 0)
+            assert 0 <= (offs[t + 1] - offs[t]) * 4 - (4 + cnt) < 4
+            for run in words[w0 + 4: w0 + 4 + cnt]:
                 l, q, ln = int(run >> 24), int((run >> 12) & 0xfff), int(run & 0xfff) + 1
                 assert q + ln <= tile and ln <= 8
                 assert np.all(rec[t * tile + q: t * tile + q + ln] == 0)
@@ -76,8 +73,9 @@ def test_binding_covers_every_tile_once(built_lib):
             order = np.argsort(b["item_t0"][it])
             t0, t1 = b["item_t0"][it][order], b["item_t1"][it][order]
             assert t0[0] == 0 and t1[-1] == n_tiles and np.array_equal(t0[1:], t1[:-1])
-        # every slot is read back exactly once
-        assert sorted(b["fin_slots"].tolist()) == list(range(b["n_slots"]))
+        # every slot is written by exactly one (item, label) and read back by exactly one (group, ROI)
+        assert sorted(b["slot_dst"].tolist()) == list(range(b["n_slots"]))
+        assert b["fin_ptr"][0] == 0 and b["fin_ptr"][-1] == b["n_slots"] and np.all(np.diff(b["fin_ptr"]) >= 0)
 
 
 def test_plan_argument_errors(built_lib):
