@@ -150,7 +150,9 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
         }
         mbar_fence_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();               // everything above overlapped the previous kernel's tail; global memory is read below
 
     const int rho = stage_row(lane);
     uint32_t s = 0, ph = 0;   // ring position: stage and phase parity of the next tile
@@ -300,6 +302,8 @@ __global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restr
                                                            float* __restrict__ mx_out, int32_t* __restrict__ arg_out) {
     const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (w >= n_groups * R) return;
     const int g = w / R, r = w - g * R;
     double s = 0.0;
@@ -545,7 +549,19 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
     p.item_group = b->d_item_group; p.item_t0 = b->d_item_t0; p.item_t1 = b->d_item_t1;
     p.item_slot_ptr = b->d_item_slot_ptr; p.slot_label = b->d_slot_label;
     p.slot_dst = b->d_slot_dst; p.slot_sum = b->d_slot_sum; p.slot_key = b->d_slot_key;
-#define MMAD_ROI_LAUNCH(T, W) roi_stream_kernel<T, W><<<b->grid, (W + kProducerWarps) * 32, pl->smem_bytes, st>>>(p)
+    // Both kernels carry the programmatic-stream-serialization attribute: their prologues overlap the
+    // previous kernel's tail, and each waits (griddepcontrol.wait) before it touches global memory.
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b->grid);
+    cfg.blockDim = dim3((pl->nw + kProducerWarps) * 32);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define MMAD_ROI_LAUNCH(T, W) MMAD_CUDA(cudaLaunchKernelEx(&cfg, roi_stream_kernel<T, W>, p))
     const int key = pl->tile * 100 + pl->nw;
     switch (key) {
         case 12808: MMAD_ROI_LAUNCH(128, 8); break;
@@ -557,11 +573,14 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
         default: return fail(MMAD_EUNSUPPORTED, "roi tile must be 128, 256 or 512 and consumer warps 8 or 16");
     }
 #undef MMAD_ROI_LAUNCH
-    MMAD_CUDA(cudaGetLastError());
     const int warps = b->n_groups * pl->R;
-    roi_finalize_kernel<<<(warps + 3) / 4, 128, 0, st>>>(b->d_slot_sum, b->d_slot_key, b->d_fin_ptr, pl->d_counts,
-                                                       b->n_groups, pl->R, n_vols, mean_dev, max_dev, argmax_dev);
-    MMAD_CUDA(cudaGetLastError());
+    cfg.gridDim = dim3((warps + 3) / 4);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    MMAD_CUDA(cudaLaunchKernelEx(&cfg, roi_finalize_kernel, (const double*)b->d_slot_sum,
+                                 (const unsigned long long*)b->d_slot_key, (const int32_t*)b->d_fin_ptr,
+                                 (const int32_t*)pl->d_counts, b->n_groups, pl->R, (long long)n_vols, mean_dev, max_dev,
+                                 argmax_dev));
     count_launch(2);
     return MMAD_OK;
 }
@@ -580,7 +599,7 @@ int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_
     MMAD_CHECK_ARG(n_voxels > 0 && n_voxels < (1ll << 31) - 4096, "roi_plan_create: n_voxels must be in (0, 2^31)");
     MMAD_CHECK_ARG(n_rois >= 1 && n_rois <= 255, "roi_plan_create: n_rois must be 1..255");
     MMAD_CHECK_ARG(tile == 128 || tile == 256 || tile == 512, "roi_plan_create: tile must be 128, 256 or 512");
-    if (consumer_warps == 0) consumer_warps = 8;
+    if (consumer_warps == 0) consumer_warps = 16;
     MMAD_CHECK_ARG(consumer_warps == 8 || consumer_warps == 16, "roi_plan_create: consumer_warps must be 8 or 16");
     mmad_roi_plan* pl = new mmad_roi_plan();
     pl->V = n_voxels; pl->R = n_rois; pl->tile = tile; pl->nw = consumer_warps;
