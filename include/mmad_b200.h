@@ -69,7 +69,9 @@ int mmad_roi_plan_counts_dev(const mmad_roi_plan* plan, const int32_t** counts_d
  *   max_dev    float32[n_vols x n_rois]  max over member voxels (0 if empty)
  *   argmax_dev int32  [n_vols x n_rois]  flat voxel index of the first max
  *                                        (-1 if the ROI is empty)
- * Asynchronous on `stream`. */
+ * With all three NULL only the streaming kernel runs (partials stay in the
+ * plan's workspace); bench.py uses that to time the dominant kernel alone.
+ * Asynchronous on `stream`.  A plan serves one in-flight call at a time. */
 int mmad_roi_pool_f32(mmad_roi_plan* plan, const float* vols_dev, int64_t n_vols,
                       float* mean_dev, float* max_dev, int32_t* argmax_dev,
                       void* stream);

@@ -151,6 +151,14 @@ class RoiPlan:
             _lib.check(rc, "mmad_roi_pool_f32")
         return mean, mx, arg
 
+    def stream_only(self, vols: torch.Tensor) -> None:
+        """Runs only the streaming kernel (no outputs) — for timing the dominant kernel alone."""
+        v = self._check_vols(vols)
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            rc = _lib.load().mmad_roi_pool_f32(self._h, v.data_ptr(), v.shape[0], None, None, None, c_void_p(stream))
+        _lib.check(rc, "mmad_roi_pool_f32")
+
     def mean_backward(self, grad_mean: torch.Tensor) -> torch.Tensor:
         g = grad_mean.contiguous().to(torch.float32)
         n = g.shape[0]

@@ -1,0 +1,54 @@
+"""N>1 host logic on CPU: world_size-2 gloo process group."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from multimodal_ad_b200.sharding import gather_subject_rows, max_over_ranks, shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 3, 8):
+            got = [i for r in range(world) for i in shard_range(n, r, world)]
+            assert got == list(range(n))
+            sizes = [len(shard_range(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_subjects = 7
+        mine = shard_range(n_subjects, rank, world)
+        rows = torch.tensor([[float(i), float(i) * 2] for i in mine]).reshape(len(mine), 2)
+        full = gather_subject_rows(rows, n_subjects)
+        assert torch.equal(full, torch.tensor([[float(i), float(i) * 2] for i in range(n_subjects)]))
+        t = max_over_ranks(1.0 + rank)
+        assert t == float(world)
+        if rank == 0:
+            out.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == "ok"
