@@ -30,7 +30,7 @@ BATCH = 64
 WORKLOAD = "roi_pool_aal3like_170labels_batch64_1x91x109x91_f32"
 # dram__bytes_read.sum + dram__bytes_write.sum of one roi_stream_kernel launch, from the committed
 # ncu --set full capture (profiles/); None until a capture of the current kernel is committed.
-TRAFFIC_NCU = None
+TRAFFIC_NCU = 238.5e6   # profiles/r01_roi_stream_ncu_full.csv: 231.95 MB read + 6.6 MB written per launch
 
 
 def measured_peaks():
