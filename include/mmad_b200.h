@@ -93,6 +93,26 @@ int mmad_roi_pool_mean_backward_f32(mmad_roi_plan* plan, const float* grad_mean_
  * move (volume bytes + run programme + outputs); bench.py's roofline uses it. */
 int64_t mmad_roi_pool_algorithmic_bytes(const mmad_roi_plan* plan, int64_t n_vols);
 
+/* ------------------------------------------------------------------ */
+/* Part 2: Conv3d / BatchNorm3d / ReLU stacks (NDHWC bf16 activations)  */
+/* ------------------------------------------------------------------ */
+
+/* y = conv3d(x, w): cubic kernel k, same stride / padding / dilation on the
+ * three axes, no bias (resnet.py:14-23, :126-132, :188-194 all use
+ * bias=False).  x: (N,D,H,W,Cin) bf16, w: [Cout][k*k*k][Cin] bf16 (tap index
+ * = (kd*k + kh)*k + kw), y: (N,Do,Ho,Wo,Cout) bf16, all device, 16-byte
+ * aligned.  Cin % 64 == 0; Cout in {64,128,256} or a multiple of 256.
+ * If stats_partials != NULL it receives, per CTA, the per-channel sum and sum
+ * of squares of the stored outputs: float[mmad_conv3d_stats_partials(...)]
+ * [Cout][2] (inputs of mmad_bn_finalize).  Implicit GEMM on tcgen05/TMEM with
+ * TMA-staged operands; dgrad of a stride-1 convolution is the same call on the
+ * flipped / transposed weights (mmad_conv3d_prep_weights). */
+int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_partials,
+                         int N, int D, int H, int W, int Cin, int Cout,
+                         int k, int stride, int pad, int dil, void* stream);
+int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout,
+                               int k, int stride, int pad, int dil);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,11 @@ def load() -> ctypes.CDLL:
                                             POINTER(c_int64), POINTER(c_int32)]
     lib.mmad_roi_plan_binding.argtypes = [P, c_int64, c_int32, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                           P, P, P, P, P, P, P]
+    I = ctypes.c_int
+    lib.mmad_conv3d_fwd_bf16.argtypes = [P, P, P, P] + [I] * 10 + [P]
+    lib.mmad_conv3d_fwd_bf16.restype = I
+    lib.mmad_conv3d_stats_partials.argtypes = [I] * 9
+    lib.mmad_conv3d_stats_partials.restype = I
     for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",
                  "mmad_roi_plan_counts_dev", "mmad_roi_pool_f32", "mmad_roi_pool_host_f32",
                  "mmad_roi_pool_mean_backward_f32", "mmad_roi_plan_programme", "mmad_roi_plan_binding"):

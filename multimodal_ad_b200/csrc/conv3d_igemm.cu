@@ -1,0 +1,365 @@
+// Conv3d as an implicit GEMM on tcgen05 / TMEM, operands staged by TMA (sm_100a).
+// Replaces torch.nn.Conv3d of /root/reference/models/resnet.py:14-23 (conv3x3x3, dilated), :126-132 (stem, via
+// im2col), :188-194 (1x1x1 downsample) behind include/mmad_b200.h part 2.  The same kernel computes dgrad of
+// unit-stride convolutions when given the flipped / transposed weights.
+//
+//   activations  NDHWC bf16           weights  [Cout][taps][Cin] bf16           output  NDHWC bf16
+//   GEMM view:   M = output voxels (128 per tile: a tw x th x td box), N = Cout tile (BN = 64/128/256),
+//                K = taps x Cin, walked in slices of 64 channels (= one 128-byte SWIZZLE_128B row).
+//   K-step:      ONE 5-D TMA box of the input (tap offset, dilation and stride folded into the box origin /
+//                element strides; zero padding = TMA out-of-bounds fill) + ONE 3-D box of the weights,
+//                then 4 x tcgen05.mma (M128 x BN x K16), fp32 accumulators in TMEM.
+//   Warp roles:  warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 epilogue
+//                (tcgen05.ld -> bf16 -> swizzled smem -> TMA store; per-channel sum / sum-of-squares of the stored
+//                bf16 values for the BatchNorm that follows).  Two TMEM accumulator buffers, persistent CTAs.
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace mmad {
+
+struct ConvGeom {
+    int N, D, H, W, Cin;          // input
+    int Do, Ho, Wo, Cout;         // output
+    int kd, kh, kw, stride, pad, dil;
+    int tw, th, td;               // output tile box, tw*th*td == 128, powers of two
+    int lw, lh;                   // log2(tw), log2(th)
+    int tiles_w, tiles_h, tiles_d, m_tiles, n_tiles;
+    int kc;                       // Cin / 64
+    int stages;
+    int nout;                     // epilogue staging buffers (1 or 2)
+};
+
+constexpr int kConvThreads = 256;
+constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
+constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+    constexpr int B_TILE = BN * 128;
+    constexpr int STAGE = kATileBytes + B_TILE;
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulator buffers (128, 256 or 512 columns)
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+    unsigned char* sm = smem_raw + (base - raw);
+    const int S = g.stages;
+    const uint32_t stage0 = base;
+    const uint32_t out0 = base + (uint32_t)S * STAGE;      // nout x 16 KB epilogue staging
+    unsigned char* tail = sm + (size_t)S * STAGE + (size_t)g.nout * kStageOutBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);    // full[S], empty[S], tfull[2], tempty[2]
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);     // [2][Cout] (two row halves)
+    float* st_sq = st_sum + 2 * g.Cout;                           // [2][Cout]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_s), TMEM_COLS);
+    for (int i = threadIdx.x; i < 4 * g.Cout; i += kConvThreads) st_sum[i] = 0.f;   // st_sum and st_sq are contiguous
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    const int total_tiles = g.m_tiles * g.n_tiles;
+    const int taps = g.kd * g.kh * g.kw;
+    const int ksteps = taps * g.kc;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
+                int r = mt;
+                const int wt = r % g.tiles_w; r /= g.tiles_w;
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r % g.tiles_d; r /= g.tiles_d;
+                const int n = r;
+                const int w0 = wt * g.tw * g.stride - g.pad, h0 = ht * g.th * g.stride - g.pad,
+                          d0 = dt * g.td * g.stride - g.pad;
+                int tap = 0;
+                for (int a = 0; a < g.kd; ++a)
+                    for (int b = 0; b < g.kh; ++b)
+                        for (int c = 0; c < g.kw; ++c, ++tap)
+                            for (int cc = 0; cc < g.kc; ++cc) {
+                                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
+                                const uint32_t sa = stage0 + s * STAGE;
+                                tma_load_5d(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
+                                            d0 + a * g.dil, n);
+                                tma_load_3d(sa + kATileBytes, &tmB, full0 + 8 * s, cc * 64, tap, nt * BN);
+                                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                            }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer (one thread) ============================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0, it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < ksteps; ++k) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + s * STAGE;
+                    const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc = umma_desc_sw128(sa + kATileBytes, 16, 1024);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)                   // 4 x K16 inside the 64-wide (128-byte) swizzled row
+                        umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * s);                  // frees the smem slot when these MMAs retire
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================ epilogue: TMEM -> bf16 -> smem -> TMA store (+ BN statistics) ============================
+        const int ew = warp - 4;                                  // == warp % 4: the TMEM lane quarter this warp may read
+        const int et = threadIdx.x - 128;                         // 0..127
+        const int row = ew * 32 + lane;                           // output voxel inside the tile == TMEM lane
+        uint32_t it = 0, nstore = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
+            int r = mt;
+            const int wt = r % g.tiles_w; r /= g.tiles_w;
+            const int ht = r % g.tiles_h; r /= g.tiles_h;
+            const int dt = r % g.tiles_d; r /= g.tiles_d;
+            const int n = r;
+            const int w0 = wt * g.tw, h0 = ht * g.th, d0 = dt * g.td;
+            const int vw = min(g.tw, g.Wo - w0), vh = min(g.th, g.Ho - h0), vd = min(g.td, g.Do - d0);   // valid extent
+
+            mbar_wait(tfull0 + 8 * acc, aph);
+            tc_fence_after();
+            for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
+                const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
+                if (et == 0) {                                    // the store that last used this buffer has finished reading it
+                    if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
+                named_bar_sync(2, 128);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                        const uint32_t p1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                        const uint32_t p2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                        const uint32_t p3 = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                        const uint32_t chunk = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);      // SWIZZLE_128B
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row * 128 + chunk * 16), "r"(p0),
+                                     "r"(p1), "r"(p2), "r"(p3)
+                                     : "memory");
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0) {
+                    tma_store_5d(&tmC, ob, nt * BN + sub * 64, w0, h0, d0, n);
+                    tma_store_commit();
+                }
+                if (stats_partials) {
+                    // thread -> (channel c, row half): sum and sum of squares of the stored bf16 values over valid voxels
+                    const int c = et & 63, hf = et >> 6;
+                    float sum = 0.f, sq = 0.f;
+                    const unsigned char* obp = sm + (ob - base);
+                    for (int rr = hf * 64; rr < hf * 64 + 64; ++rr) {
+                        const int wi = rr & (g.tw - 1), hi = (rr >> g.lw) & (g.th - 1), di = rr >> (g.lw + g.lh);
+                        if (wi < vw && hi < vh && di < vd) {
+                            const uint32_t off = rr * 128 + (((uint32_t)(c >> 3) ^ (uint32_t)(rr & 7)) << 4) + (c & 7) * 2;
+                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(obp + off));
+                            sum += x;
+                            sq += x * x;
+                        }
+                    }
+                    const int ch = nt * BN + sub * 64 + c;
+                    st_sum[hf * g.Cout + ch] += sum;              // single owner thread per entry
+                    st_sq[hf * g.Cout + ch] += sq;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+        if (et == 0) tma_store_wait<0>();
+        if (stats_partials) {
+            named_bar_sync(2, 128);
+            for (int ch = et; ch < g.Cout; ch += 128) {
+                stats_partials[((size_t)blockIdx.x * g.Cout + ch) * 2 + 0] = st_sum[ch] + st_sum[g.Cout + ch];
+                stats_partials[((size_t)blockIdx.x * g.Cout + ch) * 2 + 1] = st_sq[ch] + st_sq[g.Cout + ch];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host
+// ---------------------------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* basep, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(MMAD_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(basep), dims, strides_bytes,
+                     box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MMAD_ECUDA, "cuTensorMapEncodeTiled failed (CUresult " + std::to_string((int)r) + ")");
+    return MMAD_OK;
+}
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// Output tile box tw x th x td = 128 (powers of two) with the least padding waste for this output extent.
+static void pick_tile(int Wo, int Ho, int Do, int stride, int& tw, int& th, int& td) {
+    double best = 1e30;
+    for (int a = 1; a <= 128; a *= 2)
+        for (int b = 1; a * b <= 128; b *= 2) {
+            const int c = 128 / (a * b);
+            if (a * stride > 256 || b * stride > 256 || c * stride > 256) continue;   // TMA box limit
+            const double cover = (double)((Wo + a - 1) / a * a) * ((Ho + b - 1) / b * b) * ((Do + c - 1) / c * c);
+            const double score = cover - 1e-3 * a;               // prefer wide-in-W tiles on ties (longer contiguous rows)
+            if (score < best) { best = score; tw = a; th = b; td = c; }
+        }
+}
+
+static int conv_smem_bytes(int bn, int stages, int nout, int cout) {
+    return 1024 + stages * (kATileBytes + bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
+}
+
+}  // namespace mmad
+
+using namespace mmad;
+
+extern "C" {
+
+// Number of per-CTA statistic partials mmad_conv3d_fwd_bf16 writes for a given problem (== grid size).
+int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout, int k, int stride, int pad, int dil) {
+    const int Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1, Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1,
+              Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    int tw = 0, th = 0, td = 0;
+    pick_tile(Wo, Ho, Do, stride, tw, th, td);
+    const int bn = std::min(256, Cout);
+    const long long tiles = (long long)N * ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((Do + td - 1) / td) * (Cout / bn);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::min<long long>(tiles, sms);
+}
+
+int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W,
+                         int Cin, int Cout, int k, int stride, int pad, int dil, void* stream) {
+    MMAD_CHECK_ARG(x && w && y, "conv3d_fwd: null pointer");
+    MMAD_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: empty input");
+    MMAD_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv3d_fwd: Cin must be a multiple of 64");
+    MMAD_CHECK_ARG(Cout % 64 == 0 && Cout >= 64 && (Cout <= 256 || Cout % 256 == 0) && (Cout == 64 || Cout % 128 == 0) &&
+                       Cout <= 2048,
+                   "conv3d_fwd: Cout must be 64, 128, 256 or a multiple of 256 (<= 2048)");
+    MMAD_CHECK_ARG(k >= 1 && k <= 7 && stride >= 1 && stride <= 2 && dil >= 1 && pad >= 0, "conv3d_fwd: bad kernel geometry");
+    MMAD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0,
+                   "conv3d_fwd: pointers must be 16-byte aligned");
+    ConvGeom g = {};
+    g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
+    g.kd = g.kh = g.kw = k; g.stride = stride; g.pad = pad; g.dil = dil;
+    g.Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    MMAD_CHECK_ARG(g.Do > 0 && g.Ho > 0 && g.Wo > 0, "conv3d_fwd: empty output");
+    pick_tile(g.Wo, g.Ho, g.Do, stride, g.tw, g.th, g.td);
+    g.lw = ilog2(g.tw); g.lh = ilog2(g.th);
+    g.tiles_w = (g.Wo + g.tw - 1) / g.tw; g.tiles_h = (g.Ho + g.th - 1) / g.th; g.tiles_d = (g.Do + g.td - 1) / g.td;
+    g.m_tiles = N * g.tiles_w * g.tiles_h * g.tiles_d;
+    const int bn = std::min(256, Cout);
+    g.n_tiles = Cout / bn;
+    g.kc = Cin / 64;
+    g.nout = bn == 256 ? 1 : 2;
+    int stages = 8;
+    while (stages > 2 && conv_smem_bytes(bn, stages, g.nout, Cout) > 227 * 1024) --stages;
+    g.stages = stages;
+    const int smem = conv_smem_bytes(bn, stages, g.nout, Cout);
+
+    CUtensorMap tmA, tmB, tmC;
+    {
+        const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+        const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};
+        const uint32_t box[5] = {64, (uint32_t)(g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), 1};
+        const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
+        int rc = make_tmap_bf16(&tmA, x, 5, dims, str, box, es);
+        if (rc) return rc;
+    }
+    {
+        const int taps = k * k * k;
+        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
+        const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2};
+        const uint32_t box[3] = {64, 1, (uint32_t)bn};
+        const uint32_t es[3] = {1, 1, 1};
+        int rc = make_tmap_bf16(&tmB, w, 3, dims, str, box, es);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)N};
+        const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)g.Wo * Cout * 2, (uint64_t)g.Ho * g.Wo * Cout * 2,
+                                 (uint64_t)g.Do * g.Ho * g.Wo * Cout * 2};
+        const uint32_t box[5] = {64, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.td, 1};
+        const uint32_t es[5] = {1, 1, 1, 1, 1};
+        int rc = make_tmap_bf16(&tmC, y, 5, dims, str, box, es);
+        if (rc) return rc;
+    }
+    int dev = 0, sms = 148;
+    MMAD_CUDA(cudaGetDevice(&dev));
+    MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MMAD_CONV_LAUNCH(BNV)                                                                                               \
+    do {                                                                                                                    \
+        static bool attr_done = false;                                                                                      \
+        if (!attr_done) {                                                                                                   \
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            attr_done = true;                                                                                               \
+        }                                                                                                                   \
+        conv3d_igemm_kernel<BNV><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);                       \
+    } while (0)
+    if (bn == 64) MMAD_CONV_LAUNCH(64);
+    else if (bn == 128) MMAD_CONV_LAUNCH(128);
+    else MMAD_CONV_LAUNCH(256);
+#undef MMAD_CONV_LAUNCH
+    MMAD_CUDA(cudaGetLastError());
+    count_launch();
+    return MMAD_OK;
+}
+
+}  // extern "C"
