@@ -113,6 +113,80 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
 int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout,
                                int k, int stride, int pad, int dil);
 
+/* Weight gradient of the same convolution (the dW half of Conv3d.backward):
+ * partials[split][Cout][taps][Cin] fp32 = split-K partial sums over output
+ * voxels of dy[v][co] * x[v*stride + tap*dil - pad][ci]; x (N,D,H,W,Cin) and
+ * dy (N,Do,Ho,Wo,Cout) bf16 NDHWC.  mmad_conv3d_wgrad_workspace returns the
+ * fp32 element count of `partials` (and the split count); mmad_wgrad_reduce
+ * sums the splits into torch's (Cout, Cin, k,k,k) fp32 layout.
+ * Cin in {64} or a multiple of 128; Cout in {64,128} or a multiple of 256. */
+int64_t mmad_conv3d_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cout,
+                                    int k, int stride, int pad, int dil, int* nsplit_out);
+int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials,
+                           int N, int D, int H, int W, int Cin, int Cout,
+                           int k, int stride, int pad, int dil, void* stream);
+int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw,
+                      int Cout, int Cin, int taps, void* stream);
+
+/* torch weights (Cout, Cin, k,k,k) fp32 -> forward layout [Cout][taps][Cin]
+ * bf16 (w_fwd) and dgrad layout [Cin][taps reversed][Cout] bf16 (w_dgrad);
+ * either output may be NULL. */
+int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad,
+                             int Cout, int Cin, int taps, void* stream);
+
+/* Stem (resnet.py:126-132: Conv3d(1, 64, 7, stride 2, pad 3)) as im2col + GEMM:
+ * x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, column (kd*k+kh)*k+kw,
+ * zero padded to Kpad (384); the GEMM is mmad_conv3d_fwd_bf16 with k = 1 on the
+ * (1,1,1,rows,Kpad) view, its wgrad mmad_conv3d_wgrad_bf16 on the same view. */
+int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W,
+                     int k, int stride, int pad, int Kpad, void* stream);
+int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream);
+int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream);
+
+/* BatchNorm3d (resnet.py:46,49,134), training statistics from the conv
+ * epilogue's partials: mean, invstd, scale = gamma*invstd, shift = beta -
+ * mean*scale (all float[C]); running_mean/var updated like nn.BatchNorm3d
+ * (momentum, unbiased variance) unless NULL.  `count` = voxels per channel. */
+int mmad_bn_finalize(const float* partials, int nparts, int C, double count,
+                     const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* eval mode: the same four vectors from the running statistics */
+int mmad_bn_eval_params(int C, const float* gamma, const float* beta,
+                        const float* running_mean, const float* running_var, float eps,
+                        float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* y = act(x*scale + shift [+ res*rscale + rshift | + res]); x, res: rows x C
+ * bf16; relu != 0 applies ReLU (resnet.py:57-67); out_bf16 and/or out_f32. */
+int mmad_bn_apply(const void* x, const float* scale, const float* shift,
+                  const void* res, const float* rscale, const float* rshift, int relu,
+                  void* out_bf16, float* out_f32, int64_t rows, int C, void* stream);
+/* Backward of ReLU + BatchNorm3d.  reduce: g = (dy [+ dy2]) * (mask > 0),
+ * written to g_out (bf16, may be NULL) with per-block partial sums of g and
+ * g*xhat; finalize: dgamma, dbeta and the per-channel means mg, mgx; apply:
+ * dx = gamma*invstd*(g - mg - xhat*mgx).  dy is bf16 (dy_bf16) or fp32
+ * (dy_f32), both rows x C in NDHWC order; mask NULL = no ReLU. */
+int mmad_bn_bwd_partials(int64_t rows);
+int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2,
+                       const void* mask, const void* x, const float* mean, const float* invstd,
+                       void* g_out, float* partials, int64_t rows, int C, void* stream);
+int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
+                         float* dgamma, float* dbeta, float* mg, float* mgx, void* stream);
+int mmad_bn_bwd_apply(const void* g, const void* x, const float* mean, const float* invstd,
+                      const float* gamma, const float* mg, const float* mgx,
+                      void* dx, int64_t rows, int C, void* stream);
+
+/* MaxPool3d(kernel 3, stride 2, padding 1) (resnet.py:136), NDHWC bf16; idx
+ * keeps the winning tap per element (uint8, rows x C) for the backward. */
+int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
+int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream);
+
+/* y[2*o] = x[o], zero elsewhere: dgrad of a stride-2 convolution is the
+ * unit-stride convolution of this with the flipped kernel. */
+int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx,
+                        int Dy, int Hy, int Wy, int C, void* stream);
+/* (N, C, S) fp32 [torch NCDHW] -> (N, S, C) bf16 [NDHWC] */
+int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

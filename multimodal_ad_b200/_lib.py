@@ -60,6 +60,31 @@ def load() -> ctypes.CDLL:
     lib.mmad_conv3d_fwd_bf16.restype = I
     lib.mmad_conv3d_stats_partials.argtypes = [I] * 9
     lib.mmad_conv3d_stats_partials.restype = I
+    F, D_, L = ctypes.c_float, ctypes.c_double, c_int64
+    sigs = {
+        "mmad_conv3d_wgrad_bf16": [P, P, P] + [I] * 10 + [P],
+        "mmad_wgrad_reduce": [P, I, P, I, I, I, P],
+        "mmad_conv3d_prep_weights": [P, P, P, I, I, I, P],
+        "mmad_stem_im2col": [P, P] + [I] * 8 + [P],
+        "mmad_stem_prep_weights": [P, P, I, I, I, P],
+        "mmad_stem_unpad_wgrad": [P, P, I, I, I, P],
+        "mmad_bn_finalize": [P, I, I, D_, P, P, F, F, P, P, P, P, P, P, P],
+        "mmad_bn_eval_params": [I, P, P, P, P, F, P, P, P, P, P],
+        "mmad_bn_apply": [P, P, P, P, P, P, I, P, P, L, I, P],
+        "mmad_bn_bwd_partials": [L],
+        "mmad_bn_bwd_reduce": [P, P, P, P, P, P, P, P, P, L, I, P],
+        "mmad_bn_bwd_finalize": [P, I, I, D_, P, P, P, P, P],
+        "mmad_bn_bwd_apply": [P, P, P, P, P, P, P, P, L, I, P],
+        "mmad_maxpool3d_fwd": [P, P, P, I, I, I, I, I, P],
+        "mmad_maxpool3d_bwd": [P, P, P, I, I, I, I, I, P],
+        "mmad_upsample_zero2": [P, P] + [I] * 8 + [P],
+        "mmad_ncs_f32_to_nsc_bf16": [P, P, I, I, L, P],
+    }
+    for name, args in sigs.items():
+        getattr(lib, name).argtypes = args
+        getattr(lib, name).restype = I
+    lib.mmad_conv3d_wgrad_workspace.argtypes = [I] * 10 + [POINTER(ctypes.c_int)]
+    lib.mmad_conv3d_wgrad_workspace.restype = c_int64
     for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",
                  "mmad_roi_plan_counts_dev", "mmad_roi_pool_f32", "mmad_roi_pool_host_f32",
                  "mmad_roi_pool_mean_backward_f32", "mmad_roi_plan_programme", "mmad_roi_plan_binding"):

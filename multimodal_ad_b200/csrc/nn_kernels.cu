@@ -1,0 +1,492 @@
+// Bandwidth-bound companions of the Conv3d implicit GEMM (sm_100a): weight re-layout, stem im2col, BatchNorm3d
+// statistics / apply / backward, ReLU, residual add, MaxPool3d, zero-insertion upsampling, layout conversion.
+// Replaces nn.BatchNorm3d / nn.ReLU / nn.MaxPool3d / `out += residual` of /root/reference/models/resnet.py:46-69,
+// :134-136, :204-213 (forward and backward).  All activations are NDHWC bf16 with C % 8 == 0; every kernel moves
+// 16-byte vectors (8 channels) per thread.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace mmad {
+
+struct bf16x8 { uint4 v; };
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+static inline int grid_for(long long work, int block, int cap) { return (int)std::max<long long>(1, std::min<long long>((work + block - 1) / block, cap)); }
+
+// ---- weights: torch (Cout, Cin, k,k,k) fp32 -> forward layout [Cout][taps][Cin] bf16 and dgrad layout [Cin][taps][Cout] bf16
+//      (taps reversed: correlation with the flipped kernel).  Cin may be padded up to cin_pad with zeros (stem: 1 -> K=384).
+__global__ void prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wt,
+                                    int Cout, int Cin, int taps) {
+    const long long total = (long long)Cout * Cin * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % taps);
+        const int ci = (int)((i / taps) % Cin);
+        const int co = (int)(i / ((long long)taps * Cin));
+        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+        if (wf) wf[((long long)co * taps + tap) * Cin + ci] = v;
+        if (wt) wt[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = v;
+    }
+}
+// stem weights (Cout, 1, 7,7,7) fp32 -> [Cout][Kpad] bf16 (a 1x1x1 conv over the im2col matrix), zero padded
+__global__ void prep_stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int K, int Kpad) {
+    const int total = Cout * Kpad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i % Kpad, co = i / Kpad;
+        wf[i] = __float2bfloat16_rn(k < K ? w[co * K + k] : 0.f);
+    }
+}
+// dW of the stem: [Cout][1][Kpad] fp32 (wgrad output layout with taps = 1, Cin = Kpad) -> (Cout, 1, 7,7,7) fp32
+__global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int K, int Kpad) {
+    const int total = Cout * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
+}
+
+// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, k = 7, stride 2, pad 3, column = (kd*7+kh)*7+kw
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
+                                                          int H, int W, int Do, int Ho, int Wo, int k, int stride, int pad,
+                                                          int Kpad) {
+    // one warp per output voxel row; lane l writes columns l*8 .. l*8+7 (16 bytes) for 48 lanes' worth -> loop
+    const long long rows = (long long)N * Do * Ho * Wo;
+    const int K = k * k * k;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < rows; r += nwarps) {
+        long long t = r;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho); t /= Ho;
+        const int od = (int)(t % Do); t /= Do;
+        const int n = (int)t;
+        const float* xn = x + (long long)n * D * H * W;
+        for (int c0 = lane * 8; c0 < Kpad; c0 += 256) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                float v = 0.f;
+                if (c < K) {
+                    const int kw = c % k, kh = (c / k) % k, kd = c / (k * k);
+                    const int iw = ow * stride + kw - pad, ih = oh * stride + kh - pad, id = od * stride + kd - pad;
+                    if (iw >= 0 && iw < W && ih >= 0 && ih < H && id >= 0 && id < D) v = __ldg(xn + ((long long)id * H + ih) * W + iw);
+                }
+                f[j] = v;
+            }
+            *reinterpret_cast<uint4*>(col + r * Kpad + c0) = pack8(f);
+        }
+    }
+}
+
+// ---- BatchNorm statistics: per-CTA partial (sum, sum of squares) -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale;
+//      running statistics updated like nn.BatchNorm3d (momentum, unbiased variance).  One thread per channel, double accumulation.
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) { s += partials[((size_t)p * C + c) * 2]; q += partials[((size_t)p * C + c) * 2 + 1]; }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    mean_out[c] = (float)mean; invstd_out[c] = invstd; scale_out[c] = sc; shift_out[c] = beta[c] - (float)mean * sc;
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+// eval mode: scale / shift from the running statistics
+__global__ void bn_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ running_mean,
+                               const float* __restrict__ running_var, float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                               float* __restrict__ scale_out, float* __restrict__ shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = rsqrtf(running_var[c] + eps);
+    const float sc = gamma[c] * invstd;
+    mean_out[c] = running_mean[c]; invstd_out[c] = invstd; scale_out[c] = sc; shift_out[c] = beta[c] - running_mean[c] * sc;
+}
+
+// ---- y = act(x*scale + shift  [+ res*rscale + rshift | + res]);  x, res bf16 NDHWC;  out bf16 and/or fp32 (same NDHWC order)
+template <bool RELU>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       const uint4* __restrict__ res, const float* __restrict__ rscale,
+                                                       const float* __restrict__ rshift, uint4* __restrict__ out_bf16,
+                                                       float4* __restrict__ out_f32, long long nvec, int C) {
+    const int cv = C >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        float f[8];
+        unpack8(x[i], f);
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(shift + c0), b1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+        if (res) {
+            float r[8];
+            unpack8(res[i], r);
+            if (rscale) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], rscale[c0 + j], rshift[c0 + j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += r[j];
+            }
+        }
+        if (RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (out_bf16) out_bf16[i] = pack8(f);
+        if (out_f32) { out_f32[2 * i] = make_float4(f[0], f[1], f[2], f[3]); out_f32[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]); }
+    }
+}
+
+// ---- BatchNorm / ReLU backward, pass 1: g = (dy [+ dy2]) * (mask > 0) ; per-channel partial sums of g and g*xhat.
+//      dy may be bf16 (dy_bf16) or fp32 (dy_f32, same NDHWC order).  Writes g (bf16) when g_out != NULL.
+//      Block = 256 threads = 8 row-lanes x 32 channel-vectors... generic: thread owns channel vector (i % cv); block partials in smem.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ dy_bf16, const float4* __restrict__ dy_f32,
+                                                            const uint4* __restrict__ dy2, const uint4* __restrict__ mask,
+                                                            const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, uint4* __restrict__ g_out,
+                                                            float* __restrict__ partials, long long rows, int C) {
+    // each block walks rows [r0, r1); thread t handles channel vector (t % cv) of rows r0 + t / cv, + 256/cv, ...
+    extern __shared__ float red[];   // [256][16]
+    const int cv = C >> 3;           // vectors per row: 8, 16, 32 or 64
+    const int rpb = 256 / cv;        // rows per block step (>= 4)
+    const int tv = threadIdx.x % cv, tr = threadIdx.x / cv;
+    const int c0 = tv * 8;
+    float mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
+    for (long long r = r0 + tr; r < r1; r += rpb) {
+        const long long i = r * cv + tv;
+        float g[8];
+        if (dy_bf16) unpack8(dy_bf16[i], g);
+        else { const float4 a = dy_f32[2 * i], b = dy_f32[2 * i + 1]; g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w; }
+        if (dy2) { float h[8]; unpack8(dy2[i], h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += h[j]; }
+        if (mask) { float m[8]; unpack8(mask[i], m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
+        float xv[8];
+        unpack8(x[i], xv);
+        if (g_out) {
+            const uint4 gp = pack8(g);
+            g_out[i] = gp;
+            unpack8(gp, g);          // statistics of the ROUNDED g, the values pass 2 will read
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sg[j] += g[j]; sgx[j] += g[j] * (xv[j] - mu[j]) * is[j]; }
+    }
+    float* my = red + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[j] = sg[j]; my[8 + j] = sgx[j]; }
+    __syncthreads();
+    if (threadIdx.x < cv) {          // thread tv sums the rpb row-lanes of its channel vector
+        float a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = 0.f;
+        for (int q = 0; q < rpb; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] += red[(q * cv + threadIdx.x) * 16 + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            partials[((size_t)blockIdx.x * C + c0 + j) * 2] = a[j];
+            partials[((size_t)blockIdx.x * C + c0 + j) * 2 + 1] = a[8 + j];
+        }
+    }
+}
+// sums the block partials; writes dgamma, dbeta and the two per-channel means the apply pass needs
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ mg, float* __restrict__ mgx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) { s += partials[((size_t)p * C + c) * 2]; q += partials[((size_t)p * C + c) * 2 + 1]; }
+    if (dbeta) dbeta[c] = (float)s;
+    if (dgamma) dgamma[c] = (float)q;
+    mg[c] = (float)(s / count);
+    mgx[c] = (float)(q / count);
+}
+// pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat))      (eval mode: dx = gamma*invstd*g with mg = mgx = 0)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mg, const float* __restrict__ mgx,
+                                                           uint4* __restrict__ dx, long long nvec, int C) {
+    const int cv = C >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * 8;
+        float gv[8], xv[8], o[8];
+        unpack8(g[i], gv);
+        unpack8(x[i], xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float is = invstd[c0 + j];
+            const float xh = (xv[j] - mean[c0 + j]) * is;
+            o[j] = gamma[c0 + j] * is * (gv[j] - mg[c0 + j] - xh * mgx[c0 + j]);
+        }
+        dx[i] = pack8(o);
+    }
+}
+
+// ---- MaxPool3d k3 s2 p1 (resnet.py:136), NDHWC bf16; the winning tap index (0..26, first maximum in (kd,kh,kw) order) is kept
+//      for the backward pass.
+__global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int N,
+                                                            int D, int H, int W, int C, int Do, int Ho, int Wo) {
+    const int cv = C >> 3;
+    const long long total = (long long)N * Do * Ho * Wo * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int v = (int)(t % cv); t /= cv;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho); t /= Ho;
+        const int od = (int)(t % Do); t /= Do;
+        const int n = (int)t;
+        float best[8];
+        int bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+        int tap = 0;
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw, ++tap) {
+                    const int id = od * 2 + kd - 1, ih = oh * 2 + kh - 1, iw = ow * 2 + kw - 1;
+                    if (id < 0 || id >= D || ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+                    float f[8];
+                    unpack8(x[((((long long)n * D + id) * H + ih) * W + iw) * cv + v], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (f[j] > best[j]) { best[j] = f[j]; bi[j] = tap; }
+                }
+        y[i] = pack8(best);
+        uint2 p;
+        p.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+        p.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+        idx[i] = p;
+    }
+}
+// gather form of the backward: every input voxel collects from the (<= 8) windows that contain it and picked it
+__global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
+                                                            int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
+    const int cv = C >> 3;
+    const long long total = (long long)N * D * H * W * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int v = (int)(t % cv); t /= cv;
+        const int iw = (int)(t % W); t /= W;
+        const int ih = (int)(t % H); t /= H;
+        const int id = (int)(t % D); t /= D;
+        const int n = (int)t;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int kd = 0; kd < 3; ++kd) {
+            const int od2 = id + 1 - kd;
+            if (od2 < 0 || (od2 & 1) || (od2 >> 1) >= Do) continue;
+            for (int kh = 0; kh < 3; ++kh) {
+                const int oh2 = ih + 1 - kh;
+                if (oh2 < 0 || (oh2 & 1) || (oh2 >> 1) >= Ho) continue;
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ow2 = iw + 1 - kw;
+                    if (ow2 < 0 || (ow2 & 1) || (ow2 >> 1) >= Wo) continue;
+                    const long long o = ((((long long)n * Do + (od2 >> 1)) * Ho + (oh2 >> 1)) * Wo + (ow2 >> 1)) * cv + v;
+                    const uint2 p = idx[o];
+                    const int tap = (kd * 3 + kh) * 3 + kw;
+                    float f[8];
+                    unpack8(dy[o], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int w = (int)(((j < 4 ? p.x : p.y) >> (8 * (j & 3))) & 0xffu);
+                        if (w == tap) acc[j] += f[j];
+                    }
+                }
+            }
+        }
+        dx[i] = pack8(acc);
+    }
+}
+
+// ---- zero insertion: y (N, Dy,Hy,Wy, C), y[2*o] = x[o], zero elsewhere (dgrad of a stride-2 convolution = unit-stride
+//      convolution of the zero-upsampled gradient with the flipped kernel)
+__global__ void __launch_bounds__(256) upsample_zero2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int Dx, int Hx, int Wx,
+                                                             int Dy, int Hy, int Wy, int C) {
+    const int cv = C >> 3;
+    const long long total = (long long)N * Dy * Hy * Wy * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int v = (int)(t % cv); t /= cv;
+        const int w = (int)(t % Wy); t /= Wy;
+        const int h = (int)(t % Hy); t /= Hy;
+        const int d = (int)(t % Dy); t /= Dy;
+        const int n = (int)t;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (!((w | h | d) & 1) && (w >> 1) < Wx && (h >> 1) < Hx && (d >> 1) < Dx)
+            o = x[((((long long)n * Dx + (d >> 1)) * Hx + (h >> 1)) * Wx + (w >> 1)) * cv + v];
+        y[i] = o;
+    }
+}
+
+// ---- layout: (N, C, S) fp32 (torch NCDHW, S = D*H*W) -> (N, S, C) bf16, 32x32 shared-memory transpose
+__global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, long long S) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long s0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long long s = s0 + tx;
+        tile[j][tx] = (c < C && s < S) ? x[((long long)n * C + c) * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const long long s = s0 + j;
+        const int c = c0 + tx;
+        if (c < C && s < S) y[((long long)n * S + s) * C + c] = __float2bfloat16_rn(tile[tx][j]);
+    }
+}
+
+// ---- wgrad epilogue: sum the split-K partials [nsplit][Cout][taps][Cin] fp32 -> torch layout (Cout, Cin, taps) fp32
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin, int taps) {
+    const long long total = (long long)Cout * Cin * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const int tap = (int)((i / Cin) % taps);
+        const int co = (int)(i / ((long long)Cin * taps));
+        float s = 0.f;
+        for (int p = 0; p < nsplit; ++p) s += part[(size_t)p * total + i];
+        dw[((long long)co * Cin + ci) * taps + tap] = s;
+    }
+}
+
+}  // namespace mmad
+
+using namespace mmad;
+#define ST ((cudaStream_t)stream)
+#define LAUNCH_OK() do { MMAD_CUDA(cudaGetLastError()); count_launch(); return MMAD_OK; } while (0)
+
+extern "C" {
+
+int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream) {
+    MMAD_CHECK_ARG(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && taps > 0, "prep_weights: bad argument");
+    const long long total = (long long)Cout * Cin * taps;
+    prep_weights_kernel<<<grid_for(total, 256, 2048), 256, 0, ST>>>(w, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, taps);
+    LAUNCH_OK();
+}
+int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream) {
+    MMAD_CHECK_ARG(w && w_fwd && K <= Kpad && Kpad % 64 == 0, "stem_prep_weights: bad argument");
+    prep_stem_weights_kernel<<<grid_for((long long)Cout * Kpad, 256, 1024), 256, 0, ST>>>(w, (__nv_bfloat16*)w_fwd, Cout, K, Kpad);
+    LAUNCH_OK();
+}
+int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream) {
+    MMAD_CHECK_ARG(dw_padded && dw, "stem_unpad_wgrad: null pointer");
+    unpad_stem_wgrad_kernel<<<grid_for((long long)Cout * K, 256, 1024), 256, 0, ST>>>(dw_padded, dw, Cout, K, Kpad);
+    LAUNCH_OK();
+}
+int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int k, int stride, int pad, int Kpad, void* stream) {
+    MMAD_CHECK_ARG(x && col && Kpad % 8 == 0 && k * k * k <= Kpad, "stem_im2col: bad argument");
+    const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    const long long rows = (long long)N * Do * Ho * Wo;
+    im2col_stem_kernel<<<grid_for(rows * 32, 256, 148 * 16), 256, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, k, stride, pad, Kpad);
+    LAUNCH_OK();
+}
+int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                     float* shift, void* stream) {
+    MMAD_CHECK_ARG(partials && gamma && beta && mean && invstd && scale && shift && C > 0 && count > 0, "bn_finalize: bad argument");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partials, nparts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+                                                       mean, invstd, scale, shift);
+    LAUNCH_OK();
+}
+int mmad_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                        float* mean, float* invstd, float* scale, float* shift, void* stream) {
+    MMAD_CHECK_ARG(gamma && beta && running_mean && running_var && mean && invstd && scale && shift, "bn_eval_params: null pointer");
+    bn_eval_kernel<<<(C + 127) / 128, 128, 0, ST>>>(C, gamma, beta, running_mean, running_var, eps, mean, invstd, scale, shift);
+    LAUNCH_OK();
+}
+int mmad_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale, const float* rshift,
+                  int relu, void* out_bf16, float* out_f32, int64_t rows, int C, void* stream) {
+    MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
+    const long long nvec = rows * (C / 8);
+    const int grid = grid_for(nvec, 256, 148 * 16);
+    if (relu) bn_apply_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
+    else bn_apply_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
+    LAUNCH_OK();
+}
+// number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
+int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 4)); }
+int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2, const void* mask, const void* x, const float* mean,
+                       const float* invstd, void* g_out, float* partials, int64_t rows, int C, void* stream) {
+    MMAD_CHECK_ARG((dy_bf16 || dy_f32) && x && mean && invstd && partials && rows > 0, "bn_bwd_reduce: bad argument");
+    MMAD_CHECK_ARG(C % 64 == 0 && C <= 512, "bn_bwd_reduce: C must be 64, 128, 256 or 512");
+    const int grid = mmad_bn_bwd_partials(rows);
+    bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), ST>>>((const uint4*)dy_bf16, (const float4*)dy_f32, (const uint4*)dy2,
+                                                                     (const uint4*)mask, (const uint4*)x, mean, invstd, (uint4*)g_out,
+                                                                     partials, rows, C);
+    LAUNCH_OK();
+}
+int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count, float* dgamma, float* dbeta, float* mg, float* mgx,
+                         void* stream) {
+    MMAD_CHECK_ARG(partials && mg && mgx && C > 0, "bn_bwd_finalize: bad argument");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partials, nparts, C, count, dgamma, dbeta, mg, mgx);
+    LAUNCH_OK();
+}
+int mmad_bn_bwd_apply(const void* g, const void* x, const float* mean, const float* invstd, const float* gamma, const float* mg,
+                      const float* mgx, void* dx, int64_t rows, int C, void* stream) {
+    MMAD_CHECK_ARG(g && x && mean && invstd && gamma && mg && mgx && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
+    const long long nvec = rows * (C / 8);
+    bn_bwd_apply_kernel<<<grid_for(nvec, 256, 148 * 16), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, mean, invstd, gamma, mg, mgx, (uint4*)dx, nvec, C);
+    LAUNCH_OK();
+}
+int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {
+    MMAD_CHECK_ARG(x && y && idx && C % 8 == 0, "maxpool3d_fwd: bad argument");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * Do * Ho * Wo * (C / 8);
+    maxpool3d_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)x, (uint4*)y, (uint2*)idx, N, D, H, W, C, Do, Ho, Wo);
+    LAUNCH_OK();
+}
+int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream) {
+    MMAD_CHECK_ARG(dy && dx && idx && C % 8 == 0, "maxpool3d_bwd: bad argument");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * D * H * W * (C / 8);
+    maxpool3d_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo);
+    LAUNCH_OK();
+}
+int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx, int Dy, int Hy, int Wy, int C, void* stream) {
+    MMAD_CHECK_ARG(x && y && C % 8 == 0, "upsample_zero2: bad argument");
+    const long long total = (long long)N * Dy * Hy * Wy * (C / 8);
+    upsample_zero2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)x, (uint4*)y, N, Dx, Hx, Wx, Dy, Hy, Wy, C);
+    LAUNCH_OK();
+}
+int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, void* stream) {
+    MMAD_CHECK_ARG(x && y && N > 0 && C > 0 && S > 0, "ncs_f32_to_nsc_bf16: bad argument");
+    dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+    ncs_f32_to_nsc_bf16_kernel<<<grid, 256, 0, ST>>>(x, (__nv_bfloat16*)y, C, S);
+    LAUNCH_OK();
+}
+int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
+    MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
+    const long long total = (long long)Cout * Cin * taps;
+    wgrad_reduce_kernel<<<grid_for(total, 256, 2048), 256, 0, ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    LAUNCH_OK();
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+"""3-D ResNet image branch — drop-in for /root/reference/models/resnet.py.
+
+Same names (`conv3x3x3`, `BasicBlock`, `Bottleneck`, `ResNet`, `resnet10` … `resnet200`), same constructor
+arguments, same parameter / buffer names (so `state_dict()`s are interchangeable, resnet.py:112-202), same
+initialisation (resnet.py:171-176).  `ResNet.forward` (resnet.py:204-215) runs the backbone
+(conv1 → bn1 → relu → maxpool → layer1..4) on the CUDA library behind include/mmad_b200.h — implicit-GEMM Conv3d on
+tcgen05/TMEM (csrc/conv3d_igemm.cu, csrc/conv3d_wgrad.cu) and the bandwidth kernels of csrc/nn_kernels.cu — inside ONE
+`torch.autograd.Function`; `conv_seg` (the head the training scripts replace, train_ResNet3D.py:66-71) stays a normal
+torch module applied to the backbone's output.
+
+The nn.Conv3d / nn.BatchNorm3d objects are parameter containers only: their own forward is never called.  Activations
+live as NDHWC bf16 between kernels; convolutions accumulate in fp32.  There is no CPU / cuDNN fallback: a CPU tensor, a
+non-BasicBlock network or shortcut type 'A' raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+
+__all__ = ['ResNet', 'resnet10', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152', 'resnet200']
+
+STEM_KPAD = 384      # 7*7*7 = 343 im2col columns, zero padded to a multiple of 64
+
+
+def conv3x3x3(in_planes, out_planes, stride=1, dilation=1):
+    # resnet.py:14-23
+    return nn.Conv3d(in_planes, out_planes, kernel_size=3, dilation=dilation, stride=stride, padding=dilation, bias=False)
+
+
+def downsample_basic_block(x, planes, stride, no_cuda=False):
+    # resnet.py:26-37 (shortcut type 'A'); kept for API parity, not on the accelerated path
+    out = F.avg_pool3d(x, kernel_size=1, stride=stride)
+    zero_pads = torch.zeros(out.size(0), planes - out.size(1), out.size(2), out.size(3), out.size(4),
+                            dtype=out.dtype, device=out.device)
+    return torch.cat([out, zero_pads], dim=1)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None):
+        super().__init__()
+        self.conv1 = conv3x3x3(inplanes, planes, stride=stride, dilation=dilation)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = conv3x3x3(planes, planes, dilation=dilation)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.downsample = downsample
+        self.stride = stride
+        self.dilation = dilation
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv3d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm3d(planes)
+        self.conv2 = nn.Conv3d(planes, planes, kernel_size=3, stride=stride, dilation=dilation, padding=dilation, bias=False)
+        self.bn2 = nn.BatchNorm3d(planes)
+        self.conv3 = nn.Conv3d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm3d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+        self.dilation = dilation
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# kernel plumbing
+# ----------------------------------------------------------------------------------------------------------------
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Run:
+    """One forward or backward pass: library handle, stream, allocation helpers, thin kernel wrappers."""
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        self.dev = device
+        self.stream = c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+    def empty(self, shape, dtype=torch.bfloat16):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def chk(self, rc, what):
+        _lib.check(rc, what)
+
+    # y = conv(x, w_fwd) [+ per-CTA BN statistic partials]
+    def conv(self, x, w_fwd, cout, k, stride, pad, dil, want_stats):
+        n, d, h, w, cin = x.shape
+        do = (d + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        ho = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        wo = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        y = self.empty((n, do, ho, wo, cout))
+        part = None
+        if want_stats:
+            npart = self.lib.mmad_conv3d_stats_partials(n, d, h, w, cout, k, stride, pad, dil)
+            part = self.empty((npart, cout, 2), torch.float32)
+        self.chk(self.lib.mmad_conv3d_fwd_bf16(_p(x), _p(w_fwd), _p(y), _p(part), n, d, h, w, cin, cout, k, stride, pad, dil,
+                                               self.stream), "mmad_conv3d_fwd_bf16")
+        return y, part
+
+    def wgrad(self, x, dy, cout, k, stride, pad, dil, out_dw):
+        """out_dw: fp32 tensor in torch layout (Cout, Cin, k,k,k) (or any tensor of Cout*Cin*taps elements)."""
+        n, d, h, w, cin = x.shape
+        nsplit = ctypes.c_int(0)
+        elems = self.lib.mmad_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, pad, dil, ctypes.byref(nsplit))
+        if elems < 0:
+            raise _lib.MmadError("mmad_conv3d_wgrad_workspace: bad geometry")
+        ws = self.empty((elems,), torch.float32)
+        self.chk(self.lib.mmad_conv3d_wgrad_bf16(_p(x), _p(dy), _p(ws), n, d, h, w, cin, cout, k, stride, pad, dil, self.stream),
+                 "mmad_conv3d_wgrad_bf16")
+        self.chk(self.lib.mmad_wgrad_reduce(_p(ws), nsplit.value, _p(out_dw), cout, cin, k * k * k, self.stream), "mmad_wgrad_reduce")
+
+    def prep_weights(self, conv: nn.Conv3d, want_dgrad):
+        cout, cin, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+        taps = k * k * k
+        wf = self.empty((cout, taps, cin))
+        wt = self.empty((cin, taps, cout)) if want_dgrad else None
+        self.chk(self.lib.mmad_conv3d_prep_weights(_p(conv.weight.detach()), _p(wf), _p(wt), cout, cin, taps, self.stream),
+                 "mmad_conv3d_prep_weights")
+        return wf, wt
+
+    def bn_params(self, bn: nn.BatchNorm3d, part, count, training):
+        c = bn.num_features
+        vec = self.empty((4, c), torch.float32)          # mean, invstd, scale, shift
+        g, b = bn.weight.detach(), bn.bias.detach()
+        if training:
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            track = bn.track_running_stats and bn.running_mean is not None
+            self.chk(self.lib.mmad_bn_finalize(_p(part), part.shape[0], c, float(count), _p(g), _p(b), bn.eps, momentum,
+                                               _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None,
+                                               _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]), self.stream), "mmad_bn_finalize")
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            self.chk(self.lib.mmad_bn_eval_params(c, _p(g), _p(b), _p(bn.running_mean), _p(bn.running_var), bn.eps,
+                                                  _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]), self.stream), "mmad_bn_eval_params")
+        return vec
+
+    def bn_apply(self, x, vec, relu, res=None, res_vec=None, out_f32=False):
+        rows, c = x.numel() // x.shape[-1], x.shape[-1]
+        out = self.empty(x.shape, torch.float32 if out_f32 else torch.bfloat16)
+        self.chk(self.lib.mmad_bn_apply(_p(x), _p(vec[2]), _p(vec[3]), _p(res), _p(res_vec[2]) if res_vec is not None else None,
+                                        _p(res_vec[3]) if res_vec is not None else None, 1 if relu else 0,
+                                        None if out_f32 else _p(out), _p(out) if out_f32 else None, rows, c, self.stream),
+                 "mmad_bn_apply")
+        return out
+
+    def bn_bwd(self, dy, dy2, mask, x, vec, gamma, training, dy_is_f32=False, want_g=True):
+        """-> dx (bf16), g (bf16 or None), dgamma, dbeta (fp32)."""
+        rows, c = x.numel() // x.shape[-1], x.shape[-1]
+        npart = self.lib.mmad_bn_bwd_partials(rows)
+        part = self.empty((npart, c, 2), torch.float32)
+        g = self.empty(x.shape) if want_g else None
+        self.chk(self.lib.mmad_bn_bwd_reduce(None if dy_is_f32 else _p(dy), _p(dy) if dy_is_f32 else None, _p(dy2), _p(mask), _p(x),
+                                             _p(vec[0]), _p(vec[1]), _p(g), _p(part), rows, c, self.stream), "mmad_bn_bwd_reduce")
+        out = self.empty((4, c), torch.float32)           # dgamma, dbeta, mg, mgx
+        self.chk(self.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                                               self.stream), "mmad_bn_bwd_finalize")
+        if not training:                                  # eval-mode BN is an affine map: no batch-statistic terms
+            out[2:].zero_()
+        dx = self.empty(x.shape)
+        src = g if want_g else dy
+        self.chk(self.lib.mmad_bn_bwd_apply(_p(src), _p(x), _p(vec[0]), _p(vec[1]), _p(gamma), _p(out[2]), _p(out[3]), _p(dx),
+                                            rows, c, self.stream), "mmad_bn_bwd_apply")
+        return dx, g, out[0], out[1]
+
+
+def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_grad: bool):
+    """Returns (features fp32 (N,D',H',W',C) NDHWC, tape for the backward pass)."""
+    r = _Run(x.device)
+    lib = r.lib
+    n, cin, d, h, w = x.shape
+    if cin != 1:
+        raise _lib.MmadError("the accelerated stem expects 1 input channel (resnet.py:126-132)")
+    x = x.contiguous().float()
+    tape = {"blocks": [], "training": training}
+
+    # ---- stem: conv1 7x7x7 s2 p3 as im2col + GEMM, bn1, relu, maxpool (resnet.py:205-208) ----
+    k, s, p = 7, 2, 3
+    do, ho, wo = (d + 2 * p - k) // s + 1, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    rows = n * do * ho * wo
+    col = r.empty((1, 1, 1, rows, STEM_KPAD))
+    r.chk(lib.mmad_stem_im2col(_p(x), _p(col), n, d, h, w, k, s, p, STEM_KPAD, r.stream), "mmad_stem_im2col")
+    wstem = r.empty((64, 1, STEM_KPAD))
+    r.chk(lib.mmad_stem_prep_weights(_p(model.conv1.weight.detach()), _p(wstem), 64, k * k * k, STEM_KPAD, r.stream),
+          "mmad_stem_prep_weights")
+    c0, part = r.conv(col, wstem, 64, 1, 1, 0, 1, training)
+    c0 = c0.view(n, do, ho, wo, 64)
+    v0 = r.bn_params(model.bn1, part, rows, training)
+    a0 = r.bn_apply(c0, v0, relu=True)
+    pd, ph, pw = (do - 1) // 2 + 1, (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
+    p0 = r.empty((n, pd, ph, pw, 64))
+    idx0 = torch.empty((n, pd, ph, pw, 64), dtype=torch.uint8, device=x.device)
+    r.chk(lib.mmad_maxpool3d_fwd(_p(a0), _p(p0), _p(idx0), n, do, ho, wo, 64, r.stream), "mmad_maxpool3d_fwd")
+    tape["stem"] = dict(col=col if need_grad else None, c0=c0, v0=v0, a0=a0, idx0=idx0, in_shape=(n, d, h, w))
+
+    # ---- residual stages (resnet.py:209-212) ----
+    cur = p0
+    blocks = [b for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer]
+    for bi, blk in enumerate(blocks):
+        last = bi == len(blocks) - 1
+        st, dil = blk.conv1.stride[0], blk.conv1.dilation[0]
+        planes = blk.conv1.out_channels
+        w1f, w1t = r.prep_weights(blk.conv1, need_grad)
+        w2f, w2t = r.prep_weights(blk.conv2, need_grad)
+        c1, part1 = r.conv(cur, w1f, planes, 3, st, dil, dil, training)
+        cnt = c1.numel() // planes
+        v1 = r.bn_params(blk.bn1, part1, cnt, training)
+        a1 = r.bn_apply(c1, v1, relu=True)
+        c2, part2 = r.conv(a1, w2f, planes, 3, 1, dil, dil, training)
+        v2 = r.bn_params(blk.bn2, part2, cnt, training)
+        rec = dict(blk=blk, xin=cur, c1=c1, v1=v1, a1=a1, c2=c2, v2=v2, w1t=w1t, w2t=w2t, stride=st, dil=dil)
+        if blk.downsample is not None:
+            dconv, dbn = blk.downsample[0], blk.downsample[1]
+            wdf, wdt = r.prep_weights(dconv, need_grad)
+            cd, partd = r.conv(cur, wdf, planes, 1, dconv.stride[0], 0, 1, training)
+            vd = r.bn_params(dbn, partd, cnt, training)
+            out = r.bn_apply(c2, v2, relu=True, res=cd, res_vec=vd, out_f32=last)
+            rec.update(cd=cd, vd=vd, wdt=wdt)
+        else:
+            out = r.bn_apply(c2, v2, relu=True, res=cur, out_f32=last)
+        rec["out"] = out
+        tape["blocks"].append(rec)
+        cur = out
+    return cur, tape
+
+
+def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):
+    """grad_out: gradient w.r.t. the (N,C,D',H',W')-shaped output view.  Returns {parameter: gradient}."""
+    r = _Run(grad_out.device)
+    lib = r.lib
+    training = tape["training"]
+    grads = {}
+    last = tape["blocks"][-1]
+    n, do, ho, wo, c = last["out"].shape
+    # gradient of the NDHWC fp32 output; accept either memory order of the NCDHW-shaped gradient
+    g_ndhwc = grad_out.permute(0, 2, 3, 4, 1)
+    if g_ndhwc.is_contiguous() and grad_out.dtype == torch.float32:
+        dy, dy_f32 = g_ndhwc, True
+    else:
+        src = grad_out.contiguous().float()
+        dy = r.empty((n, do, ho, wo, c))
+        r.chk(lib.mmad_ncs_f32_to_nsc_bf16(_p(src), _p(dy), n, c, do * ho * wo, r.stream), "mmad_ncs_f32_to_nsc_bf16")
+        dy_f32 = False
+    dy2 = None
+    for rec in reversed(tape["blocks"]):
+        blk, st, dil = rec["blk"], rec["stride"], rec["dil"]
+        planes = blk.conv1.out_channels
+        inpl = blk.conv1.in_channels
+        # out = relu(bn2(c2) + res): g2 = dy * (out > 0)
+        dc2, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, dy_is_f32=dy_f32)
+        dy_f32 = False
+        grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
+        gw = torch.empty_like(blk.conv2.weight)
+        r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw)
+        grads[blk.conv2.weight] = gw
+        da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
+        dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
+        grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
+        gw = torch.empty_like(blk.conv1.weight)
+        r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw)
+        grads[blk.conv1.weight] = gw
+        xin = rec["xin"]
+        # dgrad of conv1
+        if st == 1:
+            dx1, _ = r.conv(dc1, rec["w1t"], inpl, 3, 1, dil, dil, False)
+        else:
+            up = r.empty(tuple(xin.shape[:4]) + (planes,))
+            r.chk(lib.mmad_upsample_zero2(_p(dc1), _p(up), xin.shape[0], dc1.shape[1], dc1.shape[2], dc1.shape[3], xin.shape[1],
+                                          xin.shape[2], xin.shape[3], planes, r.stream), "mmad_upsample_zero2")
+            dx1, _ = r.conv(up, rec["w1t"], inpl, 3, 1, 2 * dil - dil, dil, False)    # pad' = dil*(k-1) - pad
+        if "cd" in rec:
+            dconv, dbn = blk.downsample[0], blk.downsample[1]
+            dcd, _, dg, db = r.bn_bwd(g2, None, None, rec["cd"], rec["vd"], dbn.weight.detach(), training, want_g=False)
+            grads[dbn.weight], grads[dbn.bias] = dg, db
+            gw = torch.empty_like(dconv.weight)
+            r.wgrad(xin, dcd, planes, 1, dconv.stride[0], 0, 1, gw)
+            grads[dconv.weight] = gw
+            if dconv.stride[0] == 1:
+                dx2, _ = r.conv(dcd, rec["wdt"], inpl, 1, 1, 0, 1, False)
+            else:
+                up = r.empty(tuple(xin.shape[:4]) + (planes,))
+                r.chk(lib.mmad_upsample_zero2(_p(dcd), _p(up), xin.shape[0], dcd.shape[1], dcd.shape[2], dcd.shape[3], xin.shape[1],
+                                              xin.shape[2], xin.shape[3], planes, r.stream), "mmad_upsample_zero2")
+                dx2, _ = r.conv(up, rec["wdt"], inpl, 1, 1, 0, 1, False)
+        else:
+            dx2 = g2                                                                # identity shortcut
+        dy, dy2 = dx1, dx2
+
+    # ---- stem backward: maxpool, relu+bn1, wgrad of the im2col GEMM (no input gradient: the MRI volume is data) ----
+    stem = tape["stem"]
+    n, d, h, w = stem["in_shape"]
+    a0 = stem["a0"]
+    dsum = r.empty(dy.shape)
+    # dy + dy2 is needed as one tensor by the max-pool gather; fold the add into a bn_apply with scale 1 / shift 0
+    ones = torch.ones((4, 64), dtype=torch.float32, device=dy.device)
+    ones[3].zero_()
+    r.chk(lib.mmad_bn_apply(_p(dy), _p(ones[2]), _p(ones[3]), _p(dy2), None, None, 0, _p(dsum), None, dy.numel() // 64, 64, r.stream),
+          "mmad_bn_apply")
+    da0 = r.empty(a0.shape)
+    r.chk(lib.mmad_maxpool3d_bwd(_p(dsum), _p(stem["idx0"]), _p(da0), n, a0.shape[1], a0.shape[2], a0.shape[3], 64, r.stream),
+          "mmad_maxpool3d_bwd")
+    dc0, _, dg, db = r.bn_bwd(da0, None, a0, stem["c0"], stem["v0"], model.bn1.weight.detach(), training, want_g=True)
+    grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
+    rows = dc0.numel() // 64
+    gwp = r.empty((64, STEM_KPAD), torch.float32)
+    r.wgrad(stem["col"], dc0.view(1, 1, 1, rows, 64), 64, 1, 1, 0, 1, gwp)
+    gw = torch.empty_like(model.conv1.weight)
+    r.chk(lib.mmad_stem_unpad_wgrad(_p(gwp), _p(gw), 64, 343, STEM_KPAD, r.stream), "mmad_stem_unpad_wgrad")
+    grads[model.conv1.weight] = gw
+    return grads
+
+
+class _BackboneFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        feats, tape = _backbone_forward(model, x, model.training, True)
+        ctx.model, ctx.tape, ctx.params = model, tape, params
+        return feats.permute(0, 4, 1, 2, 3)              # (N, C, D', H', W') view over NDHWC memory
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = _backbone_backward(ctx.model, ctx.tape, grad_out)
+        ctx.tape = None
+        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+class ResNet(nn.Module):
+    # resnet.py:112-215
+    def __init__(self, block, layers, sample_input_D, sample_input_H, sample_input_W, num_seg_classes,
+                 shortcut_type='B', no_cuda=False):
+        self.inplanes = 64
+        self.no_cuda = no_cuda
+        super().__init__()
+        self.block_type = block
+        self.shortcut_type = shortcut_type
+        self.conv1 = nn.Conv3d(1, 64, kernel_size=7, stride=(2, 2, 2), padding=(3, 3, 3), bias=False)
+        self.bn1 = nn.BatchNorm3d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool3d(kernel_size=(3, 3, 3), stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0], shortcut_type)
+        self.layer2 = self._make_layer(block, 128, layers[1], shortcut_type, stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], shortcut_type, stride=1, dilation=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], shortcut_type, stride=1, dilation=4)
+        self.conv_seg = nn.Sequential(
+            nn.ConvTranspose3d(512 * block.expansion, 32, 2, stride=2),
+            nn.BatchNorm3d(32),
+            nn.ReLU(inplace=True),
+            nn.Conv3d(32, 32, kernel_size=3, stride=(1, 1, 1), padding=(1, 1, 1), bias=False),
+            nn.BatchNorm3d(32),
+            nn.ReLU(inplace=True),
+            nn.Conv3d(32, num_seg_classes, kernel_size=1, stride=(1, 1, 1), bias=False))
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out')
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+
+    def _make_layer(self, block, planes, blocks, shortcut_type, stride=1, dilation=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            if shortcut_type == 'A':
+                downsample = partial(downsample_basic_block, planes=planes * block.expansion, stride=stride,
+                                     no_cuda=self.no_cuda)
+            else:
+                downsample = nn.Sequential(
+                    nn.Conv3d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                    nn.BatchNorm3d(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride=stride, dilation=dilation, downsample=downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, dilation=dilation))
+        return nn.Sequential(*layers)
+
+    def backbone_parameters(self):
+        ps = [self.conv1.weight, self.bn1.weight, self.bn1.bias]
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                ps += [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias]
+                if blk.downsample is not None:
+                    ps += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
+        return ps
+
+    def features(self, x):
+        """conv1 … layer4 (resnet.py:205-212) -> (N, 512, D/8.., H/8.., W/8..) fp32."""
+        if not x.is_cuda:
+            raise _lib.MmadError("multimodal_ad_b200 ResNet runs on CUDA tensors only (no CPU fallback)")
+        if self.block_type is not BasicBlock or self.shortcut_type != 'B':
+            raise _lib.MmadError("accelerated path covers BasicBlock networks (resnet10/18/34) with shortcut type 'B'")
+        with torch.cuda.device(x.device):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.backbone_parameters()):
+                return _BackboneFunction.apply(x, self, *self.backbone_parameters())
+            feats, _ = _backbone_forward(self, x, self.training, False)
+            return feats.permute(0, 4, 1, 2, 3)
+
+    def forward(self, x):
+        x = self.features(x)
+        x = self.conv_seg(x)
+        return x
+
+
+def resnet10(**kwargs):
+    return ResNet(BasicBlock, [1, 1, 1, 1], **kwargs)
+
+
+def resnet18(**kwargs):
+    return ResNet(BasicBlock, [2, 2, 2, 2], **kwargs)
+
+
+def resnet34(**kwargs):
+    return ResNet(BasicBlock, [3, 4, 6, 3], **kwargs)
+
+
+def resnet50(**kwargs):
+    return ResNet(Bottleneck, [3, 4, 6, 3], **kwargs)
+
+
+def resnet101(**kwargs):
+    return ResNet(Bottleneck, [3, 4, 23, 3], **kwargs)
+
+
+def resnet152(**kwargs):
+    return ResNet(Bottleneck, [3, 8, 36, 3], **kwargs)
+
+
+def resnet200(**kwargs):
+    return ResNet(Bottleneck, [3, 24, 36, 3], **kwargs)

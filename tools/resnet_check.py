@@ -1,0 +1,49 @@
+"""GPU check of the whole accelerated ResNet (forward + backward) against the torch fp32 oracle (developer tool)."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+from multimodal_ad_b200.models import resnet
+from oracle.resnet_oracle import resnet_features_oracle
+
+def main(depth=10, n=2, size=32, seed=0):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(seed)
+    fn = {10: resnet.resnet10, 18: resnet.resnet18}[depth]
+    model = fn(sample_input_D=size, sample_input_H=size, sample_input_W=size, num_seg_classes=1).cuda()
+    layers = [len(l) for l in (model.layer1, model.layer2, model.layer3, model.layer4)]
+    # make BN affine parameters non-trivial
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.3, 0.3)
+    x = torch.rand(n, 1, size, size, size, device="cuda")
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.train()
+    feats = model.features(x)
+    wgt = torch.randn_like(feats) / feats.numel() ** 0.5
+    loss = (feats * wgt).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    ref = resnet_features_oracle(leaves, x, layers, True)
+    (ref * wgt).sum().backward()
+    def rel(a, b): return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+    out = {"feat_rel": rel(feats, ref), "feat_shape": list(feats.shape)}
+    named = dict(model.named_parameters())
+    worst = []
+    for k, v in leaves.items():
+        if v.grad is None or k.startswith("conv_seg"): continue
+        g = named[k].grad
+        worst.append((rel(g, v.grad) if g is not None else float("nan"), k))
+    worst.sort(reverse=True)
+    out["grad_rel_worst"] = worst[:8]
+    out["grad_rel_median"] = sorted(w for w, _ in worst)[len(worst) // 2]
+    # running stats
+    out["running_mean_rel"] = rel(model.bn1.running_mean, 0.9 * sd["bn1.running_mean"] + 0.1 * F.conv3d(x, sd["conv1.weight"], stride=2, padding=3).mean(dim=(0, 2, 3, 4)))
+    print(json.dumps(out), flush=True)
+
+if __name__ == "__main__":
+    a = [int(v) for v in sys.argv[1:]]
+    main(*a)
