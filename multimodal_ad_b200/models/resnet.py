@@ -148,14 +148,15 @@ class _Run:
                                                   _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]), self.stream), "mmad_bn_eval_params")
         return vec
 
-    def bn_apply(self, x, vec, relu, res=None, res_vec=None, out_f32=False):
+    def bn_apply(self, x, vec, relu, res=None, res_vec=None, also_f32=False):
+        """-> bf16 activation (and, with also_f32, the same values in fp32 for the caller-facing output)."""
         rows, c = x.numel() // x.shape[-1], x.shape[-1]
-        out = self.empty(x.shape, torch.float32 if out_f32 else torch.bfloat16)
+        out = self.empty(x.shape)
+        out32 = self.empty(x.shape, torch.float32) if also_f32 else None
         self.chk(self.lib.mmad_bn_apply(_p(x), _p(vec[2]), _p(vec[3]), _p(res), _p(res_vec[2]) if res_vec is not None else None,
                                         _p(res_vec[3]) if res_vec is not None else None, 1 if relu else 0,
-                                        None if out_f32 else _p(out), _p(out) if out_f32 else None, rows, c, self.stream),
-                 "mmad_bn_apply")
-        return out
+                                        _p(out), _p(out32), rows, c, self.stream), "mmad_bn_apply")
+        return (out, out32) if also_f32 else out
 
     def bn_bwd(self, dy, dy2, mask, x, vec, gamma, training, dy_is_f32=False, want_g=True):
         """-> dx (bf16), g (bf16 or None), dgamma, dbeta (fp32)."""
@@ -227,14 +228,17 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
             wdf, wdt = r.prep_weights(dconv, need_grad)
             cd, partd = r.conv(cur, wdf, planes, 1, dconv.stride[0], 0, 1, training)
             vd = r.bn_params(dbn, partd, cnt, training)
-            out = r.bn_apply(c2, v2, relu=True, res=cd, res_vec=vd, out_f32=last)
+            out = r.bn_apply(c2, v2, relu=True, res=cd, res_vec=vd, also_f32=last)
             rec.update(cd=cd, vd=vd, wdt=wdt)
         else:
-            out = r.bn_apply(c2, v2, relu=True, res=cur, out_f32=last)
-        rec["out"] = out
+            out = r.bn_apply(c2, v2, relu=True, res=cur, also_f32=last)
+        out32 = None
+        if last:
+            out, out32 = out
+        rec["out"] = out                                   # bf16: next block's input and the ReLU mask of the backward
         tape["blocks"].append(rec)
         cur = out
-    return cur, tape
+    return out32, tape
 
 
 def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):

@@ -1,0 +1,182 @@
+"""GPU parity of the Conv3d / BatchNorm / ReLU / MaxPool kernels (through the C-ABI) against torch fp32 on the same
+bf16-rounded operands.  Tolerances: bf16 storage => 2^-8 relative per stored element (north star: 2e-2 in bf16)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def run(built_lib):
+    from multimodal_ad_b200.models.resnet import _Run
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _Run(torch.device("cuda", 0))
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+CONV_CASES = [
+    (1, 1, 8, 16, 64, 64, 1, 1, 0, 1), (1, 2, 8, 16, 128, 128, 1, 1, 0, 1), (1, 4, 8, 16, 64, 256, 1, 1, 0, 1),
+    (2, 8, 8, 8, 64, 64, 3, 1, 1, 1), (1, 8, 16, 16, 128, 256, 3, 1, 2, 2), (1, 16, 16, 16, 64, 128, 3, 2, 1, 1),
+    (1, 16, 16, 16, 64, 128, 1, 2, 0, 1), (1, 5, 7, 9, 64, 64, 3, 1, 1, 1), (1, 6, 11, 23, 64, 512, 3, 1, 4, 4),
+    (2, 32, 32, 32, 64, 64, 3, 1, 1, 1), (1, 1, 1, 5000, 384, 64, 1, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", CONV_CASES)
+def test_conv3d_forward_and_statistics(cfg, run):
+    n, d, h, w, cin, cout, k, stride, pad, dil = cfg
+    g = torch.Generator(device="cuda").manual_seed(sum(cfg))
+    x = torch.randn((n, d, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn((cout, k ** 3, cin), device="cuda", generator=g) / (k ** 1.5 * cin ** 0.5)).to(torch.bfloat16)
+    y, part = run.conv(x, wt, cout, k, stride, pad, dil, True)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), wt.float().reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3),
+                   stride=stride, padding=pad, dilation=dil).permute(0, 2, 3, 4, 1)
+    assert not torch.isnan(y.float()).any()
+    # every element within one bf16 rounding step of the fp32 result (+ fp32 accumulation-order slack)
+    assert torch.all((y.float() - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
+    yb = y.float().reshape(-1, cout)
+    s = part.sum(0)
+    assert torch.allclose(s[:, 0], yb.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (yb * yb).sum(0), rtol=1e-4, atol=1e-2)
+
+
+WG_CASES = [
+    (1, 4, 4, 4, 64, 64, 1, 1, 0, 1), (1, 4, 8, 8, 128, 128, 1, 1, 0, 1), (2, 8, 8, 8, 64, 64, 3, 1, 1, 1),
+    (1, 8, 8, 16, 128, 256, 3, 1, 2, 2), (1, 16, 16, 16, 64, 128, 3, 2, 1, 1), (1, 16, 16, 16, 64, 128, 1, 2, 0, 1),
+    (1, 5, 7, 9, 256, 512, 3, 1, 4, 4), (1, 1, 1, 4096, 384, 64, 1, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", WG_CASES)
+def test_conv3d_wgrad_and_dgrad(cfg, run):
+    from multimodal_ad_b200.models.resnet import _p
+
+    n, d, h, w, cin, cout, k, stride, pad, dil = cfg
+    g = torch.Generator(device="cuda").manual_seed(sum(cfg) + 1)
+    x = torch.randn((n, d, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    wt = torch.randn((cout, cin, k, k, k), device="cuda", generator=g) / (k ** 1.5 * cin ** 0.5)
+    do, ho, wo = [(v + 2 * pad - dil * (k - 1) - 1) // stride + 1 for v in (d, h, w)]
+    dy = torch.randn((n, do, ho, wo, cout), device="cuda", generator=g).to(torch.bfloat16)
+    xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wr = wt.to(torch.bfloat16).float().requires_grad_(True)
+    F.conv3d(xr, wr, stride=stride, padding=pad, dilation=dil).backward(dy.float().permute(0, 4, 1, 2, 3))
+    gw = torch.empty_like(wt)
+    run.wgrad(x, dy, cout, k, stride, pad, dil, gw)
+    assert _rel(gw, wr.grad) < 1e-4                     # fp32 accumulation of exact bf16 products: 1e-4 relative (fp32/tf32 bound)
+    if cin == 384:
+        return
+    taps = k ** 3
+    wf, wtr = run.empty((cout, taps, cin)), run.empty((cin, taps, cout))
+    run.chk(run.lib.mmad_conv3d_prep_weights(_p(wt), _p(wf), _p(wtr), cout, cin, taps, run.stream), "prep")
+    assert torch.equal(wf.float(), wt.to(torch.bfloat16).float().reshape(cout, cin, taps).permute(0, 2, 1))
+    src = dy
+    if stride == 2:
+        src = run.empty((n, d, h, w, cout))
+        run.chk(run.lib.mmad_upsample_zero2(_p(dy), _p(src), n, do, ho, wo, d, h, w, cout, run.stream), "up")
+        chk = torch.zeros_like(src)
+        chk[:, ::2, ::2, ::2][:, :do, :ho, :wo] = dy
+        assert torch.equal(src, chk)
+    dx, _ = run.conv(src, wtr, cin, k, 1, dil * (k - 1) - pad, dil, False)
+    ref = xr.grad.permute(0, 2, 3, 4, 1)
+    assert torch.all((dx.float() - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
+
+
+@pytest.mark.parametrize("c,rows", [(64, 4099), (128, 513), (256, 70), (512, 1000)])
+def test_batchnorm_forward_backward(c, rows, run):
+    from multimodal_ad_b200.models.resnet import _p
+
+    g = torch.Generator(device="cuda").manual_seed(c + rows)
+    x = (torch.randn((1, 1, 1, rows, c), device="cuda", generator=g) * 1.7 + 0.3).to(torch.bfloat16)
+    res = torch.randn((1, 1, 1, rows, c), device="cuda", generator=g).to(torch.bfloat16)
+    bn = torch.nn.BatchNorm3d(c).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    # statistics partials the conv epilogue would have produced (two fake CTAs)
+    xf = x.float().reshape(rows, c)
+    half = rows // 2
+    part = torch.stack([torch.stack([xf[:half].sum(0), (xf[:half] ** 2).sum(0)], 1),
+                        torch.stack([xf[half:].sum(0), (xf[half:] ** 2).sum(0)], 1)]).contiguous()
+    vec = run.bn_params(bn, part, rows, True)
+    out = run.bn_apply(x, vec, relu=True, res=res)
+    # torch reference on the same rounded operands
+    xt = xf.clone().requires_grad_(True)
+    gam, bet = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    yt = F.batch_norm(xt.t().reshape(1, c, rows), rm, rv, gam, bet, True, 0.1, bn.eps).reshape(c, rows).t()
+    ot = F.relu(yt + res.float().reshape(rows, c))
+    assert torch.allclose(vec[0], xf.mean(0), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(vec[1], 1.0 / torch.sqrt(xf.var(0, unbiased=False) + bn.eps), rtol=1e-4)
+    assert torch.allclose(bn.running_mean, rm, rtol=1e-5, atol=1e-6) and torch.allclose(bn.running_var, rv, rtol=1e-4, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
+    o = out.float().reshape(rows, c)
+    assert torch.all((o - ot).abs() <= 2 ** -8 * ot.abs() + 1e-5)
+    # backward: dy (+ dy2), ReLU mask from the stored output
+    dy = torch.randn((1, 1, 1, rows, c), device="cuda", generator=g).to(torch.bfloat16)
+    dy2 = torch.randn((1, 1, 1, rows, c), device="cuda", generator=g).to(torch.bfloat16)
+    dx, gk, dgam, dbet = run.bn_bwd(dy, dy2, out, x, vec, bn.weight.detach(), True)
+    gsum = (dy.float() + dy2.float()).reshape(rows, c) * (o > 0)
+    gsum_r = gsum.to(torch.bfloat16).float()
+    assert torch.equal(gk.float().reshape(rows, c), gsum_r)
+    # autograd of the same graph fed with the rounded g (what pass 2 consumes)
+    yt2 = F.batch_norm(xt.t().reshape(1, c, rows), rm0.clone(), rv0.clone(), gam, bet, True, 0.1, bn.eps).reshape(c, rows).t()
+    yt2.backward(gsum_r)
+    assert _rel(dgam, gam.grad) < 1e-4 and _rel(dbet, bet.grad) < 1e-4
+    assert torch.all((dx.float().reshape(rows, c) - xt.grad).abs() <= 2 ** -8 * xt.grad.abs() + 3e-3 * xt.grad.abs().max())
+    assert _rel(dx, xt.grad) < 5e-3
+    # eval mode is an affine map
+    bn.eval()
+    vec_e = run.bn_params(bn, None, rows, False)
+    oe = run.bn_apply(x, vec_e, relu=False)
+    ref_e = F.batch_norm(xf.t().reshape(1, c, rows), bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.1, bn.eps)
+    assert _rel(oe.reshape(rows, c), ref_e.reshape(c, rows).t()) < 4e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 7, 9, 11), (1, 16, 4, 6)])
+def test_maxpool_forward_backward(shape, run):
+    from multimodal_ad_b200.models.resnet import _p
+
+    n, d, h, w = shape
+    c = 64
+    g = torch.Generator(device="cuda").manual_seed(d * h * w)
+    x = torch.randn((n, d, h, w, c), device="cuda", generator=g).to(torch.bfloat16)
+    do, ho, wo = (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = run.empty((n, do, ho, wo, c))
+    idx = torch.empty((n, do, ho, wo, c), dtype=torch.uint8, device="cuda")
+    run.chk(run.lib.mmad_maxpool3d_fwd(_p(x), _p(y), _p(idx), n, d, h, w, c, run.stream), "maxpool fwd")
+    xt = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    yt = F.max_pool3d(xt, 3, 2, 1)
+    assert torch.equal(y.float(), yt.permute(0, 2, 3, 4, 1))
+    dy = torch.randn((n, do, ho, wo, c), device="cuda", generator=g).to(torch.bfloat16)
+    dx = run.empty((n, d, h, w, c))
+    run.chk(run.lib.mmad_maxpool3d_bwd(_p(dy), _p(idx), _p(dx), n, d, h, w, c, run.stream), "maxpool bwd")
+    yt.backward(dy.float().permute(0, 4, 1, 2, 3))
+    ref = xt.grad.permute(0, 2, 3, 4, 1)
+    assert torch.all((dx.float() - ref).abs() <= 2 ** -7 * ref.abs() + 1e-6)      # sum of <= 8 bf16 terms, rounded once
+
+
+def test_layout_transpose_and_stem_im2col(run):
+    from multimodal_ad_b200.models.resnet import STEM_KPAD, _p
+
+    x = torch.randn((2, 70, 5 * 6 * 7), device="cuda")
+    y = run.empty((2, 5 * 6 * 7, 70))
+    run.chk(run.lib.mmad_ncs_f32_to_nsc_bf16(_p(x), _p(y), 2, 70, 5 * 6 * 7, run.stream), "transpose")
+    assert torch.equal(y, x.permute(0, 2, 1).to(torch.bfloat16))
+    v = torch.rand((2, 1, 9, 12, 10), device="cuda")
+    do, ho, wo = [(s + 6 - 7) // 2 + 1 for s in (9, 12, 10)]
+    col = run.empty((2 * do * ho * wo, STEM_KPAD))
+    run.chk(run.lib.mmad_stem_im2col(_p(v), _p(col), 2, 9, 12, 10, 7, 2, 3, STEM_KPAD, run.stream), "im2col")
+    ref = F.unfold(F.pad(v, (3, 3, 3, 3, 3, 3)).reshape(2, 1, 15, 18 * 16), 1)  # placeholder shape use
+    unf = F.pad(v, (3, 3, 3, 3, 3, 3)).unfold(2, 7, 2).unfold(3, 7, 2).unfold(4, 7, 2)        # (2,1,do,ho,wo,7,7,7)
+    unf = unf.reshape(2 * do * ho * wo, 343).to(torch.bfloat16)
+    assert torch.equal(col[:, :343], unf) and torch.all(col[:, 343:] == 0)

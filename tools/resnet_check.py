@@ -26,20 +26,23 @@ def main(depth=10, n=2, size=32, seed=0):
     loss = (feats * wgt).sum()
     loss.backward()
     torch.cuda.synchronize()
-    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
-    ref = resnet_features_oracle(leaves, x, layers, True)
-    (ref * wgt).sum().backward()
     def rel(a, b): return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
-    out = {"feat_rel": rel(feats, ref), "feat_shape": list(feats.shape)}
     named = dict(model.named_parameters())
-    worst = []
-    for k, v in leaves.items():
-        if v.grad is None or k.startswith("conv_seg"): continue
-        g = named[k].grad
-        worst.append((rel(g, v.grad) if g is not None else float("nan"), k))
-    worst.sort(reverse=True)
-    out["grad_rel_worst"] = worst[:8]
-    out["grad_rel_median"] = sorted(w for w, _ in worst)[len(worst) // 2]
+    out = {"feat_shape": list(feats.shape)}
+    for emu in (True, False):
+        leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        ref = resnet_features_oracle(leaves, x, layers, True, emulate_bf16=emu)
+        (ref * wgt).sum().backward()
+        tag = "emu" if emu else "fp32"
+        out[f"feat_rel_{tag}"] = rel(feats, ref)
+        errs = []
+        for k, v in leaves.items():
+            if v.grad is None or k.startswith("conv_seg"): continue
+            g = named[k].grad
+            errs.append((k, round(rel(g, v.grad), 5) if g is not None else float("nan")))
+        out[f"grad_rel_{tag}"] = errs if emu else sorted(errs, key=lambda t: -t[1])[:4]
+        out[f"grad_rel_median_{tag}"] = sorted(e for _, e in errs)[len(errs) // 2]
+        out[f"grad_rel_max_{tag}"] = max(e for _, e in errs)
     # running stats
     out["running_mean_rel"] = rel(model.bn1.running_mean, 0.9 * sd["bn1.running_mean"] + 0.1 * F.conv3d(x, sd["conv1.weight"], stride=2, padding=3).mean(dim=(0, 2, 3, 4)))
     print(json.dumps(out), flush=True)
