@@ -327,12 +327,27 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
     return grads
 
 
+def tape_stages(model: "ResNet", tape) -> dict:
+    """Stored activations of a forward tape as {stage name: NCDHW fp32 tensor} (test / debugging aid; the names are
+    the ones oracle/resnet_oracle.py accepts for `forced`)."""
+    f = lambda t: t.float().permute(0, 4, 1, 2, 3)          # noqa: E731
+    out = {"c0": f(tape["stem"]["c0"]), "a0": f(tape["stem"]["a0"])}
+    names = [f"layer{li}.{bi}" for li, layer in enumerate((model.layer1, model.layer2, model.layer3, model.layer4), 1)
+             for bi in range(len(layer))]
+    for pre, rec in zip(names, tape["blocks"]):
+        for k in ("c1", "a1", "c2", "cd", "out"):
+            if k in rec:
+                out[f"{pre}.{k}"] = f(rec[k])
+    return out
+
+
 class _BackboneFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, model, *params):
         need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         feats, tape = _backbone_forward(model, x, model.training, True)
         ctx.model, ctx.tape, ctx.params = model, tape, params
+        model._last_tape = tape if getattr(model, "keep_tape", False) else None
         return feats.permute(0, 4, 1, 2, 3)              # (N, C, D', H', W') view over NDHWC memory
 
     @staticmethod

@@ -21,7 +21,10 @@ def main(depth=10, n=2, size=32, seed=0):
     x = torch.rand(n, 1, size, size, size, device="cuda")
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model.train()
+    model.keep_tape = True
     feats = model.features(x)
+    from multimodal_ad_b200.models.resnet import tape_stages
+    forced = tape_stages(model, model._last_tape)
     wgt = torch.randn_like(feats) / feats.numel() ** 0.5
     loss = (feats * wgt).sum()
     loss.backward()
@@ -29,18 +32,18 @@ def main(depth=10, n=2, size=32, seed=0):
     def rel(a, b): return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
     named = dict(model.named_parameters())
     out = {"feat_shape": list(feats.shape)}
-    for emu in (True, False):
+    for emu in ("forced", True, False):
         leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
-        ref = resnet_features_oracle(leaves, x, layers, True, emulate_bf16=emu)
+        ref = resnet_features_oracle(leaves, x, layers, True, emulate_bf16=bool(emu), forced=forced if emu == "forced" else None)
         (ref * wgt).sum().backward()
-        tag = "emu" if emu else "fp32"
+        tag = emu if emu == "forced" else ("emu" if emu else "fp32")
         out[f"feat_rel_{tag}"] = rel(feats, ref)
         errs = []
         for k, v in leaves.items():
             if v.grad is None or k.startswith("conv_seg"): continue
             g = named[k].grad
             errs.append((k, round(rel(g, v.grad), 5) if g is not None else float("nan")))
-        out[f"grad_rel_{tag}"] = errs if emu else sorted(errs, key=lambda t: -t[1])[:4]
+        out[f"grad_rel_{tag}"] = errs if emu == "forced" else sorted(errs, key=lambda t: -t[1])[:3]
         out[f"grad_rel_median_{tag}"] = sorted(e for _, e in errs)[len(errs) // 2]
         out[f"grad_rel_max_{tag}"] = max(e for _, e in errs)
     # running stats
