@@ -162,17 +162,19 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift,
                   void* out_bf16, float* out_f32, int64_t rows, int C, void* stream);
 /* Backward of ReLU + BatchNorm3d.  reduce: g = (dy [+ dy2]) * (mask > 0),
  * written to g_out (bf16, may be NULL) with per-block partial sums of g and
- * g*xhat; finalize: dgamma, dbeta and the per-channel means mg, mgx; apply:
- * dx = gamma*invstd*(g - mg - xhat*mgx).  dy is bf16 (dy_bf16) or fp32
- * (dy_f32), both rows x C in NDHWC order; mask NULL = no ReLU. */
+ * g*xhat; finalize: dgamma, dbeta and coef = float[3][C] with
+ * dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = coef0*g + coef1*x + coef2
+ * (training == 0: eval-mode BatchNorm is affine, dx = gamma*invstd*g); apply:
+ * that map.  dy is bf16 (dy_bf16) or fp32 (dy_f32), both rows x C in NDHWC
+ * order; mask NULL = no ReLU. */
 int mmad_bn_bwd_partials(int64_t rows);
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2,
                        const void* mask, const void* x, const float* mean, const float* invstd,
                        void* g_out, float* partials, int64_t rows, int C, void* stream);
 int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
-                         float* dgamma, float* dbeta, float* mg, float* mgx, void* stream);
-int mmad_bn_bwd_apply(const void* g, const void* x, const float* mean, const float* invstd,
-                      const float* gamma, const float* mg, const float* mgx,
+                         const float* gamma, const float* mean, const float* invstd, int training,
+                         float* dgamma, float* dbeta, float* coef, void* stream);
+int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef,
                       void* dx, int64_t rows, int C, void* stream);
 
 /* MaxPool3d(kernel 3, stride 2, padding 1) (resnet.py:136), NDHWC bf16; idx

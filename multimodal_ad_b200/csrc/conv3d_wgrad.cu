@@ -49,11 +49,12 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // work item
+    // work item: unit group fastest, K slice slowest, so the CTAs resident at the same time walk the SAME voxel slice
+    // (different taps / channel blocks of it) and the slice stays in L2
     int item = blockIdx.x;
-    const int ks = item % g.nsplit; item /= g.nsplit;
     const int ug = item % g.ugroups; item /= g.ugroups;
-    const int nt = item;
+    const int nt = item % g.n_tiles; item /= g.n_tiles;
+    const int ks = item;
     const int u0 = ug * g.nacc;
     const int nu = min(g.nacc, g.units - u0);                               // accumulator blocks this CTA really owns
     const int c_begin = (int)((long long)g.n_chunks * ks / g.nsplit), c_end = (int)((long long)g.n_chunks * (ks + 1) / g.nsplit);
@@ -198,7 +199,17 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
     g.nacc = std::min(g.nacc, g.units);
     g.ugroups = (g.units + g.nacc - 1) / g.nacc;
     const int items = g.n_tiles * g.ugroups;
-    g.nsplit = std::max(1, std::min(g.n_chunks, (2 * sms + items - 1) / items));
+    // split count: at least ~2 waves of CTAs, and a grid that fills whole waves (the last wave is the tail)
+    int best_s = 1;
+    double best_score = -1.0;
+    for (int sp = 1; sp <= 96 && sp <= g.n_chunks; ++sp) {
+        const long long ctas = (long long)items * sp;
+        if (ctas < 2LL * sms && sp < std::min(96, g.n_chunks)) continue;
+        const long long waves = (ctas + sms - 1) / sms;
+        const double score = (double)ctas / (double)(waves * sms) - 0.004 * sp;
+        if (score > best_score) { best_score = score; best_s = sp; }
+    }
+    g.nsplit = best_s;
     const int stage = (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     g.stages = std::max(2, std::min(6, (227 * 1024 - 1024 - 256) / stage));
     return 0;

@@ -52,51 +52,59 @@ __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
 }
 
-// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, k = 7, stride 2, pad 3, column = (kd*7+kh)*7+kw
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
-                                                          int H, int W, int Do, int Ho, int Wo, int k, int stride, int pad,
-                                                          int Kpad) {
-    // one warp per output voxel row; lane l writes columns l*8 .. l*8+7 (16 bytes) for 48 lanes' worth -> loop
+// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, k = 7, stride 2, pad 3, column = (kd*7+kh)*7+kw.
+//      One thread per 16-byte chunk (8 columns) of a row; the column -> (kd,kh,kw) split comes from a constant table.
+__constant__ signed char c_tap_d[512], c_tap_h[512], c_tap_w[512];     // -128 = padding column
+__global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
+                                                          int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
+    const int cpr = Kpad >> 3;                        // chunks per row (48)
+    const int rpb = 192 / cpr;                        // rows per block step (4)
+    const int chunk = threadIdx.x % cpr, rsub = threadIdx.x / cpr;
+    if (rsub >= rpb) return;
     const long long rows = (long long)N * Do * Ho * Wo;
-    const int K = k * k * k;
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = warp0; r < rows; r += nwarps) {
+    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
         long long t = r;
         const int ow = (int)(t % Wo); t /= Wo;
         const int oh = (int)(t % Ho); t /= Ho;
         const int od = (int)(t % Do); t /= Do;
-        const int n = (int)t;
-        const float* xn = x + (long long)n * D * H * W;
-        for (int c0 = lane * 8; c0 < Kpad; c0 += 256) {
-            float f[8];
+        const float* xn = x + t * (long long)D * H * W;
+        const int iw0 = ow * stride - pad, ih0 = oh * stride - pad, id0 = od * stride - pad;
+        float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c0 + j;
-                float v = 0.f;
-                if (c < K) {
-                    const int kw = c % k, kh = (c / k) % k, kd = c / (k * k);
-                    const int iw = ow * stride + kw - pad, ih = oh * stride + kh - pad, id = od * stride + kd - pad;
-                    if (iw >= 0 && iw < W && ih >= 0 && ih < H && id >= 0 && id < D) v = __ldg(xn + ((long long)id * H + ih) * W + iw);
-                }
-                f[j] = v;
-            }
-            *reinterpret_cast<uint4*>(col + r * Kpad + c0) = pack8(f);
+        for (int j = 0; j < 8; ++j) {
+            const int c = chunk * 8 + j;
+            const int kd = c_tap_d[c];
+            const int id = id0 + kd, ih = ih0 + c_tap_h[c], iw = iw0 + c_tap_w[c];
+            float v = 0.f;
+            if (kd >= 0 && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+                v = __ldg(xn + ((long long)id * H + ih) * W + iw);
+            f[j] = v;
         }
+        *reinterpret_cast<uint4*>(col + r * Kpad + chunk * 8) = pack8(f);
     }
 }
 
 // ---- BatchNorm statistics: per-CTA partial (sum, sum of squares) -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale;
 //      running statistics updated like nn.BatchNorm3d (momentum, unbiased variance).  One thread per channel, double accumulation.
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // one warp per channel
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
-    for (int p = 0; p < nparts; ++p) { s += partials[((size_t)p * C + c) * 2]; q += partials[((size_t)p * C + c) * 2 + 1]; }
+    for (int p = lane; p < nparts; p += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2);
+        s += v.x; q += v.y;
+    }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (lane) return;
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -216,22 +224,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
         }
     }
 }
-// sums the block partials; writes dgamma, dbeta and the two per-channel means the apply pass needs
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ mg, float* __restrict__ mgx) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// sums the block partials (one warp per channel); writes dgamma, dbeta and the three per-channel coefficients of pass 2:
+//   dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = A*g + B*x + Cc,  A = gamma*invstd, B = -A*invstd*mgx,
+//   Cc = A*(mean*invstd*mgx - mg).   Eval mode (training == 0): BatchNorm is affine, dx = A*g.
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       int training, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s = 0.0, q = 0.0;
-    for (int p = 0; p < nparts; ++p) { s += partials[((size_t)p * C + c) * 2]; q += partials[((size_t)p * C + c) * 2 + 1]; }
+    for (int p = lane; p < nparts; p += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2);
+        s += v.x; q += v.y;
+    }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (lane) return;
     if (dbeta) dbeta[c] = (float)s;
     if (dgamma) dgamma[c] = (float)q;
-    mg[c] = (float)(s / count);
-    mgx[c] = (float)(q / count);
+    const float mg = training ? (float)(s / count) : 0.f, mgx = training ? (float)(q / count) : 0.f;
+    const float a = gamma[c] * invstd[c];
+    coef[c] = a;
+    coef[C + c] = -a * invstd[c] * mgx;
+    coef[2 * C + c] = a * (mean[c] * invstd[c] * mgx - mg);
 }
-// pass 2: dx = gamma*invstd * (g - mean(g) - xhat*mean(g*xhat))      (eval mode: dx = gamma*invstd*g with mg = mgx = 0)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                           const float* __restrict__ mg, const float* __restrict__ mgx,
+// pass 2: dx = A*g + B*x + Cc
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ coef,
                                                            uint4* __restrict__ dx, long long nvec, int C) {
     const int cv = C >> 3;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
@@ -239,12 +257,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
         float gv[8], xv[8], o[8];
         unpack8(g[i], gv);
         unpack8(x[i], xv);
+        const float4 a0 = *reinterpret_cast<const float4*>(coef + c0), a1 = *reinterpret_cast<const float4*>(coef + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(coef + C + c0), b1 = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(coef + 2 * C + c0), d1 = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
+        const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float Cc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float is = invstd[c0 + j];
-            const float xh = (xv[j] - mean[c0 + j]) * is;
-            o[j] = gamma[c0 + j] * is * (gv[j] - mg[c0 + j] - xh * mgx[c0 + j]);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
         dx[i] = pack8(o);
     }
 }
@@ -404,16 +424,31 @@ int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, in
 int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int k, int stride, int pad, int Kpad, void* stream) {
     MMAD_CHECK_ARG(x && col && Kpad % 8 == 0 && k * k * k <= Kpad, "stem_im2col: bad argument");
     const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    MMAD_CHECK_ARG(Kpad <= 512 && 192 % (Kpad / 8) == 0, "stem_im2col: Kpad must be <= 512 and Kpad/8 must divide 192");
     const long long rows = (long long)N * Do * Ho * Wo;
-    im2col_stem_kernel<<<grid_for(rows * 32, 256, 148 * 16), 256, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, k, stride, pad, Kpad);
+    static int table_k = 0;
+    if (table_k != k) {                                   // column -> tap offsets
+        signed char td[512], th[512], tw[512];
+        for (int c = 0; c < 512; ++c) {
+            if (c < k * k * k) { td[c] = (signed char)(c / (k * k)); th[c] = (signed char)((c / k) % k); tw[c] = (signed char)(c % k); }
+            else { td[c] = -128; th[c] = 0; tw[c] = 0; }
+        }
+        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_d, td, 512, 0, cudaMemcpyHostToDevice, ST));
+        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_h, th, 512, 0, cudaMemcpyHostToDevice, ST));
+        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_w, tw, 512, 0, cudaMemcpyHostToDevice, ST));
+        MMAD_CUDA(cudaStreamSynchronize(ST));             // the host arrays are on this stack frame
+        table_k = k;
+    }
+    const int rpb = 192 / (Kpad / 8);
+    im2col_stem_kernel<<<grid_for((rows + rpb - 1) / rpb, 1, 148 * 32), 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
     LAUNCH_OK();
 }
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
                      float* shift, void* stream) {
     MMAD_CHECK_ARG(partials && gamma && beta && mean && invstd && scale && shift && C > 0 && count > 0, "bn_finalize: bad argument");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partials, nparts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
-                                                       mean, invstd, scale, shift);
+    bn_finalize_kernel<<<(C + 3) / 4, 128, 0, ST>>>(partials, nparts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+                                                   mean, invstd, scale, shift);
     LAUNCH_OK();
 }
 int mmad_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
@@ -443,17 +478,16 @@ int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2
                                                                      partials, rows, C);
     LAUNCH_OK();
 }
-int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count, float* dgamma, float* dbeta, float* mg, float* mgx,
-                         void* stream) {
-    MMAD_CHECK_ARG(partials && mg && mgx && C > 0, "bn_bwd_finalize: bad argument");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(partials, nparts, C, count, dgamma, dbeta, mg, mgx);
+int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* mean,
+                         const float* invstd, int training, float* dgamma, float* dbeta, float* coef, void* stream) {
+    MMAD_CHECK_ARG(partials && gamma && mean && invstd && coef && C > 0, "bn_bwd_finalize: bad argument");
+    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, ST>>>(partials, nparts, C, count, gamma, mean, invstd, training, dgamma, dbeta, coef);
     LAUNCH_OK();
 }
-int mmad_bn_bwd_apply(const void* g, const void* x, const float* mean, const float* invstd, const float* gamma, const float* mg,
-                      const float* mgx, void* dx, int64_t rows, int C, void* stream) {
-    MMAD_CHECK_ARG(g && x && mean && invstd && gamma && mg && mgx && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
+int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
+    MMAD_CHECK_ARG(g && x && coef && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    bn_bwd_apply_kernel<<<grid_for(nvec, 256, 148 * 16), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, mean, invstd, gamma, mg, mgx, (uint4*)dx, nvec, C);
+    bn_bwd_apply_kernel<<<grid_for(nvec, 256, 148 * 16), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {

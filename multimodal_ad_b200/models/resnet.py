@@ -166,15 +166,13 @@ class _Run:
         g = self.empty(x.shape) if want_g else None
         self.chk(self.lib.mmad_bn_bwd_reduce(None if dy_is_f32 else _p(dy), _p(dy) if dy_is_f32 else None, _p(dy2), _p(mask), _p(x),
                                              _p(vec[0]), _p(vec[1]), _p(g), _p(part), rows, c, self.stream), "mmad_bn_bwd_reduce")
-        out = self.empty((4, c), torch.float32)           # dgamma, dbeta, mg, mgx
-        self.chk(self.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
-                                               self.stream), "mmad_bn_bwd_finalize")
-        if not training:                                  # eval-mode BN is an affine map: no batch-statistic terms
-            out[2:].zero_()
+        out = self.empty((2, c), torch.float32)           # dgamma, dbeta
+        coef = self.empty((3, c), torch.float32)
+        self.chk(self.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(gamma), _p(vec[0]), _p(vec[1]), 1 if training else 0,
+                                               _p(out[0]), _p(out[1]), _p(coef), self.stream), "mmad_bn_bwd_finalize")
         dx = self.empty(x.shape)
         src = g if want_g else dy
-        self.chk(self.lib.mmad_bn_bwd_apply(_p(src), _p(x), _p(vec[0]), _p(vec[1]), _p(gamma), _p(out[2]), _p(out[3]), _p(dx),
-                                            rows, c, self.stream), "mmad_bn_bwd_apply")
+        self.chk(self.lib.mmad_bn_bwd_apply(_p(src), _p(x), _p(coef), _p(dx), rows, c, self.stream), "mmad_bn_bwd_apply")
         return dx, g, out[0], out[1]
 
 

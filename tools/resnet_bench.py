@@ -6,7 +6,7 @@ import torch.nn as nn
 from multimodal_ad_b200.models.Resnet3D import generate_model
 from multimodal_ad_b200 import _lib
 
-def main(batch=16, size=128, steps=5, depth=18):
+def main(batch=16, size=128, steps=5, depth=18, warmup=2):
     torch.manual_seed(0)
     model = generate_model(model_depth=depth, input_W=size, input_H=size, input_D=size, nb_class=3, pretrain_path=None,
                            dropout_rate=0.5, device=torch.device("cuda", 0))
@@ -23,7 +23,7 @@ def main(batch=16, size=128, steps=5, depth=18):
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
         opt.step()
         return loss
-    for _ in range(2):
+    for _ in range(warmup):
         l = step()
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
@@ -37,7 +37,7 @@ def main(batch=16, size=128, steps=5, depth=18):
     host_ms = (time.perf_counter() - t0) * 1e3 / steps
     # FLOPs of the convolutions (forward), x3 for fwd + dgrad + wgrad
     print(json.dumps(dict(batch=batch, size=size, ms_per_step=round(ms, 3), host_ms=round(host_ms, 3), vol_per_s=round(batch / ms * 1e3, 1),
-                          loss=float(l), launches_per_step=(_lib.launch_count() - l0) / steps,
+                          loss=float(l.detach()), launches_per_step=(_lib.launch_count() - l0) / steps,
                           mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))), flush=True)
 
 if __name__ == "__main__":
