@@ -52,15 +52,24 @@ __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
 }
 
-// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, k = 7, stride 2, pad 3, column = (kd*7+kh)*7+kw.
-//      One thread per 16-byte chunk (8 columns) of a row; the column -> (kd,kh,kw) split comes from a constant table.
-__constant__ signed char c_tap_d[512], c_tap_h[512], c_tap_w[512];     // -128 = padding column
+// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, stride 2 / pad 3 style geometry, column = (kd*K+kh)*K+kw.
+//      One thread per 16-byte chunk (8 columns) of a row; K is a template parameter so the column -> (kd,kh,kw) split is
+//      multiply-shift arithmetic.
+template <int K>
 __global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
                                                           int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
     const int cpr = Kpad >> 3;                        // chunks per row (48)
     const int rpb = 192 / cpr;                        // rows per block step (4)
     const int chunk = threadIdx.x % cpr, rsub = threadIdx.x / cpr;
     if (rsub >= rpb) return;
+    int kd[8], kh[8], kw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = chunk * 8 + j;
+        kd[j] = c < K * K * K ? c / (K * K) : -1000000;    // padding column: always out of bounds
+        kh[j] = (c / K) % K;
+        kw[j] = c % K;
+    }
     const long long rows = (long long)N * Do * Ho * Wo;
     for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
         long long t = r;
@@ -72,11 +81,9 @@ __global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restric
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = chunk * 8 + j;
-            const int kd = c_tap_d[c];
-            const int id = id0 + kd, ih = ih0 + c_tap_h[c], iw = iw0 + c_tap_w[c];
+            const int id = id0 + kd[j], ih = ih0 + kh[j], iw = iw0 + kw[j];
             float v = 0.f;
-            if (kd >= 0 && (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+            if ((unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
                 v = __ldg(xn + ((long long)id * H + ih) * W + iw);
             f[j] = v;
         }
@@ -426,21 +433,11 @@ int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int 
     const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     MMAD_CHECK_ARG(Kpad <= 512 && 192 % (Kpad / 8) == 0, "stem_im2col: Kpad must be <= 512 and Kpad/8 must divide 192");
     const long long rows = (long long)N * Do * Ho * Wo;
-    static int table_k = 0;
-    if (table_k != k) {                                   // column -> tap offsets
-        signed char td[512], th[512], tw[512];
-        for (int c = 0; c < 512; ++c) {
-            if (c < k * k * k) { td[c] = (signed char)(c / (k * k)); th[c] = (signed char)((c / k) % k); tw[c] = (signed char)(c % k); }
-            else { td[c] = -128; th[c] = 0; tw[c] = 0; }
-        }
-        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_d, td, 512, 0, cudaMemcpyHostToDevice, ST));
-        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_h, th, 512, 0, cudaMemcpyHostToDevice, ST));
-        MMAD_CUDA(cudaMemcpyToSymbolAsync(c_tap_w, tw, 512, 0, cudaMemcpyHostToDevice, ST));
-        MMAD_CUDA(cudaStreamSynchronize(ST));             // the host arrays are on this stack frame
-        table_k = k;
-    }
     const int rpb = 192 / (Kpad / 8);
-    im2col_stem_kernel<<<grid_for((rows + rpb - 1) / rpb, 1, 148 * 32), 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    MMAD_CHECK_ARG(k == 7 || k == 3, "stem_im2col: kernel size 7 (resnet.py:126-132) or 3 supported");
+    const int grid = grid_for((rows + rpb - 1) / rpb, 1, 148 * 32);
+    if (k == 7) im2col_stem_kernel<7><<<grid, 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    else im2col_stem_kernel<3><<<grid, 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
     LAUNCH_OK();
 }
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
