@@ -100,6 +100,137 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def resnet18_conv_flops(batch, size):
+    """Algorithmic conv FLOPs of one ResNet3D-18 training step on 1 x size^3 volumes (resnet.py:126-143): forward +
+    weight gradient for every convolution, + data gradient for all but the stem (its input is data)."""
+    def out(n, k, s, p, d):
+        return (n + 2 * p - d * (k - 1) - 1) // s + 1
+    s1 = out(size, 7, 2, 3, 1)
+    fwd = 2.0 * batch * s1 ** 3 * 64 * 343
+    total = 2 * fwd                                   # stem: forward + wgrad
+    sp = out(s1, 3, 2, 1, 1)                          # maxpool
+    cin = 64
+    for planes, stride, dil in ((64, 1, 1), (128, 2, 1), (256, 1, 2), (512, 1, 4)):
+        for b in range(2):
+            st = stride if b == 0 else 1
+            so = out(sp, 3, st, dil, dil)
+            c1 = 2.0 * batch * so ** 3 * planes * cin * 27
+            c2 = 2.0 * batch * so ** 3 * planes * planes * 27
+            total += 3 * (c1 + c2)
+            if b == 0 and (st != 1 or cin != planes):
+                total += 3 * 2.0 * batch * so ** 3 * planes * cin
+            cin, sp = planes, so
+    return total
+
+
+def run_resnet_train(args, rank, local_rank, world, dev, dist):
+    """BASELINE.json configs[2]: ResNet3D-18 bf16 training, batch 16 per GPU, synthetic 1x128^3, 3 classes, data parallel."""
+    import torch
+    import torch.nn as nn
+
+    from multimodal_ad_b200 import _lib
+    from multimodal_ad_b200.models.Resnet3D import generate_model
+    from multimodal_ad_b200.sharding import GradReducer, max_over_ranks
+
+    batch, size = 16, 128
+    torch.manual_seed(0)                               # same initial weights on every rank
+    model = generate_model(model_depth=18, input_W=size, input_H=size, input_D=size, nb_class=3, pretrain_path=None,
+                           dropout_rate=0.5, device=dev)
+    model.train()
+    reducer = GradReducer()
+    model.grad_reducer = reducer
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
+    crit = nn.CrossEntropyLoss()
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    xs = [torch.rand((batch, 1, size, size, size), device=dev, generator=g) for _ in range(2)]   # 2 x 134 MB
+    ys = [torch.randint(0, 3, (batch,), device=dev, generator=g) for _ in range(2)]
+
+    def step(i, x=None, y=None):
+        out = model(xs[i % 2] if x is None else x)
+        loss = crit(out, ys[i % 2] if y is None else y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer.finish(model.parameters())
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return loss
+
+    steps = max(1, min(args.steps, 10))
+    for i in range(3):
+        step(i)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = step(i)
+    b.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b), dev) / steps
+    launches = (_lib.launch_count() - l0) / steps
+    # end to end: pinned host batch -> device, step, loss back on the host
+    xh, yh = torch.rand((batch, 1, size, size, size)).pin_memory(), torch.randint(0, 3, (batch,)).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(steps, 5))
+    for i in range(n_e2e):
+        float(step(i, xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)).detach())
+    dt = max_over_ranks(time.perf_counter() - t0, dev)
+    flops = resnet18_conv_flops(batch, size)
+    peaks = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peaks = json.load(f)
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = flops / (ms * 1e-3) / 1e12
+    res = {
+        "metric": "resnet3d18_train_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s",
+        "ms_per_step": ms, "steps": steps, "dtype": "bf16", "scaling": "weak",
+        "config": {"workload": "resnet3d18_bf16_train_batch16_1x128^3_3class", "batch_per_gpu": batch,
+                   "parallelism": f"data parallel x{world}, gradient all-reduce overlapped with backward",
+                   "step": "forward + CE loss + backward + grad clip + Adam (train_ResNet3D.py:207-218)"},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained",
+                     "algorithmic_flops_per_step": flops},
+        "e2e": {"value": world * batch * n_e2e / dt, "unit": "volumes/s", "h2d_bytes_per_step": batch * size ** 3 * 4 + batch * 8,
+                "d2h_bytes_per_step": 4, "steps": n_e2e},
+        "gpu_launches": launches, "loss": float(loss.detach()),
+    }
+    del model, opt, xs
+    torch.cuda.empty_cache()
+    return res
+
+
+def resnet_cpu_baseline(seconds_cap=60.0):
+    """BASELINE.json configs[0]: the reference's PyTorch CPU path - ResNet3D-18 forward+backward, batch 2, 1x91x109x91, fp32
+    (oracle/resnet_oracle.py restates resnet.py and is pinned bit-exact against it)."""
+    import torch
+    import torch.nn.functional as F
+
+    from multimodal_ad_b200.models import resnet
+    from oracle.resnet_oracle import classifier_head_oracle, resnet_features_oracle
+
+    torch.manual_seed(0)
+    m = resnet.resnet18(sample_input_D=91, sample_input_H=109, sample_input_W=91, num_seg_classes=1)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    fw, fb = torch.randn(3, 512, requires_grad=True), torch.zeros(3, requires_grad=True)
+    x, y = torch.rand(2, 1, 91, 109, 91), torch.tensor([0, 2])
+    t0 = time.perf_counter()
+    n = 0
+    while n < 1 or (time.perf_counter() - t0 < seconds_cap / 3 and n < 3):
+        loss = F.cross_entropy(classifier_head_oracle(resnet_features_oracle(sd, x, [2, 2, 2, 2], True), fw, fb), y)
+        loss.backward()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": 2 * n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} step(s) of batch 2 x 1x91x109x91 fp32 forward+backward (BASELINE configs[0]) on the host cores"}
+
+
 def reference_step(feats, onehot):
     """One pass of the reference's own per-batch ROI expression on host cores
     (image_features.py:111-114, restated verbatim in oracle/roi_oracle.py; the one-hot
@@ -139,6 +270,11 @@ def run_reference_arm(args, rank: int):
                                    "image_features.py:80-82,111-114 on host cores"},
         "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_resnet:
+        rb = resnet_cpu_baseline()
+        line["resnet3d18_train"] = {"impl": "reference", "metric": "resnet3d18_train_volumes_per_sec", "value": rb["value"],
+                                    "unit": "volumes/s", "cpu_baseline": rb,
+                                    "config": {"workload": "resnet3d18_fp32_cpu_batch2_1x91x109x91 (BASELINE configs[0])"}}
     print(json.dumps(line), flush=True)
 
 
@@ -246,6 +382,12 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
                         "sample": f"{n} single-volume passes (~10 s) of the reference torch expression "
                                   "(image_features.py:80-82,111-114) on the host cores"}
 
+    resnet = None
+    if not args.no_resnet:
+        resnet = run_resnet_train(args, rank, local_rank, world, dev, dist)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            resnet["cpu_baseline"] = resnet_cpu_baseline()
+
     if rank == 0:
         line = {
             "metric": "roi_pool_volumes_per_sec", "value": value, "unit": "volumes/s", "n_gpus": world,
@@ -261,6 +403,7 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,
+            "resnet3d18_train": resnet,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -276,6 +419,7 @@ def main():
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet3D-18 training measurement (second workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

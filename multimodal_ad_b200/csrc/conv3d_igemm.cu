@@ -32,6 +32,18 @@ struct ConvGeom {
     int nout;                     // epilogue staging buffers (1 or 2)
 };
 
+// Bit t set: along this axis, the input box of a tile whose first output coordinate is o0 (tile extent tl) intersects
+// [0, extent) for tap t.  A tap whose box lies entirely in the zero padding contributes nothing: its K-steps are skipped
+// (with dilation 4 on a 16^3 grid that is ~1/6 of the K-steps).
+__device__ __forceinline__ uint32_t tap_axis_mask(int o0, int tl, int extent, int k, int stride, int pad, int dil) {
+    uint32_t m = 0;
+    for (int t = 0; t < k; ++t) {
+        const int lo = o0 * stride - pad + t * dil, hi = lo + (tl - 1) * stride;
+        if (hi >= 0 && lo < extent) m |= 1u << t;
+    }
+    return m;
+}
+
 constexpr int kConvThreads = 256;
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
 constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
@@ -91,10 +103,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int n = r;
                 const int w0 = wt * g.tw * g.stride - g.pad, h0 = ht * g.th * g.stride - g.pad,
                           d0 = dt * g.td * g.stride - g.pad;
+                uint32_t mw = tap_axis_mask(wt * g.tw, g.tw, g.W, g.kw, g.stride, g.pad, g.dil);
+                uint32_t mh = tap_axis_mask(ht * g.th, g.th, g.H, g.kh, g.stride, g.pad, g.dil);
+                uint32_t md = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
+                if (!mw || !mh || !md) mw = mh = md = 0xffffffffu;      // degenerate tile: run everything (all zeros)
                 int tap = 0;
                 for (int a = 0; a < g.kd; ++a)
                     for (int b = 0; b < g.kh; ++b)
-                        for (int c = 0; c < g.kw; ++c, ++tap)
+                        for (int c = 0; c < g.kw; ++c, ++tap) {
+                            if (!((md >> a) & (mh >> b) & (mw >> c) & 1u)) continue;
                             for (int cc = 0; cc < g.kc; ++cc) {
                                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                                 mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
@@ -104,6 +121,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 tma_load_3d(sa + kATileBytes, &tmB, full0 + 8 * s, cc * 64, tap, nt * BN);
                                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                             }
+                        }
             }
         }
     } else if (warp == 1) {
@@ -115,7 +133,19 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int k = 0; k < ksteps; ++k) {
+                // same tap selection as the producer
+                int ksteps_t;
+                {
+                    int r = tile / g.n_tiles;
+                    const int wt = r % g.tiles_w; r /= g.tiles_w;
+                    const int ht = r % g.tiles_h; r /= g.tiles_h;
+                    const int dt = r % g.tiles_d;
+                    const uint32_t mw = tap_axis_mask(wt * g.tw, g.tw, g.W, g.kw, g.stride, g.pad, g.dil);
+                    const uint32_t mh = tap_axis_mask(ht * g.th, g.th, g.H, g.kh, g.stride, g.pad, g.dil);
+                    const uint32_t md = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
+                    ksteps_t = (!mw || !mh || !md) ? ksteps : __popc(mw) * __popc(mh) * __popc(md) * g.kc;
+                }
+                for (int k = 0; k < ksteps_t; ++k) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = stage0 + s * STAGE;

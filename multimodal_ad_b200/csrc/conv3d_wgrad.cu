@@ -30,6 +30,21 @@ struct WgradGeom {
     int nsplit, stages;
 };
 
+// true when the input box of tap (kd,kh,kw) for the voxel chunk at output origin (ow0,oh0,od0) lies entirely in the padding
+__device__ __forceinline__ bool wg_box_oob(const WgradGeom& g, int tap, int ow0, int oh0, int od0) {
+    const int kw = tap % g.k, kh = (tap / g.k) % g.k, kd = tap / (g.k * g.k);
+    const int lw = ow0 * g.stride + kw * g.dil - g.pad, lh = oh0 * g.stride + kh * g.dil - g.pad, ld = od0 * g.stride + kd * g.dil - g.pad;
+    return lw + (g.tw - 1) * g.stride < 0 || lw >= g.W || lh + (g.th - 1) * g.stride < 0 || lh >= g.H ||
+           ld + (g.td - 1) * g.stride < 0 || ld >= g.D;
+}
+// An accumulator block is skipped for a chunk when all of its taps are out of bounds there - except on the first chunk
+// of the K slice, which always runs so that the accumulator gets initialised.
+__device__ __forceinline__ bool wg_skip(const WgradGeom& g, int u, int c, int c_begin, int ow0, int oh0, int od0) {
+    if (c == c_begin) return false;
+    if (g.mode2) return wg_box_oob(g, min(2 * u, g.taps - 1), ow0, oh0, od0) && wg_box_oob(g, min(2 * u + 1, g.taps - 1), ow0, oh0, od0);
+    return wg_box_oob(g, u / g.cib, ow0, oh0, od0);
+}
+
 constexpr int kWgThreads = 256;
 constexpr int kBoxBytes = 64 * 128;   // 64 voxels x 64 channels bf16
 
@@ -75,7 +90,6 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // ============================ TMA producer ============================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            const uint32_t bytes = (uint32_t)(nbox_b + 2 * nu) * kBoxBytes;
             for (int c = c_begin; c < c_end; ++c) {
                 int r = c;
                 const int wt = r % g.tiles_w; r /= g.tiles_w;
@@ -83,11 +97,16 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const int dt = r % g.tiles_d; r /= g.tiles_d;
                 const int n = r;
                 const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
+                uint32_t skip = 0;
+                for (int a = 0; a < nu; ++a) skip |= (wg_skip(g, u0 + a, c, c_begin, ow0, oh0, od0) ? 1u : 0u) << a;
+                if (__popc(skip) == nu) continue;                                  // nothing to do for this chunk
+                const uint32_t bytes = (uint32_t)(nbox_b + 2 * (nu - __popc(skip))) * kBoxBytes;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_arrive_expect_tx(full0 + 8 * s, bytes);
                 const uint32_t sb = base + s * STAGE;
                 for (int j = 0; j < nbox_b; ++j) tma_load_5d(sb + j * kBoxBytes, &tmDY, full0 + 8 * s, nt * g.nb + 64 * j, ow0, oh0, od0, n);
                 for (int a = 0; a < nu; ++a) {
+                    if ((skip >> a) & 1u) continue;
                     const int u = u0 + a;
                     for (int h = 0; h < 2; ++h) {
                         int tap, ci0;
@@ -108,12 +127,21 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const uint32_t idesc = umma_idesc_bf16(128, g.nb, 1, 1);
             uint32_t s = 0, ph = 0;
             for (int c = c_begin; c < c_end; ++c) {
+                int r = c;
+                const int wt = r % g.tiles_w; r /= g.tiles_w;
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r % g.tiles_d;
+                const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
+                uint32_t skip = 0;
+                for (int a = 0; a < nu; ++a) skip |= (wg_skip(g, u0 + a, c, c_begin, ow0, oh0, od0) ? 1u : 0u) << a;
+                if (__popc(skip) == nu) continue;
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t sb = base + s * STAGE;
                 // MN-major SW128: 128-byte rows are K (voxel) indices, 8-row groups 1024 B apart (SBO), 64-wide M/N atoms one box apart (LBO)
                 const uint64_t bdesc = umma_desc_sw128(sb, kBoxBytes, 1024);
                 for (int a = 0; a < nu; ++a) {
+                    if ((skip >> a) & 1u) continue;
                     const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * kBoxBytes, kBoxBytes, 1024);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)                   // K16 = 16 voxel rows = 2048 bytes

@@ -24,18 +24,33 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 static inline int grid_for(long long work, int block, int cap) { return (int)std::max<long long>(1, std::min<long long>((work + block - 1) / block, cap)); }
 
-// ---- weights: torch (Cout, Cin, k,k,k) fp32 -> forward layout [Cout][taps][Cin] bf16 and dgrad layout [Cin][taps][Cout] bf16
-//      (taps reversed: correlation with the flipped kernel).  Cin may be padded up to cin_pad with zeros (stem: 1 -> K=384).
-__global__ void prep_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wt,
-                                    int Cout, int Cin, int taps) {
-    const long long total = (long long)Cout * Cin * taps;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % taps);
-        const int ci = (int)((i / taps) % Cin);
-        const int co = (int)(i / ((long long)taps * Cin));
-        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-        if (wf) wf[((long long)co * taps + tap) * Cin + ci] = v;
-        if (wt) wt[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = v;
+// ---- weights: torch (Cout, Cin, k,k,k) fp32 -> forward layout [Cout][taps][Cin] bf16 (pass 1: per (co, 64-ci chunk) transpose
+//      of the [ci][tap] matrix through shared memory) and dgrad layout [Cin][taps reversed][Cout] bf16 (pass 2: per tap, a
+//      32x32 tiled [co][ci] -> [ci][co] transpose of the forward layout).  Both passes read and write coalesced.
+__global__ void __launch_bounds__(64) prep_weights_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cin, int taps) {
+    extern __shared__ float tile[];                  // [64][taps + 1]
+    const int co = blockIdx.y, c0 = blockIdx.x * 64;
+    const int nci = min(64, Cin - c0);
+    const float* src = w + ((long long)co * Cin + c0) * taps;            // nci * taps contiguous floats
+    for (int i = threadIdx.x; i < nci * taps; i += 64) tile[(i / taps) * (taps + 1) + (i % taps)] = src[i];
+    __syncthreads();
+    if (threadIdx.x < nci)
+        for (int t = 0; t < taps; ++t)
+            wf[((long long)co * taps + t) * Cin + c0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x * (taps + 1) + t]);
+}
+__global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wt, int Cout,
+                                                                 int Cin, int taps) {
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int co = co0 + j, ci = ci0 + tx;
+        if (co < Cout && ci < Cin) tile[j][tx] = wf[((long long)co * taps + tap) * Cin + ci];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int ci = ci0 + j, co = co0 + tx;
+        if (co < Cout && ci < Cin) wt[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = tile[tx][j];
     }
 }
 // stem weights (Cout, 1, 7,7,7) fp32 -> [Cout][Kpad] bf16 (a 1x1x1 conv over the im2col matrix), zero padded
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restr
         idx[i] = p;
     }
 }
-// gather form of the backward: every input voxel collects from the (<= 8) windows that contain it and picked it
+// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it
 __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                                             int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
     const int cv = C >> 3;
@@ -324,29 +339,25 @@ __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restr
         const int ih = (int)(t % H); t /= H;
         const int id = (int)(t % D); t /= D;
         const int n = (int)t;
+        // windows o with 2*o - 1 <= i <= 2*o + 1  <=>  o in [ceil((i-1)/2), floor((i+1)/2)]
+        const int od0 = id >> 1, od1 = min((id + 1) >> 1, Do - 1);
+        const int oh0 = ih >> 1, oh1 = min((ih + 1) >> 1, Ho - 1);
+        const int ow0 = iw >> 1, ow1 = min((iw + 1) >> 1, Wo - 1);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int kd = 0; kd < 3; ++kd) {
-            const int od2 = id + 1 - kd;
-            if (od2 < 0 || (od2 & 1) || (od2 >> 1) >= Do) continue;
-            for (int kh = 0; kh < 3; ++kh) {
-                const int oh2 = ih + 1 - kh;
-                if (oh2 < 0 || (oh2 & 1) || (oh2 >> 1) >= Ho) continue;
-                for (int kw = 0; kw < 3; ++kw) {
-                    const int ow2 = iw + 1 - kw;
-                    if (ow2 < 0 || (ow2 & 1) || (ow2 >> 1) >= Wo) continue;
-                    const long long o = ((((long long)n * Do + (od2 >> 1)) * Ho + (oh2 >> 1)) * Wo + (ow2 >> 1)) * cv + v;
+        for (int od = od0; od <= od1; ++od)
+            for (int oh = oh0; oh <= oh1; ++oh)
+                for (int ow = ow0; ow <= ow1; ++ow) {
+                    const int tap = ((id - 2 * od + 1) * 3 + (ih - 2 * oh + 1)) * 3 + (iw - 2 * ow + 1);
+                    const long long o = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * cv + v;
                     const uint2 p = idx[o];
-                    const int tap = (kd * 3 + kh) * 3 + kw;
                     float f[8];
                     unpack8(dy[o], f);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int w = (int)(((j < 4 ? p.x : p.y) >> (8 * (j & 3))) & 0xffu);
-                        if (w == tap) acc[j] += f[j];
+                        const int wsel = (int)(((j < 4 ? p.x : p.y) >> (8 * (j & 3))) & 0xffu);
+                        if (wsel == tap) acc[j] += f[j];
                     }
                 }
-            }
-        }
         dx[i] = pack8(acc);
     }
 }
@@ -391,17 +402,24 @@ __global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* _
     }
 }
 
-// ---- wgrad epilogue: sum the split-K partials [nsplit][Cout][taps][Cin] fp32 -> torch layout (Cout, Cin, taps) fp32
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin, int taps) {
-    const long long total = (long long)Cout * Cin * taps;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ci = (int)(i % Cin);
-        const int tap = (int)((i / Cin) % taps);
-        const int co = (int)(i / ((long long)Cin * taps));
-        float s = 0.f;
-        for (int p = 0; p < nsplit; ++p) s += part[(size_t)p * total + i];
-        dw[((long long)co * Cin + ci) * taps + tap] = s;
-    }
+// ---- wgrad epilogue: sum the split-K partials [nsplit][Cout][taps][Cin] fp32 -> torch layout (Cout, Cin, taps) fp32.
+//      Block = (co, 64-ci chunk): coalesced reads of [tap][ci] rows, shared-memory transpose, coalesced [ci][tap] writes.
+__global__ void __launch_bounds__(64) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin,
+                                                          int taps) {
+    extern __shared__ float tile[];                  // [taps][65]
+    const int co = blockIdx.y, c0 = blockIdx.x * 64;
+    const int nci = min(64, Cin - c0);
+    const size_t plane = (size_t)Cout * taps * Cin;
+    if (threadIdx.x < nci)
+        for (int t = 0; t < taps; ++t) {
+            const size_t o = ((size_t)co * taps + t) * Cin + c0 + threadIdx.x;
+            float sum = 0.f;
+            for (int p = 0; p < nsplit; ++p) sum += part[(size_t)p * plane + o];
+            tile[t * 65 + threadIdx.x] = sum;
+        }
+    __syncthreads();
+    float* dst = dw + ((size_t)co * Cin + c0) * taps;                    // nci * taps contiguous floats
+    for (int i = threadIdx.x; i < nci * taps; i += 64) dst[i] = tile[(i % taps) * 65 + (i / taps)];
 }
 
 }  // namespace mmad
@@ -414,9 +432,17 @@ extern "C" {
 
 int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && taps > 0, "prep_weights: bad argument");
-    const long long total = (long long)Cout * Cin * taps;
-    prep_weights_kernel<<<grid_for(total, 256, 2048), 256, 0, ST>>>(w, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad, Cout, Cin, taps);
-    LAUNCH_OK();
+    MMAD_CHECK_ARG(w_fwd, "prep_weights: the forward layout is required (the dgrad layout is derived from it)");
+    prep_weights_fwd_kernel<<<dim3((Cin + 63) / 64, Cout), 64, 64 * (taps + 1) * sizeof(float), ST>>>(w, (__nv_bfloat16*)w_fwd, Cin, taps);
+    MMAD_CUDA(cudaGetLastError());
+    count_launch();
+    if (w_dgrad) {
+        prep_weights_dgrad_kernel<<<dim3((Cin + 31) / 32, (Cout + 31) / 32, taps), 256, 0, ST>>>((const __nv_bfloat16*)w_fwd,
+                                                                                              (__nv_bfloat16*)w_dgrad, Cout, Cin, taps);
+        MMAD_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    return MMAD_OK;
 }
 int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream) {
     MMAD_CHECK_ARG(w && w_fwd && K <= Kpad && Kpad % 64 == 0, "stem_prep_weights: bad argument");
@@ -515,8 +541,7 @@ int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, v
 }
 int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
-    const long long total = (long long)Cout * Cin * taps;
-    wgrad_reduce_kernel<<<grid_for(total, 256, 2048), 256, 0, ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 64, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
     LAUNCH_OK();
 }
 

@@ -239,12 +239,26 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     return out32, tape
 
 
+class _GradDict(dict):
+    """{parameter: gradient}; hands each gradient to the model's GradReducer (if any) the moment it is enqueued, so
+    the data-parallel all-reduce overlaps the rest of the backward pass."""
+
+    def __init__(self, reducer):
+        super().__init__()
+        self.reducer = reducer
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v)
+        if self.reducer is not None:
+            self.reducer.push(v)
+
+
 def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):
     """grad_out: gradient w.r.t. the (N,C,D',H',W')-shaped output view.  Returns {parameter: gradient}."""
     r = _Run(grad_out.device)
     lib = r.lib
     training = tape["training"]
-    grads = {}
+    grads = _GradDict(getattr(model, "grad_reducer", None))
     last = tape["blocks"][-1]
     n, do, ho, wo, c = last["out"].shape
     # gradient of the NDHWC fp32 output; accept either memory order of the NCDHW-shaped gradient

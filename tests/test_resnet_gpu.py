@@ -1,0 +1,119 @@
+"""GPU parity of the accelerated 3-D ResNet (forward + backward through the C-ABI) against the torch oracle.
+
+Three comparisons (oracle/resnet_oracle.py explains the modes):
+  * forced   - the oracle graph evaluated at the CUDA path's own stored activations: pins ReLU masks and BatchNorm
+               statistics, so every parameter gradient must agree to bf16 storage accuracy.  This is the parity gate.
+  * emulated - free-running oracle with bf16 rounding at the same points; forward must stay close.
+  * fp32     - the reference's arithmetic; forward within a few 1e-2 (bf16 vs fp32 through the whole depth).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.resnet_oracle import resnet_features_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+def _model(depth, size, seed=0):
+    from multimodal_ad_b200.models import resnet
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(seed)
+    fn = {10: resnet.resnet10, 18: resnet.resnet18, 34: resnet.resnet34}[depth]
+    model = fn(sample_input_D=size, sample_input_H=size, sample_input_W=size, num_seg_classes=1).cuda()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    return model
+
+
+@pytest.mark.parametrize("depth,n,shape", [(10, 2, (32, 32, 32)), (18, 2, (64, 64, 64)), (18, 1, (45, 54, 45)), (34, 1, (32, 32, 32))])
+def test_forward_backward_vs_oracle(depth, n, shape, built_lib):
+    from multimodal_ad_b200.models.resnet import tape_stages
+
+    model = _model(depth, shape[0])
+    layers = [len(l) for l in (model.layer1, model.layer2, model.layer3, model.layer4)]
+    x = torch.rand((n, 1) + shape, device="cuda")
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.train()
+    model.keep_tape = True
+    feats = model.features(x)
+    wgt = torch.randn_like(feats) / feats.numel() ** 0.5
+    (feats * wgt).sum().backward()
+    forced = tape_stages(model, model._last_tape)
+    named = dict(model.named_parameters())
+
+    def oracle(**kw):
+        leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+        out = resnet_features_oracle(leaves, x, layers, True, **kw)
+        (out * wgt).sum().backward()
+        return out.detach(), leaves
+
+    ref, leaves = oracle(emulate_bf16=True, forced=forced)
+    assert feats.shape == ref.shape
+    assert _rel(feats, ref) < 4e-3                                       # one bf16 rounding of the final activation
+    errs = {k: _rel(named[k].grad, v.grad) for k, v in leaves.items() if v.grad is not None and not k.startswith("conv_seg")}
+    assert len(errs) >= 30 and all(named[k].grad is not None for k in errs)
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 4e-2, (worst, errs[worst])                      # bf16 storage noise accumulated over the depth
+    assert float(np.median(list(errs.values()))) < 2e-2                  # north star: 2e-2 in bf16
+    ref_e, _ = oracle(emulate_bf16=True)
+    ref_f, _ = oracle()
+    assert _rel(feats, ref_e) < 5e-2 and _rel(feats, ref_f) < 8e-2
+    # running statistics follow nn.BatchNorm3d
+    c0 = F.conv3d(x.to(torch.bfloat16).float(), sd["conv1.weight"].to(torch.bfloat16).float(), stride=2, padding=3)
+    assert _rel(model.bn1.running_mean, 0.9 * sd["bn1.running_mean"] + 0.1 * c0.mean(dim=(0, 2, 3, 4))) < 5e-3
+    assert int(model.bn1.num_batches_tracked) == 1
+
+
+def test_eval_mode_and_state_dict_roundtrip(built_lib):
+    model = _model(10, 32, seed=3)
+    x = torch.rand(2, 1, 32, 32, 32, device="cuda")
+    model.train()
+    for _ in range(3):
+        model.features(x)                                               # move the running statistics
+    model.eval()
+    with torch.no_grad():
+        y = model.features(x)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = resnet_features_oracle(sd, x, [1, 1, 1, 1], False, emulate_bf16=True)
+    assert _rel(y, ref) < 3e-2
+    from multimodal_ad_b200.models import resnet
+
+    m2 = resnet.resnet10(sample_input_D=32, sample_input_H=32, sample_input_W=32, num_seg_classes=1).cuda().eval()
+    m2.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        assert torch.equal(m2.features(x), y)                           # deterministic forward
+
+
+def test_training_script_step_runs_and_loss_decreases(built_lib):
+    """The loop body of train_ResNet3D.py:207-218 on the drop-in model (generate_model head, CE loss, clip, Adam)."""
+    from multimodal_ad_b200.models.Resnet3D import generate_model
+
+    torch.manual_seed(0)
+    model = generate_model(model_depth=18, input_W=32, input_H=32, input_D=32, nb_class=3, pretrain_path=None,
+                           dropout_rate=0.5, device=torch.device("cuda", 0))
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    crit = torch.nn.CrossEntropyLoss()
+    x = torch.rand(4, 1, 32, 32, 32, device="cuda")
+    y = torch.tensor([0, 1, 2, 1], device="cuda")
+    losses = []
+    for _ in range(12):
+        out = model(x)
+        loss = crit(out, y)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

@@ -1,0 +1,93 @@
+"""Pins oracle/resnet_oracle.py: against the reference's own models/resnet.py when /root/reference is mounted (bit for
+bit on CPU), and against the committed fixture generated from it (tests/golden/gen_resnet_golden.py)."""
+import importlib.util
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.resnet_oracle import resnet_features_oracle
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "resnet10_golden.npz"))
+REF = "/root/reference/models/resnet.py"
+
+
+def _mine(seed=1234):
+    from multimodal_ad_b200.models import resnet
+
+    torch.manual_seed(seed)
+    return resnet.resnet10(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True)
+
+
+def test_module_reproduces_reference_init_and_keys():
+    m = _mine()
+    cs = sum(float(p.double().abs().sum()) for p in m.parameters())
+    assert abs(cs - float(GOLD["init_checksum"])) < 1e-6 * cs          # same construction order, same init calls
+    keys = list(m.state_dict().keys())
+    assert keys[:6] == ["conv1.weight", "bn1.weight", "bn1.bias", "bn1.running_mean", "bn1.running_var", "bn1.num_batches_tracked"]
+    assert "layer2.0.downsample.0.weight" in keys and "layer4.0.bn2.running_var" in keys and "conv_seg.6.weight" in keys
+
+
+def test_oracle_matches_fixture_forward_and_gradients():
+    m = _mine()
+    leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    x, wgt = torch.from_numpy(GOLD["x"]), torch.from_numpy(GOLD["wgt"])
+    feats = resnet_features_oracle(leaves, x, [1, 1, 1, 1], True)
+    assert torch.allclose(feats, torch.from_numpy(GOLD["features"]), rtol=1e-5, atol=1e-6)
+    loss = (feats * wgt).sum()
+    assert abs(loss.item() - float(GOLD["loss"])) < 1e-4 * abs(float(GOLD["loss"])) + 1e-4
+    loss.backward()
+    for k in GOLD.files:
+        if k.startswith("grad__"):
+            g = leaves[k[6:]].grad
+            ref = torch.from_numpy(GOLD[k])
+            assert torch.allclose(g, ref, rtol=1e-3, atol=1e-5 * ref.abs().max().item() + 1e-7), k
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted on this box")
+def test_oracle_is_bit_exact_with_the_live_reference():
+    spec = importlib.util.spec_from_file_location("ref_resnet", REF)
+    ref = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(ref)
+        torch.manual_seed(7)
+        r = ref.resnet18(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True)
+    from multimodal_ad_b200.models import resnet
+
+    m = resnet.resnet18(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True)
+    assert list(m.state_dict().keys()) == list(r.state_dict().keys())
+    m.load_state_dict(r.state_dict())                                   # interchangeable state dicts
+    x = torch.rand(2, 1, 24, 20, 16)
+    r.train()
+    y = r.layer4(r.layer3(r.layer2(r.layer1(r.maxpool(r.relu(r.bn1(r.conv1(x))))))))
+    o = resnet_features_oracle({k: v.clone() for k, v in r.state_dict().items()}, x, [2, 2, 2, 2], True)
+    assert torch.equal(y, o)
+    r.eval()
+    y = r.layer4(r.layer3(r.layer2(r.layer1(r.maxpool(r.relu(r.bn1(r.conv1(x))))))))
+    o = resnet_features_oracle({k: v.clone() for k, v in r.state_dict().items()}, x, [2, 2, 2, 2], False)
+    assert torch.equal(y, o)
+
+
+def test_emulated_and_forced_modes_are_consistent_on_cpu():
+    m = _mine()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(GOLD["x"])
+    a = resnet_features_oracle(sd, x, [1, 1, 1, 1], True, emulate_bf16=True)
+    b = resnet_features_oracle(sd, x, [1, 1, 1, 1], True)
+    assert 1e-4 < ((a - b).norm() / b.norm()).item() < 5e-2            # bf16 storage noise, amplified by depth
+    forced = {"layer2.0.out": torch.zeros(2, 128, 2, 2, 2)}
+    c = resnet_features_oracle(sd, x, [1, 1, 1, 1], True, forced=forced)
+    assert not torch.allclose(c, b)                                       # the substituted stage feeds the rest of the net
+
+
+def test_accelerated_model_refuses_cpu_and_unsupported_variants(built_lib):
+    from multimodal_ad_b200 import _lib
+    from multimodal_ad_b200.models import resnet
+
+    with pytest.raises(_lib.MmadError, match="CUDA"):
+        _mine()(torch.zeros(1, 1, 16, 16, 16))
+    m50 = resnet.resnet50(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1)
+    assert "layer1.0.conv3.weight" in m50.state_dict()

@@ -52,3 +52,55 @@ def test_world_size_2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == "ok"
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multimodal_ad_b200.sharding import GradReducer
+
+        red = GradReducer(large_numel=8)
+        big = torch.full((16,), float(rank + 1))
+        small = [torch.full((3,), float(10 * (rank + 1))), torch.full((2, 2), float(rank))]
+        lin = torch.nn.Linear(2, 1)
+        lin.weight.grad = torch.full((1, 2), float(rank + 5))
+        lin.bias.grad = torch.full((1,), float(rank))
+        red.push(big)
+        for t in small:
+            red.push(t)
+        red.push(big)                                     # pushing the same tensor twice must not reduce it twice
+        red.finish(lin.parameters())
+        assert torch.allclose(big, torch.full((16,), 1.5))
+        assert torch.allclose(small[0], torch.full((3,), 15.0)) and torch.allclose(small[1], torch.full((2, 2), 0.5))
+        assert torch.allclose(lin.weight.grad, torch.full((1, 2), 5.5)) and torch.allclose(lin.bias.grad, torch.full((1,), 0.5))
+        if rank == 0:
+            out.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_world_size_2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == "ok"
+
+
+def test_grad_reducer_is_a_no_op_without_a_process_group():
+    from multimodal_ad_b200.sharding import GradReducer
+
+    red = GradReducer()
+    t = torch.ones(4)
+    red.push(t)
+    red.finish()
+    assert not red.active and torch.equal(t, torch.ones(4))
