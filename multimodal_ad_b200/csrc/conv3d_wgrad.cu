@@ -28,21 +28,29 @@ struct WgradGeom {
     int nb, n_tiles;              // co tile width, number of co tiles
     int nacc, ugroups;            // accumulator blocks per CTA, unit groups
     int nsplit, stages;
+    int can_skip;                 // some (tap, chunk) input box lies entirely in the padding (dilated layers): worth testing
 };
 
-// true when the input box of tap (kd,kh,kw) for the voxel chunk at output origin (ow0,oh0,od0) lies entirely in the padding
-__device__ __forceinline__ bool wg_box_oob(const WgradGeom& g, int tap, int ow0, int oh0, int od0) {
-    const int kw = tap % g.k, kh = (tap / g.k) % g.k, kd = tap / (g.k * g.k);
-    const int lw = ow0 * g.stride + kw * g.dil - g.pad, lh = oh0 * g.stride + kh * g.dil - g.pad, ld = od0 * g.stride + kd * g.dil - g.pad;
-    return lw + (g.tw - 1) * g.stride < 0 || lw >= g.W || lh + (g.th - 1) * g.stride < 0 || lh >= g.H ||
-           ld + (g.td - 1) * g.stride < 0 || ld >= g.D;
+// Per accumulator block: input-box origin offsets of its (up to two) taps, computed once per CTA.
+struct WgTapOff { int w[2], h[2], d[2]; };
+__device__ __forceinline__ void wg_tap_offsets(const WgradGeom& g, int u, WgTapOff& o) {
+    for (int h = 0; h < 2; ++h) {
+        const int tap = g.mode2 ? min(2 * u + h, g.taps - 1) : u / g.cib;
+        o.w[h] = (tap % g.k) * g.dil - g.pad;
+        o.h[h] = ((tap / g.k) % g.k) * g.dil - g.pad;
+        o.d[h] = (tap / (g.k * g.k)) * g.dil - g.pad;
+    }
 }
-// An accumulator block is skipped for a chunk when all of its taps are out of bounds there - except on the first chunk
-// of the K slice, which always runs so that the accumulator gets initialised.
-__device__ __forceinline__ bool wg_skip(const WgradGeom& g, int u, int c, int c_begin, int ow0, int oh0, int od0) {
-    if (c == c_begin) return false;
-    if (g.mode2) return wg_box_oob(g, min(2 * u, g.taps - 1), ow0, oh0, od0) && wg_box_oob(g, min(2 * u + 1, g.taps - 1), ow0, oh0, od0);
-    return wg_box_oob(g, u / g.cib, ow0, oh0, od0);
+// true when the input boxes of both taps of the block lie entirely in the zero padding for the chunk at (ow0,oh0,od0)
+__device__ __forceinline__ bool wg_oob(const WgradGeom& g, const WgTapOff& o, int ow0, int oh0, int od0) {
+    bool all = true;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int lw = ow0 * g.stride + o.w[h], lh = oh0 * g.stride + o.h[h], ld = od0 * g.stride + o.d[h];
+        all &= lw + (g.tw - 1) * g.stride < 0 || lw >= g.W || lh + (g.th - 1) * g.stride < 0 || lh >= g.H ||
+               ld + (g.td - 1) * g.stride < 0 || ld >= g.D;
+    }
+    return all;
 }
 
 constexpr int kWgThreads = 256;
@@ -90,6 +98,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // ============================ TMA producer ============================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
+            WgTapOff toff[4];
+            for (int a = 0; a < nu; ++a) wg_tap_offsets(g, u0 + a, toff[a]);
             for (int c = c_begin; c < c_end; ++c) {
                 int r = c;
                 const int wt = r % g.tiles_w; r /= g.tiles_w;
@@ -97,8 +107,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const int dt = r % g.tiles_d; r /= g.tiles_d;
                 const int n = r;
                 const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
+                // a block is skipped for a chunk whose input boxes are all padding - except on the first chunk of the K
+                // slice, which always runs so that every accumulator gets initialised
                 uint32_t skip = 0;
-                for (int a = 0; a < nu; ++a) skip |= (wg_skip(g, u0 + a, c, c_begin, ow0, oh0, od0) ? 1u : 0u) << a;
+                if (g.can_skip && c != c_begin)
+                    for (int a = 0; a < nu; ++a) skip |= (wg_oob(g, toff[a], ow0, oh0, od0) ? 1u : 0u) << a;
                 if (__popc(skip) == nu) continue;                                  // nothing to do for this chunk
                 const uint32_t bytes = (uint32_t)(nbox_b + 2 * (nu - __popc(skip))) * kBoxBytes;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -109,13 +122,9 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     if ((skip >> a) & 1u) continue;
                     const int u = u0 + a;
                     for (int h = 0; h < 2; ++h) {
-                        int tap, ci0;
-                        if (g.mode2) { tap = min(2 * u + h, g.taps - 1); ci0 = 0; }
-                        else { tap = u / g.cib; ci0 = (u % g.cib) * 128 + 64 * h; }
-                        const int kw = tap % g.k, kh = (tap / g.k) % g.k, kd = tap / (g.k * g.k);
+                        const int ci0 = g.mode2 ? 0 : (u % g.cib) * 128 + 64 * h;
                         tma_load_5d(sb + (uint32_t)(nbox_b + 2 * a + h) * kBoxBytes, &tmX, full0 + 8 * s, ci0,
-                                    ow0 * g.stride + kw * g.dil - g.pad, oh0 * g.stride + kh * g.dil - g.pad,
-                                    od0 * g.stride + kd * g.dil - g.pad, n);
+                                    ow0 * g.stride + toff[a].w[h], oh0 * g.stride + toff[a].h[h], od0 * g.stride + toff[a].d[h], n);
                     }
                 }
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -126,14 +135,18 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, g.nb, 1, 1);
             uint32_t s = 0, ph = 0;
+            WgTapOff toff[4];
+            for (int a = 0; a < nu; ++a) wg_tap_offsets(g, u0 + a, toff[a]);
             for (int c = c_begin; c < c_end; ++c) {
-                int r = c;
-                const int wt = r % g.tiles_w; r /= g.tiles_w;
-                const int ht = r % g.tiles_h; r /= g.tiles_h;
-                const int dt = r % g.tiles_d;
-                const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
                 uint32_t skip = 0;
-                for (int a = 0; a < nu; ++a) skip |= (wg_skip(g, u0 + a, c, c_begin, ow0, oh0, od0) ? 1u : 0u) << a;
+                if (g.can_skip && c != c_begin) {
+                    int r = c;
+                    const int wt = r % g.tiles_w; r /= g.tiles_w;
+                    const int ht = r % g.tiles_h; r /= g.tiles_h;
+                    const int dt = r % g.tiles_d;
+                    const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
+                    for (int a = 0; a < nu; ++a) skip |= (wg_oob(g, toff[a], ow0, oh0, od0) ? 1u : 0u) << a;
+                }
                 if (__popc(skip) == nu) continue;
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
@@ -240,6 +253,15 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
     g.nsplit = best_s;
     const int stage = (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     g.stages = std::max(2, std::min(6, (227 * 1024 - 1024 - 256) / stage));
+    // is any (tap, chunk origin) input box entirely padding along some axis?  (only then is the per-chunk test worth running)
+    g.can_skip = 0;
+    const int ext[3] = {W, H, D}, tl[3] = {g.tw, g.th, g.td}, nt[3] = {g.tiles_w, g.tiles_h, g.tiles_d};
+    for (int ax = 0; ax < 3 && !g.can_skip; ++ax)
+        for (int t = 0; t < k && !g.can_skip; ++t)
+            for (int i = 0; i < nt[ax]; ++i) {
+                const int lo = i * tl[ax] * stride + t * dil - pad;
+                if (lo + (tl[ax] - 1) * stride < 0 || lo >= ext[ax]) { g.can_skip = 1; break; }
+            }
     return 0;
 }
 

@@ -67,42 +67,46 @@ __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
 }
 
-// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, stride 2 / pad 3 style geometry, column = (kd*K+kh)*K+kw.
-//      One thread per 16-byte chunk (8 columns) of a row; K is a template parameter so the column -> (kd,kh,kw) split is
-//      multiply-shift arithmetic.
+// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, column = (kd*K+kh)*K+kw, zero padded to Kpad.
+//      A block produces a strip of 32 consecutive output voxels along W: the K*K input row segments the strip touches
+//      are staged once in shared memory (coalesced, zero filled outside the volume), then every thread assembles
+//      16-byte chunks (8 columns) of the strip's rows from shared memory; rows are written as contiguous 768-byte lines.
 template <int K>
-__global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
+__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
                                                           int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
-    const int cpr = Kpad >> 3;                        // chunks per row (48)
-    const int rpb = 192 / cpr;                        // rows per block step (4)
-    const int chunk = threadIdx.x % cpr, rsub = threadIdx.x / cpr;
-    if (rsub >= rpb) return;
-    int kd[8], kh[8], kw[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = chunk * 8 + j;
-        kd[j] = c < K * K * K ? c / (K * K) : -1000000;    // padding column: always out of bounds
-        kh[j] = (c / K) % K;
-        kw[j] = c % K;
+    constexpr int STRIP = 32;
+    extern __shared__ float seg[];                    // [K*K][segw]
+    const int segw = (STRIP - 1) * stride + K;
+    const int strips = (Wo + STRIP - 1) / STRIP;
+    int b = blockIdx.x;
+    const int sw = b % strips; b /= strips;
+    const int oh = b % Ho; b /= Ho;
+    const int od = b % Do; b /= Do;
+    const int n = b;
+    const int ow0 = sw * STRIP;
+    const int iw0 = ow0 * stride - pad, ih0 = oh * stride - pad, id0 = od * stride - pad;
+    const float* xn = x + (long long)n * D * H * W;
+    for (int i = threadIdx.x; i < K * K * segw; i += 256) {
+        const int r = i / segw, c = i - r * segw;
+        const int id = id0 + r / K, ih = ih0 + r % K, iw = iw0 + c;
+        float v = 0.f;
+        if ((unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+            v = __ldg(xn + ((long long)id * H + ih) * W + iw);
+        seg[i] = v;
     }
-    const long long rows = (long long)N * Do * Ho * Wo;
-    for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += (long long)gridDim.x * rpb) {
-        long long t = r;
-        const int ow = (int)(t % Wo); t /= Wo;
-        const int oh = (int)(t % Ho); t /= Ho;
-        const int od = (int)(t % Do); t /= Do;
-        const float* xn = x + t * (long long)D * H * W;
-        const int iw0 = ow * stride - pad, ih0 = oh * stride - pad, id0 = od * stride - pad;
+    __syncthreads();
+    const int cpr = Kpad >> 3;
+    const int nrows = min(STRIP, Wo - ow0);
+    const long long row0 = (((long long)n * Do + od) * Ho + oh) * Wo + ow0;
+    for (int item = threadIdx.x; item < nrows * cpr; item += 256) {
+        const int r = item / cpr, chunk = item - r * cpr;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int id = id0 + kd[j], ih = ih0 + kh[j], iw = iw0 + kw[j];
-            float v = 0.f;
-            if ((unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-                v = __ldg(xn + ((long long)id * H + ih) * W + iw);
-            f[j] = v;
+            const int c = chunk * 8 + j;
+            f[j] = c < K * K * K ? seg[(c / K) * segw + r * stride + c % K] : 0.f;      // c / K == kd*K + kh
         }
-        *reinterpret_cast<uint4*>(col + r * Kpad + chunk * 8) = pack8(f);
+        *reinterpret_cast<uint4*>(col + (row0 + r) * Kpad + chunk * 8) = pack8(f);
     }
 }
 
@@ -157,8 +161,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const float* __restrict__ rshift, uint4* __restrict__ out_bf16,
                                                        float4* __restrict__ out_f32, long long nvec, int C) {
     const int cv = C >> 3;
+    const bool p2 = (cv & (cv - 1)) == 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cv) * 8;
+        const int c0 = (p2 ? (int)((unsigned)i & (unsigned)(cv - 1)) : (int)(i % cv)) * 8;
         float f[8];
         unpack8(x[i], f);
         const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
@@ -274,8 +279,9 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ coef,
                                                            uint4* __restrict__ dx, long long nvec, int C) {
     const int cv = C >> 3;
+    const bool p2 = (cv & (cv - 1)) == 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cv) * 8;
+        const int c0 = (p2 ? (int)((unsigned)i & (unsigned)(cv - 1)) : (int)(i % cv)) * 8;
         float gv[8], xv[8], o[8];
         unpack8(g[i], gv);
         unpack8(x[i], xv);
@@ -331,13 +337,13 @@ __global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restr
 __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                                             int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
     const int cv = C >> 3;
-    const long long total = (long long)N * D * H * W * cv;
+    const long long total = (long long)N * D * H * W * cv;       // < 2^32 checked by the host wrapper
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;
-        const int v = (int)(t % cv); t /= cv;
-        const int iw = (int)(t % W); t /= W;
-        const int ih = (int)(t % H); t /= H;
-        const int id = (int)(t % D); t /= D;
+        unsigned t = (unsigned)i;
+        const int v = (int)(t % (unsigned)cv); t /= (unsigned)cv;
+        const int iw = (int)(t % (unsigned)W); t /= (unsigned)W;
+        const int ih = (int)(t % (unsigned)H); t /= (unsigned)H;
+        const int id = (int)(t % (unsigned)D); t /= (unsigned)D;
         const int n = (int)t;
         // windows o with 2*o - 1 <= i <= 2*o + 1  <=>  o in [ceil((i-1)/2), floor((i+1)/2)]
         const int od0 = id >> 1, od1 = min((id + 1) >> 1, Do - 1);
@@ -403,23 +409,30 @@ __global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* _
 }
 
 // ---- wgrad epilogue: sum the split-K partials [nsplit][Cout][taps][Cin] fp32 -> torch layout (Cout, Cin, taps) fp32.
-//      Block = (co, 64-ci chunk): coalesced reads of [tap][ci] rows, shared-memory transpose, coalesced [ci][tap] writes.
-__global__ void __launch_bounds__(64) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin,
-                                                          int taps) {
+//      Block = (co, 64-ci chunk), 256 threads: coalesced reads of the [tap][ci] rows of every split (4 independent partial
+//      sums per thread), shared-memory transpose, coalesced [ci][tap] writes.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin,
+                                                           int taps) {
     extern __shared__ float tile[];                  // [taps][65]
     const int co = blockIdx.y, c0 = blockIdx.x * 64;
     const int nci = min(64, Cin - c0);
     const size_t plane = (size_t)Cout * taps * Cin;
-    if (threadIdx.x < nci)
-        for (int t = 0; t < taps; ++t) {
-            const size_t o = ((size_t)co * taps + t) * Cin + c0 + threadIdx.x;
-            float sum = 0.f;
-            for (int p = 0; p < nsplit; ++p) sum += part[(size_t)p * plane + o];
-            tile[t * 65 + threadIdx.x] = sum;
+    for (int e = threadIdx.x; e < taps * 64; e += 256) {
+        const int t = e >> 6, c = e & 63;
+        if (c >= nci) continue;
+        const float* src = part + ((size_t)co * taps + t) * Cin + c0 + c;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = 0;
+        for (; p + 4 <= nsplit; p += 4) {
+            s0 += src[(size_t)p * plane]; s1 += src[(size_t)(p + 1) * plane];
+            s2 += src[(size_t)(p + 2) * plane]; s3 += src[(size_t)(p + 3) * plane];
         }
+        for (; p < nsplit; ++p) s0 += src[(size_t)p * plane];
+        tile[t * 65 + c] = (s0 + s1) + (s2 + s3);
+    }
     __syncthreads();
     float* dst = dw + ((size_t)co * Cin + c0) * taps;                    // nci * taps contiguous floats
-    for (int i = threadIdx.x; i < nci * taps; i += 64) dst[i] = tile[(i % taps) * 65 + (i / taps)];
+    for (int i = threadIdx.x; i < nci * taps; i += 256) dst[i] = tile[(i % taps) * 65 + (i / taps)];
 }
 
 }  // namespace mmad
@@ -457,13 +470,13 @@ int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, in
 int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int k, int stride, int pad, int Kpad, void* stream) {
     MMAD_CHECK_ARG(x && col && Kpad % 8 == 0 && k * k * k <= Kpad, "stem_im2col: bad argument");
     const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    MMAD_CHECK_ARG(Kpad <= 512 && 192 % (Kpad / 8) == 0, "stem_im2col: Kpad must be <= 512 and Kpad/8 must divide 192");
-    const long long rows = (long long)N * Do * Ho * Wo;
-    const int rpb = 192 / (Kpad / 8);
     MMAD_CHECK_ARG(k == 7 || k == 3, "stem_im2col: kernel size 7 (resnet.py:126-132) or 3 supported");
-    const int grid = grid_for((rows + rpb - 1) / rpb, 1, 148 * 32);
-    if (k == 7) im2col_stem_kernel<7><<<grid, 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
-    else im2col_stem_kernel<3><<<grid, 192, 0, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    const long long blocks = (long long)N * Do * Ho * ((Wo + 31) / 32);
+    MMAD_CHECK_ARG(blocks < (1ll << 31), "stem_im2col: too many output strips");
+    const int segw = 31 * stride + k;
+    const size_t smem = (size_t)k * k * segw * sizeof(float);
+    if (k == 7) im2col_stem_kernel<7><<<(unsigned)blocks, 256, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    else im2col_stem_kernel<3><<<(unsigned)blocks, 256, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
     LAUNCH_OK();
 }
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
@@ -524,6 +537,7 @@ int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, 
     MMAD_CHECK_ARG(dy && dx && idx && C % 8 == 0, "maxpool3d_bwd: bad argument");
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * D * H * W * (C / 8);
+    MMAD_CHECK_ARG(total < (1ll << 32), "maxpool3d_bwd: tensor too large for 32-bit indexing");
     maxpool3d_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo);
     LAUNCH_OK();
 }
@@ -541,7 +555,7 @@ int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, v
 }
 int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
-    wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 64, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 256, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
     LAUNCH_OK();
 }
 
