@@ -9,7 +9,9 @@
 //   K-step:      ONE 5-D TMA box of the input (tap offset, dilation and stride folded into the box origin /
 //                element strides; zero padding = TMA out-of-bounds fill) + ONE 3-D box of the weights,
 //                then 4 x tcgen05.mma (M128 x BN x K16), fp32 accumulators in TMEM.
-//   Warp roles:  warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator, warps 4-7 epilogue
+//   Warp roles:  warps 0, 2, 3 TMA producers (one elected thread each issues one cp.async.bulk.tensor per ~300 cycles, so
+//                K-steps are dealt round-robin to three issuing warps), warp 1 MMA issuer (one thread), warp 2 also
+//                allocates TMEM, warps 4-7 epilogue
 //                (tcgen05.ld -> bf16 -> swizzled smem -> TMA store; per-channel sum / sum-of-squares of the stored
 //                bf16 values for the BatchNorm that follows).  Two TMEM accumulator buffers, persistent CTAs.
 #include "tc_common.cuh"
@@ -45,6 +47,7 @@ __device__ __forceinline__ uint32_t tap_axis_mask(int o0, int tl, int extent, in
 }
 
 constexpr int kConvThreads = 256;
+constexpr int kConvProducers = 3;          // warps 0, 2, 3
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
 constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
 
@@ -90,10 +93,11 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int taps = g.kd * g.kh * g.kw;
     const int ksteps = taps * g.kc;
 
-    if (warp == 0) {
-        // ============================ TMA producer ============================
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ============================ TMA producers: K-step i is issued by producer i % 3 ============================
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+            uint32_t s = 0, ph = 0, turn = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
                 int r = mt;
@@ -113,12 +117,15 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int c = 0; c < g.kw; ++c, ++tap) {
                             if (!((md >> a) & (mh >> b) & (mw >> c) & 1u)) continue;
                             for (int cc = 0; cc < g.kc; ++cc) {
-                                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                                mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
-                                const uint32_t sa = stage0 + s * STAGE;
-                                tma_load_5d(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
-                                            d0 + a * g.dil, n);
-                                tma_load_3d(sa + kATileBytes, &tmB, full0 + 8 * s, cc * 64, tap, nt * BN);
+                                if (turn == me) {
+                                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                    mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
+                                    const uint32_t sa = stage0 + s * STAGE;
+                                    tma_load_5d(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
+                                                d0 + a * g.dil, n);
+                                    tma_load_3d(sa + kATileBytes, &tmB, full0 + 8 * s, cc * 64, tap, nt * BN);
+                                }
+                                if (++turn == kConvProducers) turn = 0;
                                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                             }
                         }

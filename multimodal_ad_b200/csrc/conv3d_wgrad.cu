@@ -13,6 +13,7 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace mmad {
 
@@ -54,6 +55,7 @@ __device__ __forceinline__ bool wg_oob(const WgradGeom& g, const WgTapOff& o, in
 }
 
 constexpr int kWgThreads = 256;
+constexpr int kWgProducers = 3;       // warps 0, 2, 3: one elected thread issues ~1 TMA op per 300 cycles, so chunks are dealt round-robin
 constexpr int kBoxBytes = 64 * 128;   // 64 voxels x 64 channels bf16
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -94,10 +96,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    if (warp == 0) {
-        // ============================ TMA producer ============================
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ============================ TMA producers: executed chunk i is issued by producer i % 3 ============================
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+            uint32_t s = 0, ph = 0, turn = 0;
             WgTapOff toff[4];
             for (int a = 0; a < nu; ++a) wg_tap_offsets(g, u0 + a, toff[a]);
             for (int c = c_begin; c < c_end; ++c) {
@@ -113,20 +116,23 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (g.can_skip && c != c_begin)
                     for (int a = 0; a < nu; ++a) skip |= (wg_oob(g, toff[a], ow0, oh0, od0) ? 1u : 0u) << a;
                 if (__popc(skip) == nu) continue;                                  // nothing to do for this chunk
-                const uint32_t bytes = (uint32_t)(nbox_b + 2 * (nu - __popc(skip))) * kBoxBytes;
-                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                mbar_arrive_expect_tx(full0 + 8 * s, bytes);
-                const uint32_t sb = base + s * STAGE;
-                for (int j = 0; j < nbox_b; ++j) tma_load_5d(sb + j * kBoxBytes, &tmDY, full0 + 8 * s, nt * g.nb + 64 * j, ow0, oh0, od0, n);
-                for (int a = 0; a < nu; ++a) {
-                    if ((skip >> a) & 1u) continue;
-                    const int u = u0 + a;
-                    for (int h = 0; h < 2; ++h) {
-                        const int ci0 = g.mode2 ? 0 : (u % g.cib) * 128 + 64 * h;
-                        tma_load_5d(sb + (uint32_t)(nbox_b + 2 * a + h) * kBoxBytes, &tmX, full0 + 8 * s, ci0,
-                                    ow0 * g.stride + toff[a].w[h], oh0 * g.stride + toff[a].h[h], od0 * g.stride + toff[a].d[h], n);
+                if (turn == me) {
+                    const uint32_t bytes = (uint32_t)(nbox_b + 2 * (nu - __popc(skip))) * kBoxBytes;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                    const uint32_t sb = base + s * STAGE;
+                    for (int j = 0; j < nbox_b; ++j) tma_load_5d(sb + j * kBoxBytes, &tmDY, full0 + 8 * s, nt * g.nb + 64 * j, ow0, oh0, od0, n);
+                    for (int a = 0; a < nu; ++a) {
+                        if ((skip >> a) & 1u) continue;
+                        const int u = u0 + a;
+                        for (int h = 0; h < 2; ++h) {
+                            const int ci0 = g.mode2 ? 0 : (u % g.cib) * 128 + 64 * h;
+                            tma_load_5d(sb + (uint32_t)(nbox_b + 2 * a + h) * kBoxBytes, &tmX, full0 + 8 * s, ci0,
+                                        ow0 * g.stride + toff[a].w[h], oh0 * g.stride + toff[a].h[h], od0 * g.stride + toff[a].d[h], n);
+                        }
                     }
                 }
+                if (++turn == kWgProducers) turn = 0;
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }
@@ -237,15 +243,17 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
     g.nb = std::min(256, Cout);
     g.n_tiles = Cout / g.nb;
     g.nacc = g.nb == 256 ? 2 : (g.nb == 128 ? 3 : 4);
+    if (const char* e = getenv("MMAD_WG_NACC")) g.nacc = std::max(1, std::min(g.nacc, atoi(e)));   // tuning knob
     g.nacc = std::min(g.nacc, g.units);
     g.ugroups = (g.units + g.nacc - 1) / g.nacc;
     const int items = g.n_tiles * g.ugroups;
     // split count: at least ~2 waves of CTAs, and a grid that fills whole waves (the last wave is the tail)
     int best_s = 1;
     double best_score = -1.0;
-    for (int sp = 1; sp <= 96 && sp <= g.n_chunks; ++sp) {
+    const int sp_max = std::min(g.n_chunks, std::max(96, (4 * sms + items - 1) / items));
+    for (int sp = 1; sp <= sp_max; ++sp) {
         const long long ctas = (long long)items * sp;
-        if (ctas < 2LL * sms && sp < std::min(96, g.n_chunks)) continue;
+        if (ctas < 2LL * sms && sp < sp_max) continue;
         const long long waves = (ctas + sms - 1) / sms;
         const double score = (double)ctas / (double)(waves * sms) - 0.004 * sp;
         if (score > best_score) { best_score = score; best_s = sp; }
@@ -253,6 +261,7 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
     g.nsplit = best_s;
     const int stage = (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     g.stages = std::max(2, std::min(6, (227 * 1024 - 1024 - 256) / stage));
+    if (const char* e = getenv("MMAD_WG_STAGES")) g.stages = std::max(1, std::min(g.stages, atoi(e)));   // tuning knob
     // is any (tap, chunk origin) input box entirely padding along some axis?  (only then is the per-chunk test worth running)
     g.can_skip = 0;
     const int ext[3] = {W, H, D}, tl[3] = {g.tw, g.th, g.td}, nt[3] = {g.tiles_w, g.tiles_h, g.tiles_d};
