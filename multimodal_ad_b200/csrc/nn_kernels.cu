@@ -72,10 +72,10 @@ __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __
 //      are staged once in shared memory (coalesced, zero filled outside the volume), then every thread assembles
 //      16-byte chunks (8 columns) of the strip's rows from shared memory; rows are written as contiguous 768-byte lines.
 template <int K>
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
+__global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
                                                           int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
     constexpr int STRIP = 32;
-    extern __shared__ float seg[];                    // [K*K][segw]
+    extern __shared__ float seg[];                    // [K*K][segw] + one zero word for the padding columns
     const int segw = (STRIP - 1) * stride + K;
     const int strips = (Wo + STRIP - 1) / STRIP;
     int b = blockIdx.x;
@@ -86,27 +86,36 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
     const int ow0 = sw * STRIP;
     const int iw0 = ow0 * stride - pad, ih0 = oh * stride - pad, id0 = od * stride - pad;
     const float* xn = x + (long long)n * D * H * W;
-    for (int i = threadIdx.x; i < K * K * segw; i += 256) {
-        const int r = i / segw, c = i - r * segw;
-        const int id = id0 + r / K, ih = ih0 + r % K, iw = iw0 + c;
-        float v = 0.f;
-        if ((unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
-            v = __ldg(xn + ((long long)id * H + ih) * W + iw);
-        seg[i] = v;
+    const int nseg = K * K * segw;
+    for (int r = threadIdx.x / 32; r < K * K; r += 6) {          // one warp per (kd,kh) row segment: coalesced reads
+        const int id = id0 + r / K, ih = ih0 + r % K;
+        const bool rowok = (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H;
+        const float* src = xn + ((long long)id * H + ih) * W;
+        for (int c = threadIdx.x & 31; c < segw; c += 32) {
+            const int iw = iw0 + c;
+            seg[r * segw + c] = (rowok && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
+        }
+    }
+    if (threadIdx.x == 0) seg[nseg] = 0.f;
+    // this thread's chunk (8 columns) and their shared-memory offsets, fixed for the whole strip
+    const int cpr = Kpad >> 3;                        // 48 chunks per row, 192 threads = 4 rows at a time
+    const int chunk = threadIdx.x % cpr, rsub = threadIdx.x / cpr, rstep = 192 / cpr;
+    int off[8], mul[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = chunk * 8 + j;
+        const bool real = c < K * K * K;
+        off[j] = real ? (c / K) * segw + c % K : nseg;           // c / K == kd*K + kh
+        mul[j] = real ? stride : 0;
     }
     __syncthreads();
-    const int cpr = Kpad >> 3;
     const int nrows = min(STRIP, Wo - ow0);
-    const long long row0 = (((long long)n * Do + od) * Ho + oh) * Wo + ow0;
-    for (int item = threadIdx.x; item < nrows * cpr; item += 256) {
-        const int r = item / cpr, chunk = item - r * cpr;
+    __nv_bfloat16* dst = col + ((((long long)n * Do + od) * Ho + oh) * Wo + ow0) * Kpad + chunk * 8;
+    for (int r = rsub; r < nrows; r += rstep) {
         float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = chunk * 8 + j;
-            f[j] = c < K * K * K ? seg[(c / K) * segw + r * stride + c % K] : 0.f;      // c / K == kd*K + kh
-        }
-        *reinterpret_cast<uint4*>(col + (row0 + r) * Kpad + chunk * 8) = pack8(f);
+        for (int j = 0; j < 8; ++j) f[j] = seg[off[j] + r * mul[j]];
+        *reinterpret_cast<uint4*>(dst + (long long)r * Kpad) = pack8(f);
     }
 }
 
@@ -333,7 +342,8 @@ __global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restr
         idx[i] = p;
     }
 }
-// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it
+// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it.
+// The eight candidate (index, gradient) pairs are loaded up front (predicated) so their latencies overlap.
 __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                                             int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
     const int cv = C >> 3;
@@ -345,25 +355,33 @@ __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restr
         const int ih = (int)(t % (unsigned)H); t /= (unsigned)H;
         const int id = (int)(t % (unsigned)D); t /= (unsigned)D;
         const int n = (int)t;
-        // windows o with 2*o - 1 <= i <= 2*o + 1  <=>  o in [ceil((i-1)/2), floor((i+1)/2)]
-        const int od0 = id >> 1, od1 = min((id + 1) >> 1, Do - 1);
-        const int oh0 = ih >> 1, oh1 = min((ih + 1) >> 1, Ho - 1);
-        const int ow0 = iw >> 1, ow1 = min((iw + 1) >> 1, Wo - 1);
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int od = od0; od <= od1; ++od)
-            for (int oh = oh0; oh <= oh1; ++oh)
-                for (int ow = ow0; ow <= ow1; ++ow) {
-                    const int tap = ((id - 2 * od + 1) * 3 + (ih - 2 * oh + 1)) * 3 + (iw - 2 * ow + 1);
-                    const long long o = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * cv + v;
-                    const uint2 p = idx[o];
-                    float f[8];
-                    unpack8(dy[o], f);
+        // windows o with 2*o - 1 <= i <= 2*o + 1: o = i >> 1, and (for odd i) o + 1
+        const int o_d[2] = {id >> 1, (id + 1) >> 1}, o_h[2] = {ih >> 1, (ih + 1) >> 1}, o_w[2] = {iw >> 1, (iw + 1) >> 1};
+        const bool v_d[2] = {true, (id & 1) && o_d[1] < Do}, v_h[2] = {true, (ih & 1) && o_h[1] < Ho}, v_w[2] = {true, (iw & 1) && o_w[1] < Wo};
+        uint2 pi[8];
+        uint4 gy[8];
+        int tap[8];
+        bool ok[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int wsel = (int)(((j < 4 ? p.x : p.y) >> (8 * (j & 3))) & 0xffu);
-                        if (wsel == tap) acc[j] += f[j];
-                    }
-                }
+        for (int q = 0; q < 8; ++q) {
+            const int a = q >> 2, b = (q >> 1) & 1, c = q & 1;
+            ok[q] = v_d[a] && v_h[b] && v_w[c];
+            tap[q] = ((id - 2 * o_d[a] + 1) * 3 + (ih - 2 * o_h[b] + 1)) * 3 + (iw - 2 * o_w[c] + 1);
+            const long long o = ((((long long)n * Do + o_d[a]) * Ho + o_h[b]) * Wo + o_w[c]) * cv + v;
+            pi[q] = ok[q] ? idx[o] : make_uint2(0xffffffffu, 0xffffffffu);
+            gy[q] = ok[q] ? dy[o] : make_uint4(0, 0, 0, 0);
+        }
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float f[8];
+            unpack8(gy[q], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int wsel = (int)(((j < 4 ? pi[q].x : pi[q].y) >> (8 * (j & 3))) & 0xffu);
+                acc[j] += wsel == tap[q] ? f[j] : 0.f;
+            }
+        }
         dx[i] = pack8(acc);
     }
 }
@@ -474,9 +492,10 @@ int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int 
     const long long blocks = (long long)N * Do * Ho * ((Wo + 31) / 32);
     MMAD_CHECK_ARG(blocks < (1ll << 31), "stem_im2col: too many output strips");
     const int segw = 31 * stride + k;
-    const size_t smem = (size_t)k * k * segw * sizeof(float);
-    if (k == 7) im2col_stem_kernel<7><<<(unsigned)blocks, 256, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
-    else im2col_stem_kernel<3><<<(unsigned)blocks, 256, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    MMAD_CHECK_ARG(192 % (Kpad / 8) == 0, "stem_im2col: Kpad / 8 must divide 192 (Kpad = 384)");
+    const size_t smem = ((size_t)k * k * segw + 1) * sizeof(float);
+    if (k == 7) im2col_stem_kernel<7><<<(unsigned)blocks, 192, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    else im2col_stem_kernel<3><<<(unsigned)blocks, 192, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
     LAUNCH_OK();
 }
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
