@@ -182,6 +182,22 @@ int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef,
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
 int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream);
 
+/* Fused stem (resnet.py:205-208 after conv1): p = maxpool3d(relu(bn(c)), 3, 2, 1)
+ * in one pass over the conv output c (N,D,H,W,C) bf16; the post-ReLU tensor is
+ * never stored.  Backward: the max-pool gradient gather and the ReLU mask are
+ * recomputed inside both BatchNorm-backward passes (reduce: partial sums of g
+ * and g*xhat, float[mmad_stem_bwd_partials][C][2], feed mmad_bn_bwd_finalize;
+ * apply: dc = coef0*g + coef1*c + coef2).  dp (+ optional dp2) is the gradient
+ * of the pooled tensor; vec = float[4][C] (mean, invstd, scale, shift). */
+int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float* shift,
+                                  void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
+int mmad_stem_bwd_partials(int N, int D, int H, int W, int C);
+int mmad_stem_bwd_reduce(const void* dp, const void* dp2, const void* idx, const void* c,
+                         const float* vec, float* partials, int N, int D, int H, int W, int C, void* stream);
+int mmad_stem_bwd_apply(const void* dp, const void* dp2, const void* idx, const void* c,
+                        const float* vec, const float* coef, void* dc,
+                        int N, int D, int H, int W, int C, void* stream);
+
 /* y[2*o] = x[o], zero elsewhere: dgrad of a stride-2 convolution is the
  * unit-stride convolution of this with the flipped kernel. */
 int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx,

@@ -78,6 +78,10 @@ def load() -> ctypes.CDLL:
         "mmad_maxpool3d_fwd": [P, P, P, I, I, I, I, I, P],
         "mmad_maxpool3d_bwd": [P, P, P, I, I, I, I, I, P],
         "mmad_upsample_zero2": [P, P] + [I] * 8 + [P],
+        "mmad_stem_bn_relu_maxpool_fwd": [P, P, P, P, P, I, I, I, I, I, P],
+        "mmad_stem_bwd_partials": [I] * 5,
+        "mmad_stem_bwd_reduce": [P, P, P, P, P, P, I, I, I, I, I, P],
+        "mmad_stem_bwd_apply": [P, P, P, P, P, P, P, I, I, I, I, I, P],
         "mmad_ncs_f32_to_nsc_bf16": [P, P, I, I, L, P],
     }
     for name, args in sigs.items():

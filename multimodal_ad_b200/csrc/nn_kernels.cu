@@ -342,8 +342,41 @@ __global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restr
         idx[i] = p;
     }
 }
-// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it.
-// The eight candidate (index, gradient) pairs are loaded up front (predicated) so their latencies overlap.
+// gradient of the max-pool w.r.t. one input voxel vector (8 channels): sum of (dp [+ dp2]) over the <= 8 windows that
+// contain the voxel and picked it.  id, ih are block-uniform in the callers, so only the w loop can diverge.
+__device__ __forceinline__ void stem_pool_gather(const uint4* __restrict__ dp, const uint4* __restrict__ dp2, const uint2* __restrict__ idx,
+                                                 int n, int id, int ih, int iw, int v, int cv, int Do, int Ho, int Wo, float (&g)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    const int od1 = ((id & 1) && ((id + 1) >> 1) < Do) ? (id + 1) >> 1 : id >> 1;
+    const int oh1 = ((ih & 1) && ((ih + 1) >> 1) < Ho) ? (ih + 1) >> 1 : ih >> 1;
+    const int ow1 = ((iw & 1) && ((iw + 1) >> 1) < Wo) ? (iw + 1) >> 1 : iw >> 1;
+    for (int od = id >> 1; od <= od1; ++od)
+        for (int oh = ih >> 1; oh <= oh1; ++oh)
+            for (int ow = iw >> 1; ow <= ow1; ++ow) {
+                const uint32_t tap = (uint32_t)(((id - 2 * od + 1) * 3 + (ih - 2 * oh + 1)) * 3 + (iw - 2 * ow + 1));
+                const long long o = ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * cv + v;
+                const uint2 p = idx[o];
+                uint4 gy = dp[o];
+                const uint32_t t4 = tap * 0x01010101u;
+                const uint32_t mlo = __vcmpeq4(p.x, t4), mhi = __vcmpeq4(p.y, t4);      // 0xff per matching channel byte
+                if (!(mlo | mhi)) continue;
+                float a[8];
+                if (dp2) {
+                    float b[8];
+                    unpack8(gy, a);
+                    unpack8(dp2[o], b);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] += b[j];
+                } else {
+                    unpack8(gy, a);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] += (((j < 4 ? mlo : mhi) >> (8 * (j & 3))) & 1u) ? a[j] : 0.f;
+            }
+}
+
+// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it
 __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                                             int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
     const int cv = C >> 3;
@@ -355,35 +388,130 @@ __global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restr
         const int ih = (int)(t % (unsigned)H); t /= (unsigned)H;
         const int id = (int)(t % (unsigned)D); t /= (unsigned)D;
         const int n = (int)t;
-        // windows o with 2*o - 1 <= i <= 2*o + 1: o = i >> 1, and (for odd i) o + 1
-        const int o_d[2] = {id >> 1, (id + 1) >> 1}, o_h[2] = {ih >> 1, (ih + 1) >> 1}, o_w[2] = {iw >> 1, (iw + 1) >> 1};
-        const bool v_d[2] = {true, (id & 1) && o_d[1] < Do}, v_h[2] = {true, (ih & 1) && o_h[1] < Ho}, v_w[2] = {true, (iw & 1) && o_w[1] < Wo};
-        uint2 pi[8];
-        uint4 gy[8];
-        int tap[8];
-        bool ok[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int a = q >> 2, b = (q >> 1) & 1, c = q & 1;
-            ok[q] = v_d[a] && v_h[b] && v_w[c];
-            tap[q] = ((id - 2 * o_d[a] + 1) * 3 + (ih - 2 * o_h[b] + 1)) * 3 + (iw - 2 * o_w[c] + 1);
-            const long long o = ((((long long)n * Do + o_d[a]) * Ho + o_h[b]) * Wo + o_w[c]) * cv + v;
-            pi[q] = ok[q] ? idx[o] : make_uint2(0xffffffffu, 0xffffffffu);
-            gy[q] = ok[q] ? dy[o] : make_uint4(0, 0, 0, 0);
-        }
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float f[8];
-            unpack8(gy[q], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int wsel = (int)(((j < 4 ? pi[q].x : pi[q].y) >> (8 * (j & 3))) & 0xffu);
-                acc[j] += wsel == tap[q] ? f[j] : 0.f;
-            }
-        }
+        float acc[8];
+        stem_pool_gather(dy, nullptr, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, acc);
         dx[i] = pack8(acc);
     }
+}
+
+// ---- fused stem (resnet.py:206-208): p = maxpool3d(relu(bn(c)), k3 s2 p1) in one pass over the conv output c; the
+//      post-ReLU tensor is never stored.  idx keeps the winning tap (first maximum in (kd,kh,kw) order).
+__global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ c, const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift, uint4* __restrict__ y,
+                                                                       uint2* __restrict__ idx, int N, int D, int H, int W, int C, int Do,
+                                                                       int Ho, int Wo) {
+    const int cv = C >> 3;
+    const long long total = (long long)N * Do * Ho * Wo * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        unsigned t = (unsigned)i;
+        const int v = (int)(t % (unsigned)cv); t /= (unsigned)cv;
+        const int ow = (int)(t % (unsigned)Wo); t /= (unsigned)Wo;
+        const int oh = (int)(t % (unsigned)Ho); t /= (unsigned)Ho;
+        const int od = (int)(t % (unsigned)Do); t /= (unsigned)Do;
+        const int n = (int)t;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scale[v * 8 + j]; sh[j] = shift[v * 8 + j]; }
+        float best[8];
+        int bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+        int tap = 0;
+        for (int kd = 0; kd < 3; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw, ++tap) {
+                    const int id = od * 2 + kd - 1, ih = oh * 2 + kh - 1, iw = ow * 2 + kw - 1;
+                    if ((unsigned)id >= (unsigned)D || (unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) continue;
+                    float f[8];
+                    unpack8(c[((((long long)n * D + id) * H + ih) * W + iw) * cv + v], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // the activation the unfused path would have STORED: bf16(relu(bn(c)))
+                        const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f)));
+                        if (a > best[j]) { best[j] = a; bi[j] = tap; }
+                    }
+                }
+        y[i] = pack8(best);
+        uint2 p;
+        p.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+        p.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+        idx[i] = p;
+    }
+}
+
+// fused stem backward, pass 1: g = poolgrad * (relu(bn(c)) > 0); per-block partial sums of g and g*xhat (g is not stored)
+__global__ void __launch_bounds__(512) stem_bwd_reduce_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ dp2,
+                                                              const uint2* __restrict__ idx, const uint4* __restrict__ c,
+                                                              const float* __restrict__ vec /* mean, invstd, scale, shift: [4][C] */,
+                                                              float* __restrict__ partials, int N, int D, int H, int W, int C, int Do, int Ho,
+                                                              int Wo, int hrows) {
+    extern __shared__ float red[];                    // [threads][16]
+    const int cv = C >> 3;
+    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
+    const int n = blockIdx.x / D, id = blockIdx.x % D;
+    float mu[8], is[8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = vec[v * 8 + j]; is[j] = vec[C + v * 8 + j]; sc[j] = vec[2 * C + v * 8 + j]; sh[j] = vec[3 * C + v * 8 + j]; }
+    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ih = blockIdx.y * hrows; ih < min(H, (int)(blockIdx.y + 1) * hrows); ++ih)
+        for (int iw = wl; iw < W; iw += wstep) {
+            float x[8], g[8];
+            unpack8(c[((((long long)n * D + id) * H + ih) * W + iw) * cv + v], x);
+            stem_pool_gather(dp, dp2, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                sg[j] += gm;
+                sgx[j] += gm * (x[j] - mu[j]) * is[j];
+            }
+        }
+    float* my = red + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[j] = sg[j]; my[8 + j] = sgx[j]; }
+    __syncthreads();
+    if (threadIdx.x < cv) {
+        float a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = 0.f;
+        for (int q = 0; q < wstep; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] += red[(q * cv + threadIdx.x) * 16 + j];
+        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            partials[(blk * C + v * 8 + j) * 2] = a[j];
+            partials[(blk * C + v * 8 + j) * 2 + 1] = a[8 + j];
+        }
+    }
+}
+// pass 2: dc = A*g + B*c + Cc with the same on-the-fly g
+__global__ void __launch_bounds__(512) stem_bwd_apply_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ dp2,
+                                                             const uint2* __restrict__ idx, const uint4* __restrict__ c,
+                                                             const float* __restrict__ vec, const float* __restrict__ coef,
+                                                             uint4* __restrict__ dc, int N, int D, int H, int W, int C, int Do, int Ho, int Wo,
+                                                             int hrows) {
+    const int cv = C >> 3;
+    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
+    const int n = blockIdx.x / D, id = blockIdx.x % D;
+    float sc[8], sh[8], A[8], B[8], Cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = vec[2 * C + v * 8 + j]; sh[j] = vec[3 * C + v * 8 + j];
+        A[j] = coef[v * 8 + j]; B[j] = coef[C + v * 8 + j]; Cc[j] = coef[2 * C + v * 8 + j];
+    }
+    for (int ih = blockIdx.y * hrows; ih < min(H, (int)(blockIdx.y + 1) * hrows); ++ih)
+        for (int iw = wl; iw < W; iw += wstep) {
+            const long long o = ((((long long)n * D + id) * H + ih) * W + iw) * cv + v;
+            float x[8], g[8], r[8];
+            unpack8(c[o], x);
+            stem_pool_gather(dp, dp2, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                r[j] = fmaf(A[j], gm, fmaf(B[j], x[j], Cc[j]));
+            }
+            dc[o] = pack8(r);
+        }
 }
 
 // ---- zero insertion: y (N, Dy,Hy,Wy, C), y[2*o] = x[o], zero elsewhere (dgrad of a stride-2 convolution = unit-stride
@@ -558,6 +686,50 @@ int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, 
     const long long total = (long long)N * D * H * W * (C / 8);
     MMAD_CHECK_ARG(total < (1ll << 32), "maxpool3d_bwd: tensor too large for 32-bit indexing");
     maxpool3d_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo);
+    LAUNCH_OK();
+}
+int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float* shift, void* y, void* idx, int N, int D, int H, int W,
+                                  int C, void* stream) {
+    MMAD_CHECK_ARG(c && scale && shift && y && idx && C % 8 == 0, "stem_bn_relu_maxpool_fwd: bad argument");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long total = (long long)N * Do * Ho * Wo * (C / 8);
+    MMAD_CHECK_ARG(total < (1ll << 32), "stem_bn_relu_maxpool_fwd: tensor too large for 32-bit indexing");
+    stem_bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
+                                                                                    W, C, Do, Ho, Wo);
+    LAUNCH_OK();
+}
+static int stem_bwd_cfg(int N, int D, int H, int W, int C, int& threads, int& hrows, dim3& grid) {
+    const int cv = C / 8;
+    if (C % 8 || cv > 64 || 512 % cv) return -1;
+    threads = 512;
+    hrows = 8;
+    grid = dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows));
+    return 0;
+}
+// number of block partials mmad_stem_bwd_reduce writes: float[n][C][2]
+int mmad_stem_bwd_partials(int N, int D, int H, int W, int C) {
+    int threads, hrows; dim3 grid;
+    if (stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid)) return -1;
+    return (int)(grid.x * grid.y);
+}
+int mmad_stem_bwd_reduce(const void* dp, const void* dp2, const void* idx, const void* c, const float* vec, float* partials, int N, int D,
+                         int H, int W, int C, void* stream) {
+    MMAD_CHECK_ARG(dp && idx && c && vec && partials, "stem_bwd_reduce: null pointer");
+    int threads, hrows; dim3 grid;
+    MMAD_CHECK_ARG(stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid) == 0, "stem_bwd_reduce: C/8 must divide 512");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    stem_bwd_reduce_kernel<<<grid, threads, threads * 16 * sizeof(float), ST>>>((const uint4*)dp, (const uint4*)dp2, (const uint2*)idx, (const uint4*)c,
+                                                                               vec, partials, N, D, H, W, C, Do, Ho, Wo, hrows);
+    LAUNCH_OK();
+}
+int mmad_stem_bwd_apply(const void* dp, const void* dp2, const void* idx, const void* c, const float* vec, const float* coef, void* dc,
+                        int N, int D, int H, int W, int C, void* stream) {
+    MMAD_CHECK_ARG(dp && idx && c && vec && coef && dc, "stem_bwd_apply: null pointer");
+    int threads, hrows; dim3 grid;
+    MMAD_CHECK_ARG(stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid) == 0, "stem_bwd_apply: C/8 must divide 512");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    stem_bwd_apply_kernel<<<grid, threads, 0, ST>>>((const uint4*)dp, (const uint4*)dp2, (const uint2*)idx, (const uint4*)c, vec, coef, (uint4*)dc,
+                                                   N, D, H, W, C, Do, Ho, Wo, hrows);
     LAUNCH_OK();
 }
 int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx, int Dy, int Hy, int Wy, int C, void* stream) {

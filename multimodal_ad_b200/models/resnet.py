@@ -198,12 +198,13 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     c0, part = r.conv(col, wstem, 64, 1, 1, 0, 1, training)
     c0 = c0.view(n, do, ho, wo, 64)
     v0 = r.bn_params(model.bn1, part, rows, training)
-    a0 = r.bn_apply(c0, v0, relu=True)
     pd, ph, pw = (do - 1) // 2 + 1, (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
     p0 = r.empty((n, pd, ph, pw, 64))
     idx0 = torch.empty((n, pd, ph, pw, 64), dtype=torch.uint8, device=x.device)
-    r.chk(lib.mmad_maxpool3d_fwd(_p(a0), _p(p0), _p(idx0), n, do, ho, wo, 64, r.stream), "mmad_maxpool3d_fwd")
-    tape["stem"] = dict(col=col if need_grad else None, c0=c0, v0=v0, a0=a0, idx0=idx0, in_shape=(n, d, h, w))
+    # bn1 + relu + maxpool fused: the 64-channel full-resolution activation is never written
+    r.chk(lib.mmad_stem_bn_relu_maxpool_fwd(_p(c0), _p(v0[2]), _p(v0[3]), _p(p0), _p(idx0), n, do, ho, wo, 64, r.stream),
+          "mmad_stem_bn_relu_maxpool_fwd")
+    tape["stem"] = dict(col=col if need_grad else None, c0=c0, v0=v0, p0=p0, idx0=idx0, in_shape=(n, d, h, w))
 
     # ---- residual stages (resnet.py:209-212) ----
     cur = p0
@@ -315,21 +316,24 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
 
-    # ---- stem backward: maxpool, relu+bn1, wgrad of the im2col GEMM (no input gradient: the MRI volume is data) ----
+    # ---- stem backward (no input gradient: the MRI volume is data).  The max-pool gather and the ReLU mask are recomputed
+    #      inside both BatchNorm-backward passes; dy + dy2 is summed on the fly ----
     stem = tape["stem"]
     n, d, h, w = stem["in_shape"]
-    a0 = stem["a0"]
-    dsum = r.empty(dy.shape)
-    # dy + dy2 is needed as one tensor by the max-pool gather; fold the add into a bn_apply with scale 1 / shift 0
-    ones = torch.ones((4, 64), dtype=torch.float32, device=dy.device)
-    ones[3].zero_()
-    r.chk(lib.mmad_bn_apply(_p(dy), _p(ones[2]), _p(ones[3]), _p(dy2), None, None, 0, _p(dsum), None, dy.numel() // 64, 64, r.stream),
-          "mmad_bn_apply")
-    da0 = r.empty(a0.shape)
-    r.chk(lib.mmad_maxpool3d_bwd(_p(dsum), _p(stem["idx0"]), _p(da0), n, a0.shape[1], a0.shape[2], a0.shape[3], 64, r.stream),
-          "mmad_maxpool3d_bwd")
-    dc0, _, dg, db = r.bn_bwd(da0, None, a0, stem["c0"], stem["v0"], model.bn1.weight.detach(), training, want_g=True)
-    grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
+    c0, v0 = stem["c0"], stem["v0"]
+    _, sd, sh, sw, _ = c0.shape
+    npart = lib.mmad_stem_bwd_partials(n, sd, sh, sw, 64)
+    part = r.empty((npart, 64, 2), torch.float32)
+    r.chk(lib.mmad_stem_bwd_reduce(_p(dy), _p(dy2), _p(stem["idx0"]), _p(c0), _p(v0), _p(part), n, sd, sh, sw, 64, r.stream),
+          "mmad_stem_bwd_reduce")
+    gb = r.empty((2, 64), torch.float32)
+    coef = r.empty((3, 64), torch.float32)
+    r.chk(lib.mmad_bn_bwd_finalize(_p(part), npart, 64, float(c0.numel() // 64), _p(model.bn1.weight.detach()), _p(v0[0]), _p(v0[1]),
+                                   1 if training else 0, _p(gb[0]), _p(gb[1]), _p(coef), r.stream), "mmad_bn_bwd_finalize")
+    grads[model.bn1.weight], grads[model.bn1.bias] = gb[0], gb[1]
+    dc0 = r.empty(c0.shape)
+    r.chk(lib.mmad_stem_bwd_apply(_p(dy), _p(dy2), _p(stem["idx0"]), _p(c0), _p(v0), _p(coef), _p(dc0), n, sd, sh, sw, 64, r.stream),
+          "mmad_stem_bwd_apply")
     rows = dc0.numel() // 64
     gwp = r.empty((64, STEM_KPAD), torch.float32)
     r.wgrad(stem["col"], dc0.view(1, 1, 1, rows, 64), 64, 1, 1, 0, 1, gwp)
@@ -343,7 +347,7 @@ def tape_stages(model: "ResNet", tape) -> dict:
     """Stored activations of a forward tape as {stage name: NCDHW fp32 tensor} (test / debugging aid; the names are
     the ones oracle/resnet_oracle.py accepts for `forced`)."""
     f = lambda t: t.float().permute(0, 4, 1, 2, 3)          # noqa: E731
-    out = {"c0": f(tape["stem"]["c0"]), "a0": f(tape["stem"]["a0"])}
+    out = {"c0": f(tape["stem"]["c0"]), "p0": f(tape["stem"]["p0"])}
     names = [f"layer{li}.{bi}" for li, layer in enumerate((model.layer1, model.layer2, model.layer3, model.layer4), 1)
              for bi in range(len(layer))]
     for pre, rec in zip(names, tape["blocks"]):

@@ -180,3 +180,45 @@ def test_layout_transpose_and_stem_im2col(run):
     unf = F.pad(v, (3, 3, 3, 3, 3, 3)).unfold(2, 7, 2).unfold(3, 7, 2).unfold(4, 7, 2)        # (2,1,do,ho,wo,7,7,7)
     unf = unf.reshape(2 * do * ho * wo, 343).to(torch.bfloat16)
     assert torch.equal(col[:, :343], unf) and torch.all(col[:, 343:] == 0)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 7, 9, 11)])
+def test_fused_stem_matches_unfused_kernels(shape, run):
+    """bn+relu+maxpool forward and the gather-fused backward against the separate bn_apply / maxpool / bn_bwd kernels."""
+    from multimodal_ad_b200.models.resnet import _p
+
+    n, d, h, w = shape
+    c = 64
+    g = torch.Generator(device="cuda").manual_seed(d * h + w)
+    c0 = (torch.randn((n, d, h, w, c), device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    rows = n * d * h * w
+    vec = torch.stack([torch.randn(c, device="cuda", generator=g) * 0.1, torch.rand(c, device="cuda", generator=g) + 0.5,
+                       torch.rand(c, device="cuda", generator=g) + 0.5, torch.randn(c, device="cuda", generator=g) * 0.3]).contiguous()
+    gamma = vec[2] / vec[1]
+    do, ho, wo = (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    # unfused reference path
+    a0 = run.bn_apply(c0, vec, relu=True)
+    p_ref = run.empty((n, do, ho, wo, c))
+    i_ref = torch.empty((n, do, ho, wo, c), dtype=torch.uint8, device="cuda")
+    run.chk(run.lib.mmad_maxpool3d_fwd(_p(a0), _p(p_ref), _p(i_ref), n, d, h, w, c, run.stream), "mp")
+    p0 = run.empty((n, do, ho, wo, c))
+    idx = torch.empty((n, do, ho, wo, c), dtype=torch.uint8, device="cuda")
+    run.chk(run.lib.mmad_stem_bn_relu_maxpool_fwd(_p(c0), _p(vec[2]), _p(vec[3]), _p(p0), _p(idx), n, d, h, w, c, run.stream), "fused fwd")
+    assert torch.equal(p0, p_ref) and torch.equal(idx, i_ref)
+    dp = torch.randn((n, do, ho, wo, c), device="cuda", generator=g).to(torch.bfloat16)
+    dp2 = torch.randn((n, do, ho, wo, c), device="cuda", generator=g).to(torch.bfloat16)
+    dsum = (dp.float() + dp2.float()).to(torch.bfloat16)
+    da0 = run.empty((n, d, h, w, c))
+    run.chk(run.lib.mmad_maxpool3d_bwd(_p(dsum), _p(i_ref), _p(da0), n, d, h, w, c, run.stream), "mpb")
+    dx_ref, _, dg_ref, db_ref = run.bn_bwd(da0, None, a0, c0, vec, gamma, True)
+    npart = run.lib.mmad_stem_bwd_partials(n, d, h, w, c)
+    part = run.empty((npart, c, 2), torch.float32)
+    run.chk(run.lib.mmad_stem_bwd_reduce(_p(dp), _p(dp2), _p(idx), _p(c0), _p(vec), _p(part), n, d, h, w, c, run.stream), "reduce")
+    gb, coef = run.empty((2, c), torch.float32), run.empty((3, c), torch.float32)
+    run.chk(run.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(gamma), _p(vec[0]), _p(vec[1]), 1, _p(gb[0]), _p(gb[1]),
+                                         _p(coef), run.stream), "finalize")
+    dc = run.empty(c0.shape)
+    run.chk(run.lib.mmad_stem_bwd_apply(_p(dp), _p(dp2), _p(idx), _p(c0), _p(vec), _p(coef), _p(dc), n, d, h, w, c, run.stream), "apply")
+    # the unfused path rounds dp+dp2, the pooled gradient and g to bf16 on the way; the fused one keeps fp32: 1e-2 relative
+    assert _rel(gb[1], db_ref) < 1e-2 and _rel(gb[0], dg_ref) < 1e-2
+    assert _rel(dc, dx_ref) < 1.5e-2
