@@ -166,10 +166,12 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift,
  * dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = coef0*g + coef1*x + coef2
  * (training == 0: eval-mode BatchNorm is affine, dx = gamma*invstd*g); apply:
  * that map.  dy is bf16 (dy_bf16) or fp32 (dy_f32), both rows x C in NDHWC
- * order; mask NULL = no ReLU. */
+ * order; mask NULL = no ReLU, unless mask_scale/mask_shift (float[C]) are given:
+ * then the mask is recomputed as relu(x*mask_scale + mask_shift) > 0. */
 int mmad_bn_bwd_partials(int64_t rows);
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2,
                        const void* mask, const void* x, const float* mean, const float* invstd,
+                       const float* mask_scale, const float* mask_shift,
                        void* g_out, float* partials, int64_t rows, int C, void* stream);
 int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
                          const float* gamma, const float* mean, const float* invstd, int training,
@@ -182,21 +184,12 @@ int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef,
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
 int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream);
 
-/* Fused stem (resnet.py:205-208 after conv1): p = maxpool3d(relu(bn(c)), 3, 2, 1)
+/* Fused stem forward (resnet.py:205-208 after conv1): p = maxpool3d(relu(bn(c)), 3, 2, 1)
  * in one pass over the conv output c (N,D,H,W,C) bf16; the post-ReLU tensor is
- * never stored.  Backward: the max-pool gradient gather and the ReLU mask are
- * recomputed inside both BatchNorm-backward passes (reduce: partial sums of g
- * and g*xhat, float[mmad_stem_bwd_partials][C][2], feed mmad_bn_bwd_finalize;
- * apply: dc = coef0*g + coef1*c + coef2).  dp (+ optional dp2) is the gradient
- * of the pooled tensor; vec = float[4][C] (mean, invstd, scale, shift). */
+ * never stored (its ReLU mask is recomputed in the backward from c, see
+ * mask_scale / mask_shift of mmad_bn_bwd_reduce). */
 int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float* shift,
                                   void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
-int mmad_stem_bwd_partials(int N, int D, int H, int W, int C);
-int mmad_stem_bwd_reduce(const void* dp, const void* dp2, const void* idx, const void* c,
-                         const float* vec, float* partials, int N, int D, int H, int W, int C, void* stream);
-int mmad_stem_bwd_apply(const void* dp, const void* dp2, const void* idx, const void* c,
-                        const float* vec, const float* coef, void* dc,
-                        int N, int D, int H, int W, int C, void* stream);
 
 /* y[2*o] = x[o], zero elsewhere: dgrad of a stride-2 convolution is the
  * unit-stride convolution of this with the flipped kernel. */

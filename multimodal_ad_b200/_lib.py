@@ -72,16 +72,14 @@ def load() -> ctypes.CDLL:
         "mmad_bn_eval_params": [I, P, P, P, P, F, P, P, P, P, P],
         "mmad_bn_apply": [P, P, P, P, P, P, I, P, P, L, I, P],
         "mmad_bn_bwd_partials": [L],
-        "mmad_bn_bwd_reduce": [P, P, P, P, P, P, P, P, P, L, I, P],
+        "mmad_bn_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, L, I, P],
         "mmad_bn_bwd_finalize": [P, I, I, D_, P, P, P, I, P, P, P, P],
         "mmad_bn_bwd_apply": [P, P, P, P, L, I, P],
         "mmad_maxpool3d_fwd": [P, P, P, I, I, I, I, I, P],
         "mmad_maxpool3d_bwd": [P, P, P, I, I, I, I, I, P],
         "mmad_upsample_zero2": [P, P] + [I] * 8 + [P],
         "mmad_stem_bn_relu_maxpool_fwd": [P, P, P, P, P, I, I, I, I, I, P],
-        "mmad_stem_bwd_partials": [I] * 5,
-        "mmad_stem_bwd_reduce": [P, P, P, P, P, P, I, I, I, I, I, P],
-        "mmad_stem_bwd_apply": [P, P, P, P, P, P, P, I, I, I, I, I, P],
+
         "mmad_ncs_f32_to_nsc_bf16": [P, P, I, I, L, P],
     }
     for name, args in sigs.items():

@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restrict__ dy_bf16, const float4* __restrict__ dy_f32,
                                                             const uint4* __restrict__ dy2, const uint4* __restrict__ mask,
                                                             const uint4* __restrict__ x, const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, uint4* __restrict__ g_out,
+                                                            const float* __restrict__ invstd, const float* __restrict__ mscale,
+                                                            const float* __restrict__ mshift, uint4* __restrict__ g_out,
                                                             float* __restrict__ partials, long long rows, int C) {
     // each block walks rows [r0, r1); thread t handles channel vector (t % cv) of rows r0 + t / cv, + 256/cv, ...
     extern __shared__ float red[];   // [256][16]
@@ -215,9 +216,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
     const int rpb = 256 / cv;        // rows per block step (>= 4)
     const int tv = threadIdx.x % cv, tr = threadIdx.x / cv;
     const int c0 = tv * 8;
-    float mu[8], is[8];
+    float mu[8], is[8], msc[8], msh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+    for (int j = 0; j < 8; ++j) {
+        mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j];
+        msc[j] = mscale ? mscale[c0 + j] : 0.f; msh[j] = mscale ? mshift[c0 + j] : 0.f;
+    }
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long per = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
@@ -234,6 +238,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
             for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
         float xv[8];
         unpack8(x[i], xv);
+        if (mscale) {                 // ReLU mask recomputed from the pre-BN tensor: relu(x*scale + shift) > 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+        }
         if (g_out) {
             const uint4 gp = pack8(g);
             g_out[i] = gp;
@@ -439,81 +447,6 @@ __global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uin
     }
 }
 
-// fused stem backward, pass 1: g = poolgrad * (relu(bn(c)) > 0); per-block partial sums of g and g*xhat (g is not stored)
-__global__ void __launch_bounds__(512) stem_bwd_reduce_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ dp2,
-                                                              const uint2* __restrict__ idx, const uint4* __restrict__ c,
-                                                              const float* __restrict__ vec /* mean, invstd, scale, shift: [4][C] */,
-                                                              float* __restrict__ partials, int N, int D, int H, int W, int C, int Do, int Ho,
-                                                              int Wo, int hrows) {
-    extern __shared__ float red[];                    // [threads][16]
-    const int cv = C >> 3;
-    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
-    const int n = blockIdx.x / D, id = blockIdx.x % D;
-    float mu[8], is[8], sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = vec[v * 8 + j]; is[j] = vec[C + v * 8 + j]; sc[j] = vec[2 * C + v * 8 + j]; sh[j] = vec[3 * C + v * 8 + j]; }
-    float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int ih = blockIdx.y * hrows; ih < min(H, (int)(blockIdx.y + 1) * hrows); ++ih)
-        for (int iw = wl; iw < W; iw += wstep) {
-            float x[8], g[8];
-            unpack8(c[((((long long)n * D + id) * H + ih) * W + iw) * cv + v], x);
-            stem_pool_gather(dp, dp2, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                sg[j] += gm;
-                sgx[j] += gm * (x[j] - mu[j]) * is[j];
-            }
-        }
-    float* my = red + threadIdx.x * 16;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { my[j] = sg[j]; my[8 + j] = sgx[j]; }
-    __syncthreads();
-    if (threadIdx.x < cv) {
-        float a[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] = 0.f;
-        for (int q = 0; q < wstep; ++q)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] += red[(q * cv + threadIdx.x) * 16 + j];
-        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            partials[(blk * C + v * 8 + j) * 2] = a[j];
-            partials[(blk * C + v * 8 + j) * 2 + 1] = a[8 + j];
-        }
-    }
-}
-// pass 2: dc = A*g + B*c + Cc with the same on-the-fly g
-__global__ void __launch_bounds__(512) stem_bwd_apply_kernel(const uint4* __restrict__ dp, const uint4* __restrict__ dp2,
-                                                             const uint2* __restrict__ idx, const uint4* __restrict__ c,
-                                                             const float* __restrict__ vec, const float* __restrict__ coef,
-                                                             uint4* __restrict__ dc, int N, int D, int H, int W, int C, int Do, int Ho, int Wo,
-                                                             int hrows) {
-    const int cv = C >> 3;
-    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
-    const int n = blockIdx.x / D, id = blockIdx.x % D;
-    float sc[8], sh[8], A[8], B[8], Cc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = vec[2 * C + v * 8 + j]; sh[j] = vec[3 * C + v * 8 + j];
-        A[j] = coef[v * 8 + j]; B[j] = coef[C + v * 8 + j]; Cc[j] = coef[2 * C + v * 8 + j];
-    }
-    for (int ih = blockIdx.y * hrows; ih < min(H, (int)(blockIdx.y + 1) * hrows); ++ih)
-        for (int iw = wl; iw < W; iw += wstep) {
-            const long long o = ((((long long)n * D + id) * H + ih) * W + iw) * cv + v;
-            float x[8], g[8], r[8];
-            unpack8(c[o], x);
-            stem_pool_gather(dp, dp2, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                r[j] = fmaf(A[j], gm, fmaf(B[j], x[j], Cc[j]));
-            }
-            dc[o] = pack8(r);
-        }
-}
-
 // ---- zero insertion: y (N, Dy,Hy,Wy, C), y[2*o] = x[o], zero elsewhere (dgrad of a stride-2 convolution = unit-stride
 //      convolution of the zero-upsampled gradient with the flipped kernel)
 __global__ void __launch_bounds__(256) upsample_zero2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int Dx, int Hx, int Wx,
@@ -652,13 +585,14 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
 int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 4)); }
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2, const void* mask, const void* x, const float* mean,
-                       const float* invstd, void* g_out, float* partials, int64_t rows, int C, void* stream) {
+                       const float* invstd, const float* mask_scale, const float* mask_shift, void* g_out, float* partials, int64_t rows,
+                       int C, void* stream) {
     MMAD_CHECK_ARG((dy_bf16 || dy_f32) && x && mean && invstd && partials && rows > 0, "bn_bwd_reduce: bad argument");
     MMAD_CHECK_ARG(C % 64 == 0 && C <= 512, "bn_bwd_reduce: C must be 64, 128, 256 or 512");
     const int grid = mmad_bn_bwd_partials(rows);
     bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), ST>>>((const uint4*)dy_bf16, (const float4*)dy_f32, (const uint4*)dy2,
-                                                                     (const uint4*)mask, (const uint4*)x, mean, invstd, (uint4*)g_out,
-                                                                     partials, rows, C);
+                                                                     (const uint4*)mask, (const uint4*)x, mean, invstd, mask_scale, mask_shift,
+                                                                     (uint4*)g_out, partials, rows, C);
     LAUNCH_OK();
 }
 int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* mean,
@@ -696,40 +630,6 @@ int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float
     MMAD_CHECK_ARG(total < (1ll << 32), "stem_bn_relu_maxpool_fwd: tensor too large for 32-bit indexing");
     stem_bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
                                                                                     W, C, Do, Ho, Wo);
-    LAUNCH_OK();
-}
-static int stem_bwd_cfg(int N, int D, int H, int W, int C, int& threads, int& hrows, dim3& grid) {
-    const int cv = C / 8;
-    if (C % 8 || cv > 64 || 512 % cv) return -1;
-    threads = 512;
-    hrows = 8;
-    grid = dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows));
-    return 0;
-}
-// number of block partials mmad_stem_bwd_reduce writes: float[n][C][2]
-int mmad_stem_bwd_partials(int N, int D, int H, int W, int C) {
-    int threads, hrows; dim3 grid;
-    if (stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid)) return -1;
-    return (int)(grid.x * grid.y);
-}
-int mmad_stem_bwd_reduce(const void* dp, const void* dp2, const void* idx, const void* c, const float* vec, float* partials, int N, int D,
-                         int H, int W, int C, void* stream) {
-    MMAD_CHECK_ARG(dp && idx && c && vec && partials, "stem_bwd_reduce: null pointer");
-    int threads, hrows; dim3 grid;
-    MMAD_CHECK_ARG(stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid) == 0, "stem_bwd_reduce: C/8 must divide 512");
-    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    stem_bwd_reduce_kernel<<<grid, threads, threads * 16 * sizeof(float), ST>>>((const uint4*)dp, (const uint4*)dp2, (const uint2*)idx, (const uint4*)c,
-                                                                               vec, partials, N, D, H, W, C, Do, Ho, Wo, hrows);
-    LAUNCH_OK();
-}
-int mmad_stem_bwd_apply(const void* dp, const void* dp2, const void* idx, const void* c, const float* vec, const float* coef, void* dc,
-                        int N, int D, int H, int W, int C, void* stream) {
-    MMAD_CHECK_ARG(dp && idx && c && vec && coef && dc, "stem_bwd_apply: null pointer");
-    int threads, hrows; dim3 grid;
-    MMAD_CHECK_ARG(stem_bwd_cfg(N, D, H, W, C, threads, hrows, grid) == 0, "stem_bwd_apply: C/8 must divide 512");
-    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    stem_bwd_apply_kernel<<<grid, threads, 0, ST>>>((const uint4*)dp, (const uint4*)dp2, (const uint2*)idx, (const uint4*)c, vec, coef, (uint4*)dc,
-                                                   N, D, H, W, C, Do, Ho, Wo, hrows);
     LAUNCH_OK();
 }
 int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx, int Dy, int Hy, int Wy, int C, void* stream) {

@@ -158,14 +158,16 @@ class _Run:
                                         _p(out), _p(out32), rows, c, self.stream), "mmad_bn_apply")
         return (out, out32) if also_f32 else out
 
-    def bn_bwd(self, dy, dy2, mask, x, vec, gamma, training, dy_is_f32=False, want_g=True):
-        """-> dx (bf16), g (bf16 or None), dgamma, dbeta (fp32)."""
+    def bn_bwd(self, dy, dy2, mask, x, vec, gamma, training, dy_is_f32=False, want_g=True, mask_from_x=False):
+        """-> dx (bf16), g (bf16 or None), dgamma, dbeta (fp32).  mask_from_x: ReLU mask = relu(bn(x)) > 0, recomputed."""
         rows, c = x.numel() // x.shape[-1], x.shape[-1]
         npart = self.lib.mmad_bn_bwd_partials(rows)
         part = self.empty((npart, c, 2), torch.float32)
         g = self.empty(x.shape) if want_g else None
         self.chk(self.lib.mmad_bn_bwd_reduce(None if dy_is_f32 else _p(dy), _p(dy) if dy_is_f32 else None, _p(dy2), _p(mask), _p(x),
-                                             _p(vec[0]), _p(vec[1]), _p(g), _p(part), rows, c, self.stream), "mmad_bn_bwd_reduce")
+                                             _p(vec[0]), _p(vec[1]), _p(vec[2]) if mask_from_x else None,
+                                             _p(vec[3]) if mask_from_x else None, _p(g), _p(part), rows, c, self.stream),
+                 "mmad_bn_bwd_reduce")
         out = self.empty((2, c), torch.float32)           # dgamma, dbeta
         coef = self.empty((3, c), torch.float32)
         self.chk(self.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(gamma), _p(vec[0]), _p(vec[1]), 1 if training else 0,
@@ -316,24 +318,22 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
 
-    # ---- stem backward (no input gradient: the MRI volume is data).  The max-pool gather and the ReLU mask are recomputed
-    #      inside both BatchNorm-backward passes; dy + dy2 is summed on the fly ----
+    # ---- stem backward: maxpool, relu+bn1 (mask recomputed from c0), wgrad of the im2col GEMM.  No input gradient: the MRI
+    #      volume is data ----
     stem = tape["stem"]
     n, d, h, w = stem["in_shape"]
     c0, v0 = stem["c0"], stem["v0"]
-    _, sd, sh, sw, _ = c0.shape
-    npart = lib.mmad_stem_bwd_partials(n, sd, sh, sw, 64)
-    part = r.empty((npart, 64, 2), torch.float32)
-    r.chk(lib.mmad_stem_bwd_reduce(_p(dy), _p(dy2), _p(stem["idx0"]), _p(c0), _p(v0), _p(part), n, sd, sh, sw, 64, r.stream),
-          "mmad_stem_bwd_reduce")
-    gb = r.empty((2, 64), torch.float32)
-    coef = r.empty((3, 64), torch.float32)
-    r.chk(lib.mmad_bn_bwd_finalize(_p(part), npart, 64, float(c0.numel() // 64), _p(model.bn1.weight.detach()), _p(v0[0]), _p(v0[1]),
-                                   1 if training else 0, _p(gb[0]), _p(gb[1]), _p(coef), r.stream), "mmad_bn_bwd_finalize")
-    grads[model.bn1.weight], grads[model.bn1.bias] = gb[0], gb[1]
-    dc0 = r.empty(c0.shape)
-    r.chk(lib.mmad_stem_bwd_apply(_p(dy), _p(dy2), _p(stem["idx0"]), _p(c0), _p(v0), _p(coef), _p(dc0), n, sd, sh, sw, 64, r.stream),
-          "mmad_stem_bwd_apply")
+    dsum = r.empty(dy.shape)
+    # dy + dy2 is needed as one tensor by the max-pool gather; fold the add into a bn_apply with scale 1 / shift 0
+    ones = torch.ones((4, 64), dtype=torch.float32, device=dy.device)
+    ones[3].zero_()
+    r.chk(lib.mmad_bn_apply(_p(dy), _p(ones[2]), _p(ones[3]), _p(dy2), None, None, 0, _p(dsum), None, dy.numel() // 64, 64, r.stream),
+          "mmad_bn_apply")
+    da0 = r.empty(c0.shape)
+    r.chk(lib.mmad_maxpool3d_bwd(_p(dsum), _p(stem["idx0"]), _p(da0), n, c0.shape[1], c0.shape[2], c0.shape[3], 64, r.stream),
+          "mmad_maxpool3d_bwd")
+    dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=True, mask_from_x=True)
+    grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
     rows = dc0.numel() // 64
     gwp = r.empty((64, STEM_KPAD), torch.float32)
     r.wgrad(stem["col"], dc0.view(1, 1, 1, rows, 64), 64, 1, 1, 0, 1, gwp)
