@@ -81,13 +81,27 @@ def _p(t):
     return c_void_p(t.data_ptr()) if t is not None else None
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _Run:
     """One forward or backward pass: library handle, stream, allocation helpers, thin kernel wrappers."""
 
-    def __init__(self, device):
+    def __init__(self, device, use_side_stream=False):
         self.lib = _lib.load()
         self.dev = device
-        self.stream = c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        self.main = torch.cuda.current_stream(device)
+        self.stream = c_void_p(self.main.cuda_stream)
+        # weight-gradient kernels are off the backward critical path: they go to a side stream so the HBM-bound
+        # BatchNorm / ReLU kernels of the main chain run underneath the tensor-bound wgrad work
+        self.side = _side_stream(device) if use_side_stream else None
 
     def empty(self, shape, dtype=torch.bfloat16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -110,17 +124,32 @@ class _Run:
                                                self.stream), "mmad_conv3d_fwd_bf16")
         return y, part
 
-    def wgrad(self, x, dy, cout, k, stride, pad, dil, out_dw):
-        """out_dw: fp32 tensor in torch layout (Cout, Cin, k,k,k) (or any tensor of Cout*Cin*taps elements)."""
+    def wgrad(self, x, dy, cout, k, stride, pad, dil, out_dw, on_done=None):
+        """out_dw: fp32 tensor in torch layout (Cout, Cin, k,k,k) (or any tensor of Cout*Cin*taps elements).
+        Runs on the side stream when the run has one; on_done() is then called with that stream current (used to start
+        the data-parallel all-reduce of this gradient behind its own kernels)."""
         n, d, h, w, cin = x.shape
         nsplit = ctypes.c_int(0)
         elems = self.lib.mmad_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, pad, dil, ctypes.byref(nsplit))
         if elems < 0:
             raise _lib.MmadError("mmad_conv3d_wgrad_workspace: bad geometry")
         ws = self.empty((elems,), torch.float32)
-        self.chk(self.lib.mmad_conv3d_wgrad_bf16(_p(x), _p(dy), _p(ws), n, d, h, w, cin, cout, k, stride, pad, dil, self.stream),
+        stream, cs = self.main, self.stream
+        if self.side is not None:
+            self.side.wait_stream(self.main)               # x and dy were produced on the main stream
+            stream, cs = self.side, c_void_p(self.side.cuda_stream)
+            for t in (x, dy, ws, out_dw):
+                t.record_stream(self.side)                 # keep the caching allocator from reusing them early
+        self.chk(self.lib.mmad_conv3d_wgrad_bf16(_p(x), _p(dy), _p(ws), n, d, h, w, cin, cout, k, stride, pad, dil, cs),
                  "mmad_conv3d_wgrad_bf16")
-        self.chk(self.lib.mmad_wgrad_reduce(_p(ws), nsplit.value, _p(out_dw), cout, cin, k * k * k, self.stream), "mmad_wgrad_reduce")
+        self.chk(self.lib.mmad_wgrad_reduce(_p(ws), nsplit.value, _p(out_dw), cout, cin, k * k * k, cs), "mmad_wgrad_reduce")
+        if on_done is not None:
+            with torch.cuda.stream(stream):
+                on_done()
+
+    def join_side(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
 
     def prep_weights(self, conv: nn.Conv3d, want_dgrad):
         cout, cin, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
@@ -255,10 +284,17 @@ class _GradDict(dict):
         if self.reducer is not None:
             self.reducer.push(v)
 
+    def set_quiet(self, k, v):
+        """store without starting the all-reduce (the caller pushes it from the stream that produces the tensor)"""
+        super().__setitem__(k, v)
+
+    def pusher(self, v):
+        return (lambda: self.reducer.push(v)) if self.reducer is not None else None
+
 
 def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):
     """grad_out: gradient w.r.t. the (N,C,D',H',W')-shaped output view.  Returns {parameter: gradient}."""
-    r = _Run(grad_out.device)
+    r = _Run(grad_out.device, use_side_stream=getattr(model, "wgrad_side_stream", True))
     lib = r.lib
     training = tape["training"]
     grads = _GradDict(getattr(model, "grad_reducer", None))
@@ -283,14 +319,14 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         dy_f32 = False
         grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
         gw = torch.empty_like(blk.conv2.weight)
-        r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw)
-        grads[blk.conv2.weight] = gw
+        r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw, grads.pusher(gw))
+        grads.set_quiet(blk.conv2.weight, gw)
         da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
         dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
         grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
         gw = torch.empty_like(blk.conv1.weight)
-        r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw)
-        grads[blk.conv1.weight] = gw
+        r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw, grads.pusher(gw))
+        grads.set_quiet(blk.conv1.weight, gw)
         xin = rec["xin"]
         # dgrad of conv1
         if st == 1:
@@ -305,8 +341,8 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dcd, _, dg, db = r.bn_bwd(g2, None, None, rec["cd"], rec["vd"], dbn.weight.detach(), training, want_g=False)
             grads[dbn.weight], grads[dbn.bias] = dg, db
             gw = torch.empty_like(dconv.weight)
-            r.wgrad(xin, dcd, planes, 1, dconv.stride[0], 0, 1, gw)
-            grads[dconv.weight] = gw
+            r.wgrad(xin, dcd, planes, 1, dconv.stride[0], 0, 1, gw, grads.pusher(gw))
+            grads.set_quiet(dconv.weight, gw)
             if dconv.stride[0] == 1:
                 dx2, _ = r.conv(dcd, rec["wdt"], inpl, 1, 1, 0, 1, False)
             else:
@@ -337,6 +373,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
     rows = dc0.numel() // 64
     gwp = r.empty((64, STEM_KPAD), torch.float32)
     r.wgrad(stem["col"], dc0.view(1, 1, 1, rows, 64), 64, 1, 1, 0, 1, gwp)
+    r.join_side()                                          # every weight gradient is complete on the main stream from here
     gw = torch.empty_like(model.conv1.weight)
     r.chk(lib.mmad_stem_unpad_wgrad(_p(gwp), _p(gw), 64, 343, STEM_KPAD, r.stream), "mmad_stem_unpad_wgrad")
     grads[model.conv1.weight] = gw
