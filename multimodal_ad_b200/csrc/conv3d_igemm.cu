@@ -17,6 +17,7 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -253,6 +254,224 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ===============================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for 256-channel N tiles.  A cluster of two CTAs computes a 256-voxel x 256-channel
+// super tile with ONE MMA stream issued by the leader: every CTA stages its own 128 voxels of A and only HALF of the
+// weight rows, so the shared-memory traffic per MAC (TMA writes + MMA operand reads), which bounds the single-CTA kernel
+// at BN = 256, drops by a third.  Protocol (after CUTLASS' sm100 2-SM kernels): per-CTA `empty` barriers released by a
+// multicast tcgen05.commit; the leader's `full` barrier collects the TMA bytes of both CTAs; accumulator-full is multicast
+// to both epilogues, accumulator-empty is collected on the leader from both.
+// ===============================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                         const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+    constexpr int BN = 256;
+    constexpr int B_HALF = (BN / 2) * 128;
+    constexpr int STAGE = kATileBytes + B_HALF;             // 32 KB per CTA per K-step
+    constexpr uint32_t IDESC = umma_idesc_bf16(256, BN, 0, 0);
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const int S = g.stages;
+    const uint32_t stage0 = base;
+    const uint32_t out0 = base + (uint32_t)S * STAGE;
+    unsigned char* tail = sm + (size_t)S * STAGE + (size_t)g.nout * kStageOutBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);
+    float* st_sq = st_sum + 2 * g.Cout;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmC);
+    }
+    if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_s), TMEM_COLS);
+    for (int i = threadIdx.x; i < 4 * g.Cout; i += kConvThreads) st_sum[i] = 0.f;
+    tc_fence_before();
+    cluster_sync_all();                                     // both CTAs' barriers and TMEM exist before anyone signals the peer
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_super = (g.m_tiles + 1) >> 1;
+    const int total_super = m_super * g.n_tiles;
+    const int taps = g.kd * g.kh * g.kw;
+    const int ksteps = taps * g.kc;
+
+    // tap validity of a super tile = union over its two voxel tiles (both CTAs and the MMA issuer must agree)
+    auto super_masks = [&](int mp, uint32_t& mw, uint32_t& mh, uint32_t& md) {
+        mw = mh = md = 0;
+        for (int h = 0; h < 2; ++h) {
+            int r = 2 * mp + h;
+            if (r >= g.m_tiles) break;
+            const int wt = r % g.tiles_w; r /= g.tiles_w;
+            const int ht = r % g.tiles_h; r /= g.tiles_h;
+            const int dt = r % g.tiles_d;
+            uint32_t a = tap_axis_mask(wt * g.tw, g.tw, g.W, g.kw, g.stride, g.pad, g.dil);
+            uint32_t b = tap_axis_mask(ht * g.th, g.th, g.H, g.kh, g.stride, g.pad, g.dil);
+            uint32_t c = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
+            if (!a || !b || !c) a = b = c = 0xffffffffu;
+            mw |= a; mh |= b; md |= c;
+        }
+    };
+
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ============================ TMA producers (in both CTAs) ============================
+        if (lane == 0) {
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+            uint32_t s = 0, ph = 0, turn = 0;
+            for (int st = pair; st < total_super; st += n_pairs) {
+                const int nt = st % g.n_tiles, mp = st / g.n_tiles;
+                int r = 2 * mp + (int)rank;                 // this CTA's voxel tile (may be the phantom tile past the end:
+                const int wt = r % g.tiles_w; r /= g.tiles_w;   // its batch index is >= N, every box is out of bounds -> zeros)
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r % g.tiles_d; r /= g.tiles_d;
+                const int n = r;
+                const int w0 = wt * g.tw * g.stride - g.pad, h0 = ht * g.th * g.stride - g.pad, d0 = dt * g.td * g.stride - g.pad;
+                uint32_t mw, mh, md;
+                super_masks(mp, mw, mh, md);
+                int tap = 0;
+                for (int a = 0; a < g.kd; ++a)
+                    for (int b = 0; b < g.kh; ++b)
+                        for (int c = 0; c < g.kw; ++c, ++tap) {
+                            if (!((md >> a) & (mh >> b) & (mw >> c) & 1u)) continue;
+                            for (int cc = 0; cc < g.kc; ++cc) {
+                                if (turn == me) {
+                                    mbar_wait(empty0 + 8 * s, ph ^ 1);                  // my own smem slot is free
+                                    if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);   // bytes of BOTH CTAs
+                                    const uint32_t sa = stage0 + s * STAGE;
+                                    tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
+                                    tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, cc * 64, tap, nt * BN + (int)rank * (BN / 2));
+                                }
+                                if (++turn == kConvProducers) turn = 0;
+                                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer: leader CTA only ============================
+        if (lane == 0 && leader) {
+            uint32_t s = 0, ph = 0, it = 0;
+            for (int st = pair; st < total_super; st += n_pairs, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t mw, mh, md;
+                super_masks(st / g.n_tiles, mw, mh, md);
+                const int ksteps_t = (mw == 0xffffffffu) ? ksteps : __popc(mw) * __popc(mh) * __popc(md) * g.kc;
+                for (int k = 0; k < ksteps_t; ++k) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + s * STAGE;
+                    const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+                    const uint64_t bdesc = umma_desc_sw128(sa + kATileBytes, 16, 1024);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                    umma_commit_2sm(empty0 + 8 * s, 3);           // frees the slot in both CTAs
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+                umma_commit_2sm(tfull0 + 8 * acc, 3);             // accumulator complete -> both epilogues
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================ epilogue (in both CTAs): own 128 accumulator rows ============================
+        const int ew = warp - 4;
+        const int et = threadIdx.x - 128;
+        const int row = ew * 32 + lane;
+        uint32_t it = 0, nstore = 0;
+        for (int st = pair; st < total_super; st += n_pairs, ++it) {
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            const int nt = st % g.n_tiles, mp = st / g.n_tiles;
+            const int mt = 2 * mp + (int)rank;
+            int r = mt;
+            const int wt = r % g.tiles_w; r /= g.tiles_w;
+            const int ht = r % g.tiles_h; r /= g.tiles_h;
+            const int dt = r % g.tiles_d; r /= g.tiles_d;
+            const int n = r;
+            const int w0 = wt * g.tw, h0 = ht * g.th, d0 = dt * g.td;
+            const bool real = mt < g.m_tiles;
+            const int vw = real ? min(g.tw, g.Wo - w0) : 0, vh = min(g.th, g.Ho - h0), vd = min(g.td, g.Do - d0);
+
+            mbar_wait(tfull0 + 8 * acc, aph);
+            tc_fence_after();
+            for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
+                const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
+                if (et == 0) {
+                    if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                }
+                named_bar_sync(2, 128);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+                        const uint32_t p1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+                        const uint32_t p2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+                        const uint32_t p3 = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+                        const uint32_t chunk = (uint32_t)(half * 4 + q) ^ (uint32_t)(row & 7);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ob + row * 128 + chunk * 16), "r"(p0),
+                                     "r"(p1), "r"(p2), "r"(p3)
+                                     : "memory");
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0 && real) {
+                    tma_store_5d(&tmC, ob, nt * BN + sub * 64, w0, h0, d0, n);
+                    tma_store_commit();
+                }
+                if (stats_partials) {
+                    const int c = et & 63, hf = et >> 6;
+                    float sum = 0.f, sq = 0.f;
+                    const unsigned char* obp = sm + (ob - base);
+                    for (int rr = hf * 64; rr < hf * 64 + 64; ++rr) {
+                        const int wi = rr & (g.tw - 1), hi = (rr >> g.lw) & (g.th - 1), di = rr >> (g.lw + g.lh);
+                        if (wi < vw && hi < vh && di < vd) {
+                            const uint32_t off = rr * 128 + (((uint32_t)(c >> 3) ^ (uint32_t)(rr & 7)) << 4) + (c & 7) * 2;
+                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(obp + off));
+                            sum += x;
+                            sq += x * x;
+                        }
+                    }
+                    const int ch = nt * BN + sub * 64 + c;
+                    st_sum[hf * g.Cout + ch] += sum;
+                    st_sq[hf * g.Cout + ch] += sq;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty0 + 8 * acc, 0);   // the leader's MMA issuer waits for both CTAs
+        }
+        if (et == 0) tma_store_wait<0>();
+        if (stats_partials) {
+            named_bar_sync(2, 128);
+            for (int ch = et; ch < g.Cout; ch += 128) {
+                stats_partials[((size_t)blockIdx.x * g.Cout + ch) * 2 + 0] = st_sum[ch] + st_sum[g.Cout + ch];
+                stats_partials[((size_t)blockIdx.x * g.Cout + ch) * 2 + 1] = st_sq[ch] + st_sq[g.Cout + ch];
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                     // nobody frees TMEM / exits while the peer may still signal it
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Host
 // ---------------------------------------------------------------------------------------------------------------
@@ -299,6 +518,13 @@ static int conv_smem_bytes(int bn, int stages, int nout, int cout) {
     return 1024 + stages * (kATileBytes + bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
 }
 
+// CTA-pair kernel for 256-channel N tiles: on unless MMAD_CONV_PAIR=0
+static bool use_pair_kernel(int bn, long long m_tiles) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("MMAD_CONV_PAIR"); mode = e ? atoi(e) : 1; }
+    return mode != 0 && bn == 256 && m_tiles >= 2;
+}
+
 }  // namespace mmad
 
 using namespace mmad;
@@ -307,6 +533,7 @@ extern "C" {
 
 // Number of per-CTA statistic partials mmad_conv3d_fwd_bf16 writes for a given problem (== grid size).
 int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout, int k, int stride, int pad, int dil) {
+    // NOTE: must mirror the grid computed in mmad_conv3d_fwd_bf16
     const int Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1, Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1,
               Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     int tw = 0, th = 0, td = 0;
@@ -315,6 +542,8 @@ int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout, int k, int 
     const long long tiles = (long long)N * ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((Do + td - 1) / td) * (Cout / bn);
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long m_tiles = tiles / (Cout / bn);
+    if (use_pair_kernel(bn, m_tiles)) return 2 * (int)std::min<long long>(((m_tiles + 1) / 2) * (Cout / bn), sms / 2);
     return (int)std::min<long long>(tiles, sms);
 }
 
@@ -343,11 +572,13 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     const int bn = std::min(256, Cout);
     g.n_tiles = Cout / bn;
     g.kc = Cin / 64;
-    g.nout = bn == 256 ? 1 : 2;
+    const bool pairk = use_pair_kernel(bn, g.m_tiles);
+    const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
+    g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && conv_smem_bytes(bn, stages, g.nout, Cout) > 227 * 1024) --stages;
+    while (stages > 2 && conv_smem_bytes(bn_stage, stages, g.nout, Cout) > 227 * 1024) --stages;
     g.stages = stages;
-    const int smem = conv_smem_bytes(bn, stages, g.nout, Cout);
+    const int smem = conv_smem_bytes(bn_stage, stages, g.nout, Cout);
 
     CUtensorMap tmA, tmB, tmC;
     {
@@ -362,7 +593,7 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         const int taps = k * k * k;
         const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
         const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2};
-        const uint32_t box[3] = {64, 1, (uint32_t)bn};
+        const uint32_t box[3] = {64, 1, (uint32_t)bn_stage};
         const uint32_t es[3] = {1, 1, 1};
         int rc = make_tmap_bf16(&tmB, w, 3, dims, str, box, es);
         if (rc) return rc;
@@ -379,8 +610,20 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     int dev = 0, sms = 148;
     MMAD_CUDA(cudaGetDevice(&dev));
     MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pairk) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_done = true;
+        }
+        const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
+        conv3d_igemm_pair_kernel<<<2 * pairs, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);
+        MMAD_CUDA(cudaGetLastError());
+        count_launch();
+        return MMAD_OK;
+    }
+    const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
 #define MMAD_CONV_LAUNCH(BNV)                                                                                               \
     do {                                                                                                                    \
         static bool attr_done = false;                                                                                      \
