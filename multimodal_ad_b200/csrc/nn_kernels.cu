@@ -225,30 +225,47 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long per = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
-    for (long long r = r0 + tr; r < r1; r += rpb) {
-        const long long i = r * cv + tv;
-        float g[8];
-        if (dy_bf16) unpack8(dy_bf16[i], g);
-        else { const float4 a = dy_f32[2 * i], b = dy_f32[2 * i + 1]; g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w; }
-        if (dy2) { float h[8]; unpack8(dy2[i], h);
+    // two rows per iteration: all loads of both rows are issued before either is consumed (bytes in flight)
+    for (long long r = r0 + tr; r < r1; r += 2 * rpb) {
+        const long long ia = r * cv + tv;
+        const bool hasb = r + rpb < r1;
+        const long long ib = hasb ? ia + (long long)rpb * cv : ia;
+        uint4 qd[2], q2[2], qm[2], qx[2];
+        float4 fa[2], fb[2];
+        const long long ii[2] = {ia, ib};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] += h[j]; }
-        if (mask) { float m[8]; unpack8(mask[i], m);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
-        float xv[8];
-        unpack8(x[i], xv);
-        if (mscale) {                 // ReLU mask recomputed from the pre-BN tensor: relu(x*scale + shift) > 0
-#pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
-        }
-        if (g_out) {
-            const uint4 gp = pack8(g);
-            g_out[i] = gp;
-            unpack8(gp, g);          // statistics of the ROUNDED g, the values pass 2 will read
+        for (int u = 0; u < 2; ++u) {
+            if (dy_bf16) qd[u] = dy_bf16[ii[u]]; else { fa[u] = dy_f32[2 * ii[u]]; fb[u] = dy_f32[2 * ii[u] + 1]; }
+            if (dy2) q2[u] = dy2[ii[u]];
+            if (mask) qm[u] = mask[ii[u]];
+            qx[u] = x[ii[u]];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sg[j] += g[j]; sgx[j] += g[j] * (xv[j] - mu[j]) * is[j]; }
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !hasb) break;
+            float g[8];
+            if (dy_bf16) unpack8(qd[u], g);
+            else { g[0] = fa[u].x; g[1] = fa[u].y; g[2] = fa[u].z; g[3] = fa[u].w; g[4] = fb[u].x; g[5] = fb[u].y; g[6] = fb[u].z; g[7] = fb[u].w; }
+            if (dy2) { float h[8]; unpack8(q2[u], h);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] += h[j]; }
+            if (mask) { float m[8]; unpack8(qm[u], m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
+            float xv[8];
+            unpack8(qx[u], xv);
+            if (mscale) {                 // ReLU mask recomputed from the pre-BN tensor: relu(x*scale + shift) > 0
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+            }
+            if (g_out) {
+                const uint4 gp = pack8(g);
+                g_out[ii[u]] = gp;
+                unpack8(gp, g);          // statistics of the ROUNDED g, the values pass 2 will read
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sg[j] += g[j]; sgx[j] += g[j] * (xv[j] - mu[j]) * is[j]; }
+        }
     }
     float* my = red + threadIdx.x * 16;
 #pragma unroll
@@ -384,22 +401,20 @@ __device__ __forceinline__ void stem_pool_gather(const uint4* __restrict__ dp, c
             }
 }
 
-// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it
-__global__ void __launch_bounds__(256) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
-                                                            int N, int D, int H, int W, int C, int Do, int Ho, int Wo) {
+// gather form of the backward: every input voxel collects from the (<= 2 per axis) windows that contain it and picked it.
+// blockIdx.x = (n, id), blockIdx.y = group of `hrows` rows; threads cover (iw, channel vector): no per-thread divisions and
+// the d / h window loops are block-uniform.
+__global__ void __launch_bounds__(512) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
+                                                            int N, int D, int H, int W, int C, int Do, int Ho, int Wo, int hrows) {
     const int cv = C >> 3;
-    const long long total = (long long)N * D * H * W * cv;       // < 2^32 checked by the host wrapper
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        unsigned t = (unsigned)i;
-        const int v = (int)(t % (unsigned)cv); t /= (unsigned)cv;
-        const int iw = (int)(t % (unsigned)W); t /= (unsigned)W;
-        const int ih = (int)(t % (unsigned)H); t /= (unsigned)H;
-        const int id = (int)(t % (unsigned)D); t /= (unsigned)D;
-        const int n = (int)t;
-        float acc[8];
-        stem_pool_gather(dy, nullptr, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, acc);
-        dx[i] = pack8(acc);
-    }
+    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
+    const int n = blockIdx.x / D, id = blockIdx.x % D;
+    for (int ih = blockIdx.y * hrows; ih < min(H, (int)(blockIdx.y + 1) * hrows); ++ih)
+        for (int iw = wl; iw < W; iw += wstep) {
+            float acc[8];
+            stem_pool_gather(dy, nullptr, idx, n, id, ih, iw, v, cv, Do, Ho, Wo, acc);
+            dx[((((long long)n * D + id) * H + ih) * W + iw) * cv + v] = pack8(acc);
+        }
 }
 
 // ---- fused stem (resnet.py:206-208): p = maxpool3d(relu(bn(c)), k3 s2 p1) in one pass over the conv output c; the
@@ -514,6 +529,26 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     for (int i = threadIdx.x; i < nci * taps; i += 256) dst[i] = tile[(i % taps) * 65 + (i / taps)];
 }
 
+// small weight tensors (few (co, ci-chunk) blocks): one thread per element, strided write into the torch layout
+__global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout,
+                                                                 int Cin, int taps) {
+    const long long plane = (long long)Cout * taps * Cin;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= plane) return;
+    const int ci = (int)(i % Cin);
+    const int tap = (int)((i / Cin) % taps);
+    const int co = (int)(i / ((long long)Cin * taps));
+    const float* src = part + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 4 <= nsplit; p += 4) {
+        s0 += src[(size_t)p * plane]; s1 += src[(size_t)(p + 1) * plane];
+        s2 += src[(size_t)(p + 2) * plane]; s3 += src[(size_t)(p + 3) * plane];
+    }
+    for (; p < nsplit; ++p) s0 += src[(size_t)p * plane];
+    dw[((long long)co * Cin + ci) * taps + tap] = (s0 + s1) + (s2 + s3);
+}
+
 }  // namespace mmad
 
 using namespace mmad;
@@ -583,7 +618,7 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
     LAUNCH_OK();
 }
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
-int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 4)); }
+int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 8)); }
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2, const void* mask, const void* x, const float* mean,
                        const float* invstd, const float* mask_scale, const float* mask_shift, void* g_out, float* partials, int64_t rows,
                        int C, void* stream) {
@@ -617,9 +652,14 @@ int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, i
 int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream) {
     MMAD_CHECK_ARG(dy && dx && idx && C % 8 == 0, "maxpool3d_bwd: bad argument");
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    const long long total = (long long)N * D * H * W * (C / 8);
-    MMAD_CHECK_ARG(total < (1ll << 32), "maxpool3d_bwd: tensor too large for 32-bit indexing");
-    maxpool3d_bwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo);
+    const int cv = C / 8;
+    MMAD_CHECK_ARG(cv <= 512 && (long long)N * D < (1ll << 31), "maxpool3d_bwd: unsupported size");
+    int threads = 512;
+    while (threads > 32 && (threads % cv != 0 || threads / cv > W)) threads >>= 1;
+    MMAD_CHECK_ARG(threads % cv == 0, "maxpool3d_bwd: C/8 must divide a power of two <= 512");
+    const int hrows = 4;
+    maxpool3d_bwd_kernel<<<dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows)), threads, 0, ST>>>(
+        (const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo, hrows);
     LAUNCH_OK();
 }
 int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float* shift, void* y, void* idx, int N, int D, int H, int W,
@@ -646,7 +686,12 @@ int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, v
 }
 int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
-    wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 256, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    if ((long long)((Cin + 63) / 64) * Cout < 1024) {
+        const long long plane = (long long)Cout * taps * Cin;
+        wgrad_reduce_small_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    } else {
+        wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 256, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+    }
     LAUNCH_OK();
 }
 

@@ -11,6 +11,8 @@ def main(batch=16, size=128, steps=5, depth=18, warmup=2):
     model = generate_model(model_depth=depth, input_W=size, input_H=size, input_D=size, nb_class=3, pretrain_path=None,
                            dropout_rate=0.5, device=torch.device("cuda", 0))
     model.train()
+    if os.environ.get("MMAD_NO_SIDE"):
+        model.wgrad_side_stream = False
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
     crit = nn.CrossEntropyLoss()
     x = torch.rand(batch, 1, size, size, size, device="cuda")
