@@ -52,12 +52,15 @@ constexpr int kConvProducers = 3;          // warps 0, 2, 3
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
 constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
 
-template <int BN>
+// KS = K-steps per pipeline stage.  The TMA unit spends ~350 cycles per box whatever its size, so for narrow N tiles
+// (BN = 64 / 128, MMA time 132 / 264 cycles per K-step) the box COUNT is the bound: a stage then carries KS input boxes
+// and ONE weight box covering the KS consecutive K-slices (weights viewed as [64 ci][co][K-slice], see the host code).
+template <int BN, int KS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
     constexpr int B_TILE = BN * 128;
-    constexpr int STAGE = kATileBytes + B_TILE;
+    constexpr int STAGE = KS * (kATileBytes + B_TILE);      // KS input tiles, then KS weight tiles
     constexpr uint32_t IDESC = umma_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulator buffers (128, 256 or 512 columns)
 
@@ -95,7 +98,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ksteps = taps * g.kc;
 
     if (warp == 0 || warp == 2 || warp == 3) {
-        // ============================ TMA producers: K-step i is issued by producer i % 3 ============================
+        // ============================ TMA producers: stage i is issued by producer i % 3 ============================
         if (lane == 0) {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
@@ -108,26 +111,35 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int n = r;
                 const int w0 = wt * g.tw * g.stride - g.pad, h0 = ht * g.th * g.stride - g.pad,
                           d0 = dt * g.td * g.stride - g.pad;
-                uint32_t mw = tap_axis_mask(wt * g.tw, g.tw, g.W, g.kw, g.stride, g.pad, g.dil);
-                uint32_t mh = tap_axis_mask(ht * g.th, g.th, g.H, g.kh, g.stride, g.pad, g.dil);
-                uint32_t md = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
-                if (!mw || !mh || !md) mw = mh = md = 0xffffffffu;      // degenerate tile: run everything (all zeros)
-                int tap = 0;
+                uint32_t mw = 0xffffffffu, mh = 0xffffffffu, md = 0xffffffffu;
+                if (KS == 1) {                              // tap skipping needs per-K-step weight boxes
+                    mw = tap_axis_mask(wt * g.tw, g.tw, g.W, g.kw, g.stride, g.pad, g.dil);
+                    mh = tap_axis_mask(ht * g.th, g.th, g.H, g.kh, g.stride, g.pad, g.dil);
+                    md = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
+                    if (!mw || !mh || !md) mw = mh = md = 0xffffffffu;      // degenerate tile: run everything (all zeros)
+                }
+                int tap = 0, kslice = 0, gpos = 0;          // gpos: position inside the current stage (0..KS-1)
                 for (int a = 0; a < g.kd; ++a)
                     for (int b = 0; b < g.kh; ++b)
                         for (int c = 0; c < g.kw; ++c, ++tap) {
-                            if (!((md >> a) & (mh >> b) & (mw >> c) & 1u)) continue;
-                            for (int cc = 0; cc < g.kc; ++cc) {
+                            if (!((md >> a) & (mh >> b) & (mw >> c) & 1u)) { kslice += g.kc; continue; }
+                            for (int cc = 0; cc < g.kc; ++cc, ++kslice) {
+                                const uint32_t sa = stage0 + s * STAGE;
                                 if (turn == me) {
-                                    mbar_wait(empty0 + 8 * s, ph ^ 1);
-                                    mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
-                                    const uint32_t sa = stage0 + s * STAGE;
-                                    tma_load_5d(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
+                                    if (gpos == 0) {
+                                        const int nv = min(KS, ksteps - kslice);        // K-steps in this stage (KS > 1: no skipping)
+                                        mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(nv * kATileBytes + KS * B_TILE));
+                                        tma_load_3d(sa + KS * kATileBytes, &tmB, full0 + 8 * s, 0, nt * BN, kslice);
+                                    }
+                                    tma_load_5d(sa + gpos * kATileBytes, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
                                                 d0 + a * g.dil, n);
-                                    tma_load_3d(sa + kATileBytes, &tmB, full0 + 8 * s, cc * 64, tap, nt * BN);
                                 }
-                                if (++turn == kConvProducers) turn = 0;
-                                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                                if (++gpos == KS || kslice + 1 == ksteps) {
+                                    gpos = 0;
+                                    if (++turn == kConvProducers) turn = 0;
+                                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                                }
                             }
                         }
             }
@@ -142,8 +154,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 // same tap selection as the producer
-                int ksteps_t;
-                {
+                int ksteps_t = ksteps;
+                if (KS == 1) {
                     int r = tile / g.n_tiles;
                     const int wt = r % g.tiles_w; r /= g.tiles_w;
                     const int ht = r % g.tiles_h; r /= g.tiles_h;
@@ -153,15 +165,18 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t md = tap_axis_mask(dt * g.td, g.td, g.D, g.kd, g.stride, g.pad, g.dil);
                     ksteps_t = (!mw || !mh || !md) ? ksteps : __popc(mw) * __popc(mh) * __popc(md) * g.kc;
                 }
-                for (int k = 0; k < ksteps_t; ++k) {
+                for (int k = 0; k < ksteps_t; k += KS) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = stage0 + s * STAGE;
-                    const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-                    const uint64_t bdesc = umma_desc_sw128(sa + kATileBytes, 16, 1024);
+                    const int nv = min(KS, ksteps_t - k);
+                    for (int q = 0; q < nv; ++q) {
+                        const uint64_t adesc = umma_desc_sw128(sa + q * kATileBytes, 16, 1024);
+                        const uint64_t bdesc = umma_desc_sw128(sa + KS * kATileBytes + q * B_TILE, 16, 1024);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)                   // 4 x K16 inside the 64-wide (128-byte) swizzled row
-                        umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                        for (int j = 0; j < 4; ++j)               // 4 x K16 inside the 64-wide (128-byte) swizzled row
+                            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                    }
                     umma_commit(empty0 + 8 * s);                  // frees the smem slot when these MMAs retire
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
@@ -351,7 +366,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                     if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);   // bytes of BOTH CTAs
                                     const uint32_t sa = stage0 + s * STAGE;
                                     tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
-                                    tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, cc * 64, tap, nt * BN + (int)rank * (BN / 2));
+                                    tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
                                 }
                                 if (++turn == kConvProducers) turn = 0;
                                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -514,8 +529,8 @@ static void pick_tile(int Wo, int Ho, int Do, int stride, int& tw, int& th, int&
         }
 }
 
-static int conv_smem_bytes(int bn, int stages, int nout, int cout) {
-    return 1024 + stages * (kATileBytes + bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
+static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout) {
+    return 1024 + stages * ks * (kATileBytes + bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
 }
 
 // CTA-pair kernel for 256-channel N tiles: on unless MMAD_CONV_PAIR=0
@@ -574,11 +589,18 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     g.kc = Cin / 64;
     const bool pairk = use_pair_kernel(bn, g.m_tiles);
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
+    const int ks = bn == 64 ? 4 : (bn == 128 ? 2 : 1);     // K-steps per stage (one weight box per stage)
     g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && conv_smem_bytes(bn_stage, stages, g.nout, Cout) > 227 * 1024) --stages;
+    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024) --stages;
+    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
+        g.nout = 1;                                        // trade the second epilogue buffer for pipeline depth
+        stages = 8;
+        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024) --stages;
+    }
     g.stages = stages;
-    const int smem = conv_smem_bytes(bn_stage, stages, g.nout, Cout);
+    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout);
+    MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_fwd: shared memory budget exceeded");
 
     CUtensorMap tmA, tmB, tmC;
     {
@@ -590,10 +612,12 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         if (rc) return rc;
     }
     {
+        // weights [Cout][taps][Cin] viewed as [64 ci][co][K-slice]: K-slice = tap * (Cin/64) + ci block, 128 bytes apart, so a
+        // box of KS consecutive K-slices lands as KS consecutive canonical K-major B tiles
         const int taps = k * k * k;
-        const uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout};
-        const uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2};
-        const uint32_t box[3] = {64, 1, (uint32_t)bn_stage};
+        const uint64_t dims[3] = {64, (uint64_t)Cout, (uint64_t)taps * (Cin / 64)};
+        const uint64_t str[2] = {(uint64_t)taps * Cin * 2, 128};
+        const uint32_t box[3] = {64, (uint32_t)bn_stage, (uint32_t)ks};
         const uint32_t es[3] = {1, 1, 1};
         int rc = make_tmap_bf16(&tmB, w, 3, dims, str, box, es);
         if (rc) return rc;
@@ -624,18 +648,18 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         return MMAD_OK;
     }
     const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
-#define MMAD_CONV_LAUNCH(BNV)                                                                                               \
+#define MMAD_CONV_LAUNCH(BNV, KSV)                                                                                             \
     do {                                                                                                                    \
         static bool attr_done = false;                                                                                      \
         if (!attr_done) {                                                                                                   \
-            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BNV, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_done = true;                                                                                               \
         }                                                                                                                   \
-        conv3d_igemm_kernel<BNV><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);                       \
+        conv3d_igemm_kernel<BNV, KSV><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);                  \
     } while (0)
-    if (bn == 64) MMAD_CONV_LAUNCH(64);
-    else if (bn == 128) MMAD_CONV_LAUNCH(128);
-    else MMAD_CONV_LAUNCH(256);
+    if (bn == 64) MMAD_CONV_LAUNCH(64, 4);
+    else if (bn == 128) MMAD_CONV_LAUNCH(128, 2);
+    else MMAD_CONV_LAUNCH(256, 1);
 #undef MMAD_CONV_LAUNCH
     MMAD_CUDA(cudaGetLastError());
     count_launch();

@@ -225,47 +225,30 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
     float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sgx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long per = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = per * blockIdx.x, r1 = min(rows, r0 + per);
-    // two rows per iteration: all loads of both rows are issued before either is consumed (bytes in flight)
-    for (long long r = r0 + tr; r < r1; r += 2 * rpb) {
-        const long long ia = r * cv + tv;
-        const bool hasb = r + rpb < r1;
-        const long long ib = hasb ? ia + (long long)rpb * cv : ia;
-        uint4 qd[2], q2[2], qm[2], qx[2];
-        float4 fa[2], fb[2];
-        const long long ii[2] = {ia, ib};
+    for (long long r = r0 + tr; r < r1; r += rpb) {
+        const long long i = r * cv + tv;
+        float g[8];
+        if (dy_bf16) unpack8(dy_bf16[i], g);
+        else { const float4 a = dy_f32[2 * i], b = dy_f32[2 * i + 1]; g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w; }
+        if (dy2) { float h[8]; unpack8(dy2[i], h);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (dy_bf16) qd[u] = dy_bf16[ii[u]]; else { fa[u] = dy_f32[2 * ii[u]]; fb[u] = dy_f32[2 * ii[u] + 1]; }
-            if (dy2) q2[u] = dy2[ii[u]];
-            if (mask) qm[u] = mask[ii[u]];
-            qx[u] = x[ii[u]];
+            for (int j = 0; j < 8; ++j) g[j] += h[j]; }
+        if (mask) { float m[8]; unpack8(mask[i], m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
+        float xv[8];
+        unpack8(x[i], xv);
+        if (mscale) {                 // ReLU mask recomputed from the pre-BN tensor: relu(x*scale + shift) > 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+        }
+        if (g_out) {
+            const uint4 gp = pack8(g);
+            g_out[i] = gp;
+            unpack8(gp, g);          // statistics of the ROUNDED g, the values pass 2 will read
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !hasb) break;
-            float g[8];
-            if (dy_bf16) unpack8(qd[u], g);
-            else { g[0] = fa[u].x; g[1] = fa[u].y; g[2] = fa[u].z; g[3] = fa[u].w; g[4] = fb[u].x; g[5] = fb[u].y; g[6] = fb[u].z; g[7] = fb[u].w; }
-            if (dy2) { float h[8]; unpack8(q2[u], h);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] += h[j]; }
-            if (mask) { float m[8]; unpack8(qm[u], m);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] = m[j] > 0.f ? g[j] : 0.f; }
-            float xv[8];
-            unpack8(qx[u], xv);
-            if (mscale) {                 // ReLU mask recomputed from the pre-BN tensor: relu(x*scale + shift) > 0
-#pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] = fmaf(xv[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
-            }
-            if (g_out) {
-                const uint4 gp = pack8(g);
-                g_out[ii[u]] = gp;
-                unpack8(gp, g);          // statistics of the ROUNDED g, the values pass 2 will read
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { sg[j] += g[j]; sgx[j] += g[j] * (xv[j] - mu[j]) * is[j]; }
-        }
+        for (int j = 0; j < 8; ++j) { sg[j] += g[j]; sgx[j] += g[j] * (xv[j] - mu[j]) * is[j]; }
     }
     float* my = red + threadIdx.x * 16;
 #pragma unroll
@@ -618,7 +601,7 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
     LAUNCH_OK();
 }
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
-int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 8)); }
+int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148 * 4)); }
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2, const void* mask, const void* x, const float* mean,
                        const float* invstd, const float* mask_scale, const float* mask_shift, void* g_out, float* partials, int64_t rows,
                        int C, void* stream) {
