@@ -49,6 +49,8 @@ __device__ __forceinline__ uint32_t tap_axis_mask(int o0, int tl, int extent, in
 
 constexpr int kConvThreads = 256;
 constexpr int kConvProducers = 3;          // warps 0, 2, 3
+// A producer re-enters the ring every nprod stages and waits on a PARITY, so it must never be two phases ahead of a
+// slot: that needs stages >= active producers (nprod = min(kConvProducers, stages)).
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
 constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
 
@@ -102,6 +104,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
+            const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
                 int r = mt;
@@ -137,7 +140,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 }
                                 if (++gpos == KS || kslice + 1 == ksteps) {
                                     gpos = 0;
-                                    if (++turn == kConvProducers) turn = 0;
+                                    if (++turn == nprod) turn = 0;
                                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                                 }
                             }
@@ -345,6 +348,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
+            const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
             for (int st = pair; st < total_super; st += n_pairs) {
                 const int nt = st % g.n_tiles, mp = st / g.n_tiles;
                 int r = 2 * mp + (int)rank;                 // this CTA's voxel tile (may be the phantom tile past the end:
@@ -368,7 +372,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                     tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
                                     tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
                                 }
-                                if (++turn == kConvProducers) turn = 0;
+                                if (++turn == nprod) turn = 0;
                                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                             }
                         }
@@ -589,7 +593,9 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     g.kc = Cin / 64;
     const bool pairk = use_pair_kernel(bn, g.m_tiles);
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
-    const int ks = bn == 64 ? 4 : (bn == 128 ? 2 : 1);     // K-steps per stage (one weight box per stage)
+    static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
+    if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
+    const int ks = ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1));     // K-steps per stage (one weight box per stage)
     g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
     while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024) --stages;
@@ -657,8 +663,10 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         }                                                                                                                   \
         conv3d_igemm_kernel<BNV, KSV><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);                  \
     } while (0)
-    if (bn == 64) MMAD_CONV_LAUNCH(64, 4);
-    else if (bn == 128) MMAD_CONV_LAUNCH(128, 2);
+    if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);
+    else if (bn == 64) MMAD_CONV_LAUNCH(64, 1);
+    else if (bn == 128 && ks == 2) MMAD_CONV_LAUNCH(128, 2);
+    else if (bn == 128) MMAD_CONV_LAUNCH(128, 1);
     else MMAD_CONV_LAUNCH(256, 1);
 #undef MMAD_CONV_LAUNCH
     MMAD_CUDA(cudaGetLastError());

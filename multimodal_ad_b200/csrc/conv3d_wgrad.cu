@@ -101,6 +101,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
+            const uint32_t nprod = (uint32_t)min(kWgProducers, S);     // parity waits: a producer must not lap a slot twice, so stages >= active producers
             WgTapOff toff[4];
             for (int a = 0; a < nu; ++a) wg_tap_offsets(g, u0 + a, toff[a]);
             for (int c = c_begin; c < c_end; ++c) {
@@ -132,7 +133,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         }
                     }
                 }
-                if (++turn == kWgProducers) turn = 0;
+                if (++turn == nprod) turn = 0;
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }

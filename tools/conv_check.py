@@ -51,6 +51,8 @@ if __name__ == "__main__":
         (1, 5, 7, 9, 64, 64, 3, 1, 1, 1),       # ragged extents (tiles partly out of bounds)
         (1, 6, 11, 23, 64, 512, 3, 1, 4, 4),    # dilation 4, Cout 512 (two N tiles)
         (2, 32, 32, 32, 64, 64, 3, 1, 1, 1),    # many tiles per CTA (persistent loop, TMEM double buffer)
+        (1, 1, 1, 4194304, 384, 64, 1, 1, 0, 1),  # the stem GEMM at full size (16 x 64^3 rows x 384)
+        (1, 1, 1, 300000, 384, 64, 1, 1, 0, 1),
     ]
     sel = [int(a) for a in sys.argv[1:]] or range(len(cfgs))
     ok = True
