@@ -13,6 +13,10 @@
 #include "tc_common.cuh"
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
+#include <cstdio>
 #include <cstdlib>
 
 namespace mmad {
@@ -21,8 +25,10 @@ struct WgradGeom {
     int N, D, H, W, Cin;
     int Do, Ho, Wo, Cout;
     int k, taps, stride, pad, dil;
-    int tw, th, td;               // output-voxel chunk box, tw*th*td == 64
+    int tw, th, td, tn;           // output-voxel chunk box (tn batch samples deep), tw*th*td*tn == 64 (128: pair kernel)
     int tiles_w, tiles_h, tiles_d, n_chunks;
+    int pairk;                    // 1: CTA-pair kernel (cta_group::2)
+    int cv;                       // voxels per K chunk (64 or 128)
     int mode2;                    // 1: Cin == 64, an M block is two taps x 64 ci; 0: one tap x 128 ci
     int units;                    // M blocks in total
     int cib;                      // ci blocks per tap (mode 1): Cin / 128
@@ -109,7 +115,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const int wt = r % g.tiles_w; r /= g.tiles_w;
                 const int ht = r % g.tiles_h; r /= g.tiles_h;
                 const int dt = r % g.tiles_d; r /= g.tiles_d;
-                const int n = r;
+                const int n = r * g.tn;
                 const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td;
                 // a block is skipped for a chunk whose input boxes are all padding - except on the first chunk of the K
                 // slice, which always runs so that every accumulator gets initialised
@@ -213,19 +219,240 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-static void pick_chunk(int Wo, int Ho, int Do, int stride, int& tw, int& th, int& td) {
-    double best = 1e30;
-    for (int a = 1; a <= 64; a *= 2)
-        for (int b = 1; a * b <= 64; b *= 2) {
-            const int c = 64 / (a * b);
-            if (a * stride > 256 || b * stride > 256 || c * stride > 256) continue;
-            const double cover = (double)((Wo + a - 1) / a * a) * ((Ho + b - 1) / b * b) * ((Do + c - 1) / c * c);
-            const double score = cover - 1e-3 * a;
-            if (score < best) { best = score; tw = a; th = b; td = c; }
+
+// ===============================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for Cin >= 128 and Cout >= 128.  The single-CTA kernel above is bound by the
+// NUMBER of TMA boxes it needs per MMA cycle (a box costs ~300 cycles of TMA time whatever its size): 8 boxes of 8 KB per
+// 1024 MMA cycles.  Here a K chunk is 128 voxels (16 KB boxes), an accumulator block is 256 rows x NB columns spread over the
+// two CTAs (each CTA stages the X boxes of ITS unit and only HALF of the dY columns), so a CTA issues 6 boxes per 2048 MMA
+// cycles.  Block a of a pair holds units u0 + 2a (leader) and u0 + 2a + 1 (peer).  Barrier protocol as in
+// conv3d_igemm_pair_kernel: the leader's full barrier collects both CTAs' bytes, tcgen05.commit is multicast to both.
+// ===============================================================================================================
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradGeom g,
+                         float* __restrict__ partials) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    const int S = g.stages;
+    const int nbox_b = g.nb / 128;                                          // dY boxes of this CTA's column half
+    const uint32_t boxb = (uint32_t)g.cv * 128u;                            // one box: cv voxels x 64 channels bf16
+    const uint32_t STAGE = (uint32_t)(nbox_b + 2 * g.nacc) * boxb;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * STAGE);   // full[S], empty[S], tfull
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull = empty0 + 8 * S;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    int item = blockIdx.x >> 1;
+    const int ug = item % g.ugroups; item /= g.ugroups;
+    const int nt = item % g.n_tiles; item /= g.n_tiles;
+    const int ks = item;
+    const int u0 = ug * 2 * g.nacc;
+    const int nblk = min(g.nacc, (g.units - u0 + 1) / 2);                   // accumulator blocks this pair really owns
+    const int c_begin = (int)((long long)g.n_chunks * ks / g.nsplit), c_end = (int)((long long)g.n_chunks * (ks + 1) / g.nsplit);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY);
+    }
+    if (warp == 2) tmem_alloc_2sm(smem_u32(tmem_ptr_s), 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    // Per accumulator block (registers, static indexing): the input-box origin offset of THIS CTA's unit, and for both
+    // units of the block one bit mask per axis of the chunk tiles whose input range is entirely padding (bit i = tile i).
+    // A block is skipped for a chunk when the boxes of BOTH its units are padding - the same decision in both CTAs and in
+    // the MMA issuer; the first chunk of the K slice always runs so that every accumulator gets initialised.
+    int offw[2], offh[2], offd[2], cib0[2];
+    uint32_t oobw[2][2], oobh[2][2], oobd[2][2];
+    auto axis_oob = [&](int off, int t, int tiles, int ext) -> uint32_t {
+        uint32_t m = 0;
+        if (g.can_skip)
+            for (int i = 0; i < tiles; ++i) {
+                const int lo = i * t * g.stride + off;
+                if (lo + (t - 1) * g.stride < 0 || lo >= ext) m |= 1u << i;
+            }
+        return m;
+    };
+    if (lane == 0 && warp < 4) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int u = min(u0 + 2 * a + h, g.units - 1);                 // phantom unit past the end: the last one again
+                const int tap = u / g.cib;
+                const int ow = (tap % g.k) * g.dil - g.pad, oh = ((tap / g.k) % g.k) * g.dil - g.pad, od = (tap / (g.k * g.k)) * g.dil - g.pad;
+                oobw[a][h] = axis_oob(ow, g.tw, g.tiles_w, g.W);
+                oobh[a][h] = axis_oob(oh, g.th, g.tiles_h, g.H);
+                oobd[a][h] = axis_oob(od, g.td, g.tiles_d, g.D);
+                if (h == (int)rank) { offw[a] = ow; offh[a] = oh; offd[a] = od; cib0[a] = (u % g.cib) * 128; }
+            }
+    }
+    // chunk iterator: tile coordinates advanced incrementally (the loops below are single-thread critical paths)
+    int wt, ht, dt, nn;
+    {
+        int r = c_begin;
+        wt = r % g.tiles_w; r /= g.tiles_w;
+        ht = r % g.tiles_h; r /= g.tiles_h;
+        dt = r % g.tiles_d; r /= g.tiles_d;
+        nn = r;
+    }
+    auto next_chunk = [&]() {
+        if (++wt == g.tiles_w) { wt = 0; if (++ht == g.tiles_h) { ht = 0; if (++dt == g.tiles_d) { dt = 0; ++nn; } } }
+    };
+    auto chunk_skip = [&](int c) -> uint32_t {
+        if (c == c_begin) return 0u;
+        uint32_t skip = 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+            if (a < nblk)
+                skip |= ((((oobw[a][0] >> wt) | (oobh[a][0] >> ht) | (oobd[a][0] >> dt)) & ((oobw[a][1] >> wt) | (oobh[a][1] >> ht) | (oobd[a][1] >> dt))) & 1u) << a;
+        return skip;
+    };
+
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ============================ TMA producers (in both CTAs) ============================
+        if (lane == 0) {
+            // every producer thread takes part in EVERY stage and issues every third box of it, so that the issue time of a
+            // (large, two-deep) stage stays off the critical path
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+            uint32_t s = 0, ph = 0;
+            for (int c = c_begin; c < c_end; ++c, next_chunk()) {
+                const uint32_t skip = chunk_skip(c);
+                if (__popc(skip) == nblk) continue;
+                const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td, n0 = nn * g.tn;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                if (leader && me == 0)
+                    mbar_arrive_expect_tx(full0 + 8 * s, 2u * (uint32_t)(nbox_b + 2 * (nblk - __popc(skip))) * boxb);
+                const uint32_t sb = base + s * STAGE;
+                uint32_t q = 0;
+                for (int j = 0; j < nbox_b; ++j, ++q)
+                    if (q % kWgProducers == me)
+                        tma_load_5d_2sm(sb + j * boxb, &tmDY, full0 + 8 * s, nt * g.nb + (int)rank * (g.nb / 2) + 64 * j, ow0, oh0, od0, n0);
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    if (a >= nblk || ((skip >> a) & 1u)) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h, ++q)
+                        if (q % kWgProducers == me)
+                            tma_load_5d_2sm(sb + (uint32_t)(nbox_b + 2 * a + h) * boxb, &tmX, full0 + 8 * s, cib0[a] + 64 * h,
+                                            ow0 * g.stride + offw[a], oh0 * g.stride + offh[a], od0 * g.stride + offd[a], n0);
+                }
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+            }
         }
+    }
+    if (warp == 1) {
+        // ============================ MMA issuer: leader CTA only ============================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_bf16(256, g.nb, 1, 1);
+            uint32_t s = 0, ph = 0;
+            for (int c = c_begin; c < c_end; ++c, next_chunk()) {
+                const uint32_t skip = chunk_skip(c);
+                if (__popc(skip) == nblk) continue;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t sb = base + s * STAGE;
+                const uint64_t bdesc = umma_desc_sw128(sb, boxb, 1024);
+                for (int a = 0; a < nblk; ++a) {
+                    if ((skip >> a) & 1u) continue;
+                    const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * boxb, boxb, 1024);
+                    if (g.cv == 128) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)               // K16 = 16 voxel rows = 2048 bytes
+                            umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                    }
+                }
+                umma_commit_2sm(empty0 + 8 * s, 3);
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+            }
+            umma_commit_2sm(tfull, 3);
+        }
+    }
+    if (warp >= 4) {
+        // ============================ epilogue (both CTAs): own 128 accumulator rows -> fp32 partials ============================
+        const int ew = warp - 4;
+        const int m = ew * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const size_t plane = (size_t)g.Cout * g.taps * g.Cin;
+        float* out = partials + (size_t)ks * plane;
+        for (int a = 0; a < nblk; ++a) {
+            const int u = u0 + 2 * a + (int)rank;
+            const bool valid = u < g.units;
+            const int tap = u / g.cib, ci = (u % g.cib) * 128 + m;
+            for (int n0 = 0; n0 < g.nb; n0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + a * g.nb + n0, v);
+                tmem_ld_wait();
+                if (c_end == c_begin) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int co = nt * g.nb + n0 + j;
+                        out[((size_t)co * g.taps + tap) * g.Cin + ci] = __uint_as_float(v[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int sms) {
+// (chunk, tap) pairs along one axis whose input range is not entirely padding (closed form: the stem view has millions of tiles)
+static long long axis_work(int ext_in, int ext_out, int t, int k, int stride, int pad, int dil) {
+    auto ceil_div = [](long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); };
+    const long long tiles = (ext_out + t - 1) / t, step = (long long)t * stride;
+    long long w = 0;
+    for (int tap = 0; tap < k; ++tap) {
+        const long long off = (long long)tap * dil - pad;
+        // tile i covers input [i*step + off, i*step + off + (t-1)*stride]
+        const long long below = std::min(tiles, std::max(0LL, ceil_div(-off - (long long)(t - 1) * stride, step)));   // entirely < 0
+        const long long first_above = std::min(tiles, std::max(0LL, ceil_div((long long)ext_in - off, step)));           // first tile >= ext
+        w += std::max(0LL, first_above - below);
+    }
+    return w;
+}
+
+// K-chunk box tw x th x td x tn of `cv` output voxels (powers of two; tn > 1 only when the batch divides) with the fewest
+// (chunk, tap) pairs left after padding skips; ties go to the widest box in W (longer contiguous rows).
+static void pick_chunk(int cv, int N, int W, int H, int D, int Wo, int Ho, int Do, int k, int stride, int pad, int dil, int& tw,
+                       int& th, int& td, int& tn) {   // (callers may override the result: MMAD_WG_SHAPE)
+    double best = 1e30;
+    for (int n = 1; n <= 2; n *= 2) {
+        if (N % n) continue;
+        for (int a = 1; a <= cv / n; a *= 2)
+            for (int b = 1; a * b <= cv / n; b *= 2) {
+                const int c = cv / n / (a * b);
+                if (a * stride > 256 || b * stride > 256 || c * stride > 256) continue;
+                const double work = (double)(N / n) * axis_work(W, Wo, a, k, stride, pad, dil) * axis_work(H, Ho, b, k, stride, pad, dil) *
+                                    axis_work(D, Do, c, k, stride, pad, dil);
+                const double score = work * (1.0 + 1e-3 * n) - 1e-3 * a;
+                if (score < best) { best = score; tw = a; th = b; td = c; tn = n; }
+            }
+    }
+}
+
+static int fill_geom_uncached(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int sms) {
     g = WgradGeom{};
     g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
     g.k = k; g.taps = k * k * k; g.stride = stride; g.pad = pad; g.dil = dil;
@@ -233,21 +460,37 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
     g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     if (g.Do <= 0 || g.Ho <= 0 || g.Wo <= 0) return -1;
-    pick_chunk(g.Wo, g.Ho, g.Do, stride, g.tw, g.th, g.td);
-    g.tiles_w = (g.Wo + g.tw - 1) / g.tw; g.tiles_h = (g.Ho + g.th - 1) / g.th; g.tiles_d = (g.Do + g.td - 1) / g.td;
-    const long long chunks = (long long)N * g.tiles_w * g.tiles_h * g.tiles_d;
-    if (chunks > 0x7fffffffLL) return -1;
-    g.n_chunks = (int)chunks;
     g.mode2 = Cin == 64;
     g.cib = g.mode2 ? 1 : Cin / 128;
     g.units = g.mode2 ? (g.taps + 1) / 2 : g.taps * g.cib;
     g.nb = std::min(256, Cout);
     g.n_tiles = Cout / g.nb;
-    g.nacc = g.nb == 256 ? 2 : (g.nb == 128 ? 3 : 4);
-    if (const char* e = getenv("MMAD_WG_NACC")) g.nacc = std::max(1, std::min(g.nacc, atoi(e)));   // tuning knob
-    g.nacc = std::min(g.nacc, g.units);
-    g.ugroups = (g.units + g.nacc - 1) / g.nacc;
+    static int pair_mode = -1;                         // CTA-pair kernel: on unless MMAD_WG_PAIR=0
+    if (pair_mode < 0) { const char* e = getenv("MMAD_WG_PAIR"); pair_mode = e ? atoi(e) : 1; }
+    g.pairk = pair_mode != 0 && !g.mode2 && g.nb >= 128 && g.units >= 2;
+    g.cv = 64;
+    if (g.pairk) { static int pcv = -1; if (pcv < 0) { const char* e = getenv("MMAD_WG_PAIR_CV"); pcv = e ? atoi(e) : 128; } g.cv = pcv == 128 ? 128 : 64; }
+    pick_chunk(g.cv, N, W, H, D, g.Wo, g.Ho, g.Do, k, stride, pad, dil, g.tw, g.th, g.td, g.tn);
+    if (const char* e = getenv("MMAD_WG_SHAPE")) {     // tuning knob: "tw,th,td,tn" (product must equal the chunk size)
+        int a, b, c, n;
+        if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &n) == 4 && a * b * c * n == g.cv && N % n == 0) { g.tw = a; g.th = b; g.td = c; g.tn = n; }
+    }
+    g.tiles_w = (g.Wo + g.tw - 1) / g.tw; g.tiles_h = (g.Ho + g.th - 1) / g.th; g.tiles_d = (g.Do + g.td - 1) / g.td;
+    const long long chunks = (long long)(N / g.tn) * g.tiles_w * g.tiles_h * g.tiles_d;
+    if (chunks > 0x7fffffffLL) return -1;
+    g.n_chunks = (int)chunks;
+    if (g.pairk) {
+        g.nacc = 2;                                    // blocks of 256 rows (one unit per CTA): 2 x nb <= 512 TMEM columns
+        g.nacc = std::min(g.nacc, (g.units + 1) / 2);
+        g.ugroups = (g.units + 2 * g.nacc - 1) / (2 * g.nacc);
+    } else {
+        g.nacc = g.nb == 256 ? 2 : (g.nb == 128 ? 3 : 4);
+        if (const char* e = getenv("MMAD_WG_NACC")) g.nacc = std::max(1, std::min(g.nacc, atoi(e)));   // tuning knob
+        g.nacc = std::min(g.nacc, g.units);
+        g.ugroups = (g.units + g.nacc - 1) / g.nacc;
+    }
     const int items = g.n_tiles * g.ugroups;
+    if (g.pairk) sms /= 2;                             // the schedulable unit is a CTA pair
     // split count: at least ~2 waves of CTAs, and a grid that fills whole waves (the last wave is the tail)
     int best_s = 1;
     double best_score = -1.0;
@@ -259,20 +502,59 @@ static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout
         const double score = (double)ctas / (double)(waves * sms) - 0.004 * sp;
         if (score > best_score) { best_score = score; best_s = sp; }
     }
+    if (g.pairk) {
+        // pair kernel: an item costs ~25 us of fill + epilogue on top of ~1.5 us per 128-voxel chunk (measured), and every
+        // split adds a plane of fp32 partials to write and reduce: minimise the modelled time.  In a single wave the slowest
+        // item (a tap that never falls in the padding) sets the time; over several waves the padding skips average out.
+        const double frac = (double)(axis_work(W, g.Wo, g.tw, k, stride, pad, dil) * axis_work(H, g.Ho, g.th, k, stride, pad, dil) *
+                                     axis_work(D, g.Do, g.td, k, stride, pad, dil)) /
+                            ((double)g.tiles_w * g.tiles_h * g.tiles_d * g.taps);
+        const double t_chunk = std::max(0.8, 1.5 * g.nb / 256.0) * g.cv / 128.0;
+        const double plane_mb = (double)Cout * g.taps * Cin * 4.0 / 1e6;
+        double best_t = 1e30;
+        for (int sp = 1; sp <= std::min(g.n_chunks, 64); ++sp) {
+            const long long pairs = (long long)items * sp;
+            const long long waves = (pairs + sms - 1) / sms;
+            const double f = waves == 1 ? 1.0 : 0.5 + 0.5 * frac;
+            const double t = waves * (((g.n_chunks + sp - 1) / sp) * t_chunk * f + 25.0) + sp * plane_mb * 0.25;
+            if (t < best_t) { best_t = t; best_s = sp; }
+        }
+    }
     g.nsplit = best_s;
-    const int stage = (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
+    if (const char* e = getenv("MMAD_WG_NSPLIT")) g.nsplit = std::max(1, std::min(g.n_chunks, atoi(e)));   // tuning knob
+    const int stage = g.pairk ? (g.nb / 128 + 2 * g.nacc) * g.cv * 128 : (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     g.stages = std::max(2, std::min(6, (227 * 1024 - 1024 - 256) / stage));
     if (const char* e = getenv("MMAD_WG_STAGES")) g.stages = std::max(1, std::min(g.stages, atoi(e)));   // tuning knob
     // is any (tap, chunk origin) input box entirely padding along some axis?  (only then is the per-chunk test worth running)
     g.can_skip = 0;
+    const bool masks_fit = !g.pairk || (g.tiles_w <= 32 && g.tiles_h <= 32 && g.tiles_d <= 32);   // pair kernel: 32-bit tile masks
     const int ext[3] = {W, H, D}, tl[3] = {g.tw, g.th, g.td}, nt[3] = {g.tiles_w, g.tiles_h, g.tiles_d};
-    for (int ax = 0; ax < 3 && !g.can_skip; ++ax)
+    for (int ax = 0; ax < 3 && !g.can_skip && masks_fit; ++ax)
         for (int t = 0; t < k && !g.can_skip; ++t)
             for (int i = 0; i < nt[ax]; ++i) {
                 const int lo = i * tl[ax] * stride + t * dil - pad;
                 if (lo + (tl[ax] - 1) * stride < 0 || lo >= ext[ax]) { g.can_skip = 1; break; }
             }
+    if (getenv("MMAD_WG_DEBUG"))
+        fprintf(stderr, "[wgrad] Cin %d Cout %d k %d s %d dil %d | pair %d cv %d chunk %dx%dx%dx%d chunks %d units %d nacc %d ugroups %d nsplit %d stages %d skip %d\n",
+                Cin, Cout, k, stride, dil, g.pairk, g.cv, g.tw, g.th, g.td, g.tn, g.n_chunks, g.units, g.nacc, g.ugroups, g.nsplit, g.stages, g.can_skip);
     return 0;
+}
+
+// The geometry (chunk shape search, split model) is pure host arithmetic on the argument tuple: computed once per distinct layer.
+static int fill_geom(WgradGeom& g, int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, int sms) {
+    static std::mutex mu;
+    static std::map<std::array<int, 11>, std::pair<int, WgradGeom>> cache;
+    const std::array<int, 11> key = {N, D, H, W, Cin, Cout, k, stride, pad, dil, sms};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        WgradGeom t;
+        const int rc = fill_geom_uncached(t, N, D, H, W, Cin, Cout, k, stride, pad, dil, sms);
+        it = cache.emplace(key, std::make_pair(rc, t)).first;
+    }
+    g = it->second.second;
+    return it->second.first;
 }
 
 }  // namespace mmad
@@ -306,7 +588,7 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     {
         const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
         const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};
-        const uint32_t box[5] = {64, (uint32_t)(g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), 1};
+        const uint32_t box[5] = {64, (uint32_t)(g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), (uint32_t)g.tn};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_tmap_bf16(&tmX, x, 5, dims, str, box, es);
         if (rc) return rc;
@@ -315,20 +597,23 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
         const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)N};
         const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)g.Wo * Cout * 2, (uint64_t)g.Ho * g.Wo * Cout * 2,
                                  (uint64_t)g.Do * g.Ho * g.Wo * Cout * 2};
-        const uint32_t box[5] = {64, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.td, 1};
+        const uint32_t box[5] = {64, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.td, (uint32_t)g.tn};
         const uint32_t es[5] = {1, 1, 1, 1, 1};
         int rc = make_tmap_bf16(&tmDY, dy, 5, dims, str, box, es);
         if (rc) return rc;
     }
-    const int stage = (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
+    const int stage = g.pairk ? (g.nb / 128 + 2 * g.nacc) * g.cv * 128 : (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     const int smem = 1024 + g.stages * stage + (2 * g.stages + 1) * 8 + 32;
+    MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_wgrad: shared memory budget exceeded");
     static bool attr_done = false;
     if (!attr_done) {
         MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     const int grid = g.n_tiles * g.ugroups * g.nsplit;
-    conv3d_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
+    if (g.pairk) conv3d_wgrad_pair_kernel<<<2 * grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
+    else conv3d_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
     MMAD_CUDA(cudaGetLastError());
     count_launch();
     return MMAD_OK;

@@ -34,11 +34,12 @@ def main(batch=16, size=128, steps=5, depth=18, warmup=2):
     a.record()
     for _ in range(steps):
         l = step()
+    enq_ms = (time.perf_counter() - t0) * 1e3 / steps      # host time to enqueue a step (== step time when host-bound)
     b.record(); b.synchronize()
     ms = a.elapsed_time(b) / steps
     host_ms = (time.perf_counter() - t0) * 1e3 / steps
     # FLOPs of the convolutions (forward), x3 for fwd + dgrad + wgrad
-    print(json.dumps(dict(batch=batch, size=size, ms_per_step=round(ms, 3), host_ms=round(host_ms, 3), vol_per_s=round(batch / ms * 1e3, 1),
+    print(json.dumps(dict(batch=batch, size=size, ms_per_step=round(ms, 3), host_ms=round(host_ms, 3), enqueue_ms=round(enq_ms, 3), vol_per_s=round(batch / ms * 1e3, 1),
                           loss=float(l.detach()), launches_per_step=(_lib.launch_count() - l0) / steps,
                           mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))), flush=True)
 

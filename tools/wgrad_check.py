@@ -55,6 +55,10 @@ if __name__ == "__main__":
         (1, 16, 16, 16, 64, 128, 1, 2, 0, 1),    # 1x1x1 stride 2
         (1, 5, 7, 9, 256, 512, 3, 1, 4, 4),      # ragged, dilation 4, two co tiles
         (1, 1, 1, 4096, 384, 64, 1, 1, 0, 1),    # stem view: rows x 384
+        (2, 16, 16, 16, 128, 128, 3, 1, 1, 1),   # pair kernel, odd unit count (phantom unit), batch-deep chunks
+        (2, 16, 16, 16, 256, 512, 3, 1, 4, 4),   # pair kernel, dilation 4 with padding skips, two co tiles
+        (3, 8, 8, 8, 128, 256, 3, 1, 1, 1),      # pair kernel, odd batch
+        (1, 16, 16, 16, 128, 256, 1, 1, 0, 1),   # pair kernel, 1x1x1 (one unit: phantom peer)
     ]
     sel = [int(a) for a in sys.argv[1:]] or range(len(cfgs))
     ok = True
