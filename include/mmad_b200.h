@@ -143,6 +143,29 @@ int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W,
 int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream);
 int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream);
 
+/* Stem without a materialised im2col matrix (the path the model uses).  The
+ * stride-2 7^3 convolution of one channel is rewritten as a stride-1 4^3
+ * convolution of the 8 space-to-depth phase channels (K = 512):
+ *   xs bf16 [N][Do+3][Ho+3][Wo+3][8],  xs[..][jd][jh][jw][pd*4+ph*2+pw] =
+ *   x[2jd+pd-3][2jh+ph-3][2jw+pw-3]   (mmad_stem_s2d_elems elements),
+ *   wk bf16 [64][512], K = ((kd*4+kh)*4+kw)*8 + phase, zero where a tap is 7.
+ * mmad_stem_s2d_fwd writes y (N,Do,Ho,Wo,64) bf16 and, unless NULL, the same
+ * per-CTA BatchNorm partials as mmad_conv3d_fwd_bf16
+ * ([mmad_stem_s2d_stats_partials][64][2]).  mmad_stem_s2d_wgrad replaces the
+ * weight-gradient half of conv1's backward: fp32 partials
+ * [nsplit][64][512] (mmad_stem_s2d_wgrad_workspace), summed into the torch
+ * layout (64,1,7,7,7) by mmad_stem_s2d_wgrad_reduce. */
+int64_t mmad_stem_s2d_elems(int N, int D, int H, int W);
+int mmad_stem_s2d_pack(const float* x, void* xs, int N, int D, int H, int W, void* stream);
+int mmad_stem_s2d_prep_weights(const float* w, void* wk, void* stream);
+int mmad_stem_s2d_stats_partials(int N, int D, int H, int W);
+int mmad_stem_s2d_fwd(const void* xs, const void* wk, void* y, float* stats_partials,
+                      int N, int D, int H, int W, void* stream);
+int64_t mmad_stem_s2d_wgrad_workspace(int N, int D, int H, int W, int* nsplit_out);
+int mmad_stem_s2d_wgrad(const void* xs, const void* dy, float* partials,
+                        int N, int D, int H, int W, void* stream);
+int mmad_stem_s2d_wgrad_reduce(const float* partials, int nsplit, float* dw, void* stream);
+
 /* BatchNorm3d (resnet.py:46,49,134), training statistics from the conv
  * epilogue's partials: mean, invstd, scale = gamma*invstd, shift = beta -
  * mean*scale (all float[C]); running_mean/var updated like nn.BatchNorm3d

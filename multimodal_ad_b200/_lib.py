@@ -68,6 +68,14 @@ def load() -> ctypes.CDLL:
         "mmad_stem_im2col": [P, P] + [I] * 8 + [P],
         "mmad_stem_prep_weights": [P, P, I, I, I, P],
         "mmad_stem_unpad_wgrad": [P, P, I, I, I, P],
+        "mmad_stem_s2d_elems": [I, I, I, I],
+        "mmad_stem_s2d_pack": [P, P, I, I, I, I, P],
+        "mmad_stem_s2d_prep_weights": [P, P, P],
+        "mmad_stem_s2d_stats_partials": [I, I, I, I],
+        "mmad_stem_s2d_fwd": [P, P, P, P, I, I, I, I, P],
+        "mmad_stem_s2d_wgrad_workspace": [I, I, I, I, P],
+        "mmad_stem_s2d_wgrad": [P, P, P, I, I, I, I, P],
+        "mmad_stem_s2d_wgrad_reduce": [P, I, P, P],
         "mmad_bn_finalize": [P, I, I, D_, P, P, F, F, P, P, P, P, P, P, P],
         "mmad_bn_eval_params": [I, P, P, P, P, F, P, P, P, P, P],
         "mmad_bn_apply": [P, P, P, P, P, P, I, P, P, L, I, P],
@@ -87,6 +95,9 @@ def load() -> ctypes.CDLL:
         getattr(lib, name).restype = I
     lib.mmad_conv3d_wgrad_workspace.argtypes = [I] * 10 + [POINTER(ctypes.c_int)]
     lib.mmad_conv3d_wgrad_workspace.restype = c_int64
+    lib.mmad_stem_s2d_elems.restype = c_int64
+    lib.mmad_stem_s2d_wgrad_workspace.argtypes = [I, I, I, I, POINTER(ctypes.c_int)]
+    lib.mmad_stem_s2d_wgrad_workspace.restype = c_int64
     for name in ("mmad_roi_plan_create", "mmad_roi_plan_create_ex", "mmad_roi_plan_destroy", "mmad_roi_plan_counts",
                  "mmad_roi_plan_counts_dev", "mmad_roi_pool_f32", "mmad_roi_pool_host_f32",
                  "mmad_roi_pool_mean_backward_f32", "mmad_roi_plan_programme", "mmad_roi_plan_binding"):

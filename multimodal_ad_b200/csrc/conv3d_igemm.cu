@@ -509,10 +509,16 @@ PFN_encodeTiled get_encode_tiled() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* basep, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides) {
+    return make_tmap_bf16_swz(out, basep, rank, dims, strides_bytes, box, elem_strides, 128);
+}
+
+int make_tmap_bf16_swz(CUtensorMap* out, const void* basep, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(MMAD_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(basep), dims, strides_bytes,
-                     box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MMAD_ECUDA, "cuTensorMapEncodeTiled failed (CUresult " + std::to_string((int)r) + ")");
     return MMAD_OK;

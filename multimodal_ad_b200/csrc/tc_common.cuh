@@ -19,6 +19,9 @@ PFN_encodeTiled get_encode_tiled();
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides fastest-first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides);
+// same with SWIZZLE_64B (swizzle_bytes == 64) or SWIZZLE_128B
+int make_tmap_bf16_swz(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

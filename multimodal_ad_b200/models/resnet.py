@@ -102,6 +102,7 @@ class _Run:
         # weight-gradient kernels are off the backward critical path: they go to a side stream so the HBM-bound
         # BatchNorm / ReLU kernels of the main chain run underneath the tensor-bound wgrad work
         self.side = _side_stream(device) if use_side_stream else None
+        self._keep = []                                    # tensors in use on the side stream, released by join_side()
 
     def empty(self, shape, dtype=torch.bfloat16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -124,6 +125,21 @@ class _Run:
                                                self.stream), "mmad_conv3d_fwd_bf16")
         return y, part
 
+    def stem_wgrad(self, xs, dy, n, d, h, w, out_dw):
+        """conv1 weight gradient from the space-to-depth input (include/mmad_b200.h: mmad_stem_s2d_wgrad); side stream like wgrad."""
+        nsplit = ctypes.c_int(0)
+        elems = self.lib.mmad_stem_s2d_wgrad_workspace(n, d, h, w, ctypes.byref(nsplit))
+        if elems < 0:
+            raise _lib.MmadError("mmad_stem_s2d_wgrad_workspace: bad geometry")
+        ws = self.empty((elems,), torch.float32)
+        cs = self.stream
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            cs = c_void_p(self.side.cuda_stream)
+            self._keep += [xs, dy, ws]                     # see wgrad()
+        self.chk(self.lib.mmad_stem_s2d_wgrad(_p(xs), _p(dy), _p(ws), n, d, h, w, cs), "mmad_stem_s2d_wgrad")
+        self.chk(self.lib.mmad_stem_s2d_wgrad_reduce(_p(ws), nsplit.value, _p(out_dw), cs), "mmad_stem_s2d_wgrad_reduce")
+
     def wgrad(self, x, dy, cout, k, stride, pad, dil, out_dw, on_done=None):
         """out_dw: fp32 tensor in torch layout (Cout, Cin, k,k,k) (or any tensor of Cout*Cin*taps elements).
         Runs on the side stream when the run has one; on_done() is then called with that stream current (used to start
@@ -138,8 +154,10 @@ class _Run:
         if self.side is not None:
             self.side.wait_stream(self.main)               # x and dy were produced on the main stream
             stream, cs = self.side, c_void_p(self.side.cuda_stream)
-            for t in (x, dy, ws, out_dw):
-                t.record_stream(self.side)                 # keep the caching allocator from reusing them early
+            # the operands belong to the main stream's allocator pool: hold them until join_side() instead of
+            # record_stream() (recorded blocks cannot be reused until an event query succeeds, which made the allocator
+            # fall back to cudaMalloc in the middle of the step)
+            self._keep += [x, dy, ws]
         self.chk(self.lib.mmad_conv3d_wgrad_bf16(_p(x), _p(dy), _p(ws), n, d, h, w, cin, cout, k, stride, pad, dil, cs),
                  "mmad_conv3d_wgrad_bf16")
         self.chk(self.lib.mmad_wgrad_reduce(_p(ws), nsplit.value, _p(out_dw), cout, cin, k * k * k, cs), "mmad_wgrad_reduce")
@@ -150,6 +168,7 @@ class _Run:
     def join_side(self):
         if self.side is not None:
             self.main.wait_stream(self.side)
+            self._keep.clear()                             # later main-stream work is ordered after the side stream's kernels
 
     def prep_weights(self, conv: nn.Conv3d, want_dgrad):
         cout, cin, k = conv.out_channels, conv.in_channels, conv.kernel_size[0]
@@ -217,17 +236,18 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     x = x.contiguous().float()
     tape = {"blocks": [], "training": training}
 
-    # ---- stem: conv1 7x7x7 s2 p3 as im2col + GEMM, bn1, relu, maxpool (resnet.py:205-208) ----
+    # ---- stem: conv1 7x7x7 s2 p3 as a space-to-depth implicit GEMM (no im2col matrix), bn1, relu, maxpool
+    #      (resnet.py:205-208) ----
     k, s, p = 7, 2, 3
     do, ho, wo = (d + 2 * p - k) // s + 1, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     rows = n * do * ho * wo
-    col = r.empty((1, 1, 1, rows, STEM_KPAD))
-    r.chk(lib.mmad_stem_im2col(_p(x), _p(col), n, d, h, w, k, s, p, STEM_KPAD, r.stream), "mmad_stem_im2col")
-    wstem = r.empty((64, 1, STEM_KPAD))
-    r.chk(lib.mmad_stem_prep_weights(_p(model.conv1.weight.detach()), _p(wstem), 64, k * k * k, STEM_KPAD, r.stream),
-          "mmad_stem_prep_weights")
-    c0, part = r.conv(col, wstem, 64, 1, 1, 0, 1, training)
-    c0 = c0.view(n, do, ho, wo, 64)
+    xs = r.empty((lib.mmad_stem_s2d_elems(n, d, h, w),))
+    r.chk(lib.mmad_stem_s2d_pack(_p(x), _p(xs), n, d, h, w, r.stream), "mmad_stem_s2d_pack")
+    wstem = r.empty((64, 512))
+    r.chk(lib.mmad_stem_s2d_prep_weights(_p(model.conv1.weight.detach()), _p(wstem), r.stream), "mmad_stem_s2d_prep_weights")
+    c0 = r.empty((n, do, ho, wo, 64))
+    part = r.empty((lib.mmad_stem_s2d_stats_partials(n, d, h, w), 64, 2), torch.float32) if training else None
+    r.chk(lib.mmad_stem_s2d_fwd(_p(xs), _p(wstem), _p(c0), _p(part), n, d, h, w, r.stream), "mmad_stem_s2d_fwd")
     v0 = r.bn_params(model.bn1, part, rows, training)
     pd, ph, pw = (do - 1) // 2 + 1, (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
     p0 = r.empty((n, pd, ph, pw, 64))
@@ -235,7 +255,7 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     # bn1 + relu + maxpool fused: the 64-channel full-resolution activation is never written
     r.chk(lib.mmad_stem_bn_relu_maxpool_fwd(_p(c0), _p(v0[2]), _p(v0[3]), _p(p0), _p(idx0), n, do, ho, wo, 64, r.stream),
           "mmad_stem_bn_relu_maxpool_fwd")
-    tape["stem"] = dict(col=col if need_grad else None, c0=c0, v0=v0, p0=p0, idx0=idx0, in_shape=(n, d, h, w))
+    tape["stem"] = dict(xs=xs if need_grad else None, c0=c0, v0=v0, p0=p0, idx0=idx0, in_shape=(n, d, h, w))
 
     # ---- residual stages (resnet.py:209-212) ----
     cur = p0
@@ -354,7 +374,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
 
-    # ---- stem backward: maxpool, relu+bn1 (mask recomputed from c0), wgrad of the im2col GEMM.  No input gradient: the MRI
+    # ---- stem backward: maxpool, relu+bn1 (mask recomputed from c0), wgrad of the space-to-depth GEMM.  No input gradient: the MRI
     #      volume is data ----
     stem = tape["stem"]
     n, d, h, w = stem["in_shape"]
@@ -370,12 +390,9 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
           "mmad_maxpool3d_bwd")
     dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=True, mask_from_x=True)
     grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
-    rows = dc0.numel() // 64
-    gwp = r.empty((64, STEM_KPAD), torch.float32)
-    r.wgrad(stem["col"], dc0.view(1, 1, 1, rows, 64), 64, 1, 1, 0, 1, gwp)
-    r.join_side()                                          # every weight gradient is complete on the main stream from here
     gw = torch.empty_like(model.conv1.weight)
-    r.chk(lib.mmad_stem_unpad_wgrad(_p(gwp), _p(gw), 64, 343, STEM_KPAD, r.stream), "mmad_stem_unpad_wgrad")
+    r.stem_wgrad(stem["xs"], dc0, n, d, h, w, gw)
+    r.join_side()                                          # every weight gradient is complete on the main stream from here
     grads[model.conv1.weight] = gw
     return grads
 

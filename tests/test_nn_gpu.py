@@ -53,6 +53,9 @@ WG_CASES = [
     (1, 4, 4, 4, 64, 64, 1, 1, 0, 1), (1, 4, 8, 8, 128, 128, 1, 1, 0, 1), (2, 8, 8, 8, 64, 64, 3, 1, 1, 1),
     (1, 8, 8, 16, 128, 256, 3, 1, 2, 2), (1, 16, 16, 16, 64, 128, 3, 2, 1, 1), (1, 16, 16, 16, 64, 128, 1, 2, 0, 1),
     (1, 5, 7, 9, 256, 512, 3, 1, 4, 4), (1, 1, 1, 4096, 384, 64, 1, 1, 0, 1),
+    # CTA-pair kernel: odd unit count (phantom unit), batch-deep chunks + padding skips, odd batch, single unit
+    (2, 16, 16, 16, 128, 128, 3, 1, 1, 1), (2, 16, 16, 16, 256, 512, 3, 1, 4, 4), (3, 8, 8, 8, 128, 256, 3, 1, 1, 1),
+    (1, 16, 16, 16, 128, 256, 1, 1, 0, 1),
 ]
 
 
@@ -210,3 +213,41 @@ def test_fused_stem_matches_unfused_kernels(shape, run):
     dx_a, g_a, dg_a, db_a = run.bn_bwd(da0, None, a0, c0, vec, gamma, True)
     dx_b, g_b, dg_b, db_b = run.bn_bwd(da0, None, None, c0, vec, gamma, True, mask_from_x=True)
     assert torch.equal(g_a, g_b) and torch.equal(dx_a, dx_b) and torch.equal(dg_a, dg_b) and torch.equal(db_a, db_b)
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 16), (2, 8, 8, 16), (1, 13, 11, 19), (2, 32, 32, 32), (1, 40, 31, 27)])
+def test_stem_space_to_depth_forward_statistics_wgrad(shape, run):
+    """conv1 (resnet.py:126-132) through mmad_stem_s2d_*: forward within one bf16 rounding step of torch fp32 on the same
+    bf16 operands, BatchNorm partials exact to fp32 summation, weight gradient to 1e-4 (fp32 accumulation)."""
+    from multimodal_ad_b200.models.resnet import _p
+
+    n, d, h, w = shape
+    lib = run.lib
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn((n, 1, d, h, w), device="cuda", generator=g)
+    wt = torch.randn((64, 1, 7, 7, 7), device="cuda", generator=g) / 343 ** 0.5
+    do, ho, wo = (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    xs = run.empty((lib.mmad_stem_s2d_elems(n, d, h, w),))
+    wk = run.empty((64, 512))
+    y = run.empty((n, do, ho, wo, 64))
+    part = run.empty((lib.mmad_stem_s2d_stats_partials(n, d, h, w), 64, 2), torch.float32)
+    run.chk(lib.mmad_stem_s2d_pack(_p(x), _p(xs), n, d, h, w, run.stream), "pack")
+    run.chk(lib.mmad_stem_s2d_prep_weights(_p(wt), _p(wk), run.stream), "prep")
+    run.chk(lib.mmad_stem_s2d_fwd(_p(xs), _p(wk), _p(y), _p(part), n, d, h, w, run.stream), "fwd")
+    # the packed tensors hold exactly the bf16 roundings of the operands
+    xp = F.pad(x[:, 0], (3, 2 * (wo + 3) - w - 3, 3, 2 * (ho + 3) - h - 3, 3, 2 * (do + 3) - d - 3)).to(torch.bfloat16)
+    xp = xp.view(n, do + 3, 2, ho + 3, 2, wo + 3, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(-1)
+    assert torch.equal(xs, xp)
+    xr = x.to(torch.bfloat16).float()
+    wr = wt.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv3d(xr, wr, stride=2, padding=3)
+    yf = y.float().permute(0, 4, 1, 2, 3)
+    assert torch.all((yf - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
+    st = part.double().sum(0)
+    assert torch.allclose(st[:, 0], yf.double().sum((0, 2, 3, 4)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[:, 1], (yf.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-5)
+    dy = torch.randn((n, do, ho, wo, 64), device="cuda", generator=g).to(torch.bfloat16)
+    gw = torch.empty_like(wt)
+    run.stem_wgrad(xs, dy, n, d, h, w, gw)
+    ref.backward(dy.float().permute(0, 4, 1, 2, 3))
+    assert _rel(gw, wr.grad) < 1e-4
