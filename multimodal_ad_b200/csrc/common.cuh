@@ -80,6 +80,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // previous kernel of the stream to complete and flush (no-ops when launched without the attribute).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// One lane of a fully converged warp (always the same one).  Warp-uniform loops whose asynchronous-unit instructions (TMA,
+// tcgen05) are issued under `if (elect_one())` compile to plain predicated UTMALDG / UTCHMMA on uniform registers; the
+// same instructions inside an `if (lane == 0)` region are wrapped by the compiler in an ELECT / R2UR / BRA.U.ANY
+// serialisation loop (~10 extra instructions per issue), which is what limits a "single thread" to one copy per ~300 cycles.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -57,12 +57,22 @@ constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 
 // KS = K-steps per pipeline stage.  The TMA unit spends ~350 cycles per box whatever its size, so for narrow N tiles
 // (BN = 64 / 128, MMA time 132 / 264 cycles per K-step) the box COUNT is the bound: a stage then carries KS input boxes
 // and ONE weight box covering the KS consecutive K-slices (weights viewed as [64 ci][co][K-slice], see the host code).
-template <int BN, int KS>
+//
+// WH ("w halo", 3x3x3 unit-stride undilated convolutions of 64 channels, KS == 3): the three kw taps of a (kd, kh) pair
+// read the SAME input box, loaded once with a halo of two voxels in W (10 x 4 x 4 voxels, tile 8 x 4 x 4).  UMMA applies
+// the 128-byte swizzle to absolute shared-memory address bits, so tap kw's operand is simply the box start plus kw rows
+// (128 bytes each), with the 8-row groups (one W line each) 10 rows = 1280 bytes apart.  27 input boxes per tile -> 9, and
+// 2.4x less L2->SM traffic, which is what bounds the 64-channel layers.
+constexpr int kHaloTileBytes = 160 * 128;  // 10 x 4 x 4 voxels x 64 bf16
+
+template <int BN, int KS, bool WH = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+    static_assert(!WH || KS == 3, "the W-halo variant stages the three kw taps of one (kd, kh) pair");
     constexpr int B_TILE = BN * 128;
-    constexpr int STAGE = KS * (kATileBytes + B_TILE);      // KS input tiles, then KS weight tiles
+    constexpr int A_REGION = WH ? kHaloTileBytes : KS * kATileBytes;
+    constexpr int STAGE = A_REGION + KS * B_TILE;           // input tiles (or one halo box), then KS weight tiles
     constexpr uint32_t IDESC = umma_idesc_bf16(128, BN, 0, 0);
     constexpr uint32_t TMEM_COLS = 2 * BN;      // two accumulator buffers (128, 256 or 512 columns)
 
@@ -101,7 +111,32 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: stage i is issued by producer i % 3 ============================
-        if (lane == 0) {
+        if (WH) {
+            // W-halo variant: 9 stages per tile, one per (kd, kh); 3 producers, 4 ring slots (host guarantees it).  Producer
+            // `me` owns kh == me of every kd, i.e. every third stage of the global stage sequence: no per-tap loop overhead in
+            // these single-thread loops, which otherwise cost more than the 384 MMA cycles of a stage.
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+            uint32_t G = me;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int r = tile;                               // n_tiles == 1 (Cout == 64)
+                const int wt = r % g.tiles_w; r /= g.tiles_w;
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r % g.tiles_d; r /= g.tiles_d;
+                const int w0 = wt * 8 - 1, h0 = ht * 4 - 1 + (int)me, d0 = dt * 4 - 1;
+#pragma unroll
+                for (int a = 0; a < 3; ++a, G += 3) {
+                    const uint32_t s = G & 3u, ph = (G >> 2) & 1u;
+                    const uint32_t sa = stage0 + s * STAGE;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)STAGE);
+                        tma_load_3d(sa + A_REGION, &tmB, full0 + 8 * s, 0, 0, (a * 3 + (int)me) * 3);
+                        tma_load_5d(sa, &tmA, full0 + 8 * s, 0, w0, h0, d0 + a, r);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
@@ -129,14 +164,17 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int cc = 0; cc < g.kc; ++cc, ++kslice) {
                                 const uint32_t sa = stage0 + s * STAGE;
                                 if (turn == me) {
-                                    if (gpos == 0) {
-                                        const int nv = min(KS, ksteps - kslice);        // K-steps in this stage (KS > 1: no skipping)
-                                        mbar_wait(empty0 + 8 * s, ph ^ 1);
-                                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(nv * kATileBytes + KS * B_TILE));
-                                        tma_load_3d(sa + KS * kATileBytes, &tmB, full0 + 8 * s, 0, nt * BN, kslice);
+                                    if (gpos == 0) mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                    if (elect_one()) {
+                                        if (gpos == 0) {
+                                            const int nv = min(KS, ksteps - kslice);    // K-steps in this stage (KS > 1: no skipping)
+                                            mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(nv * kATileBytes + KS * B_TILE));
+                                            tma_load_3d(sa + A_REGION, &tmB, full0 + 8 * s, 0, nt * BN, kslice);
+                                        }
+                                        tma_load_5d(sa + gpos * kATileBytes, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
+                                                    d0 + a * g.dil, n);
                                     }
-                                    tma_load_5d(sa + gpos * kATileBytes, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil,
-                                                d0 + a * g.dil, n);
+                                    __syncwarp();
                                 }
                                 if (++gpos == KS || kslice + 1 == ksteps) {
                                     gpos = 0;
@@ -148,8 +186,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ============================ MMA issuer (one thread) ============================
-        if (lane == 0) {
+        // ============================ MMA issuer (whole warp walks the loop, one elected lane issues) ============================
+        {
             uint32_t s = 0, ph = 0, it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
@@ -173,17 +211,23 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tc_fence_after();
                     const uint32_t sa = stage0 + s * STAGE;
                     const int nv = min(KS, ksteps_t - k);
-                    for (int q = 0; q < nv; ++q) {
-                        const uint64_t adesc = umma_desc_sw128(sa + q * kATileBytes, 16, 1024);
-                        const uint64_t bdesc = umma_desc_sw128(sa + KS * kATileBytes + q * B_TILE, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)               // 4 x K16 inside the 64-wide (128-byte) swizzled row
-                            umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                        for (int q = 0; q < KS; ++q) {
+                            if (q >= nv) break;
+                            const uint64_t adesc = WH ? umma_desc_sw128(sa + q * 128, 16, 1280) : umma_desc_sw128(sa + q * kATileBytes, 16, 1024);
+                            const uint64_t bdesc = umma_desc_sw128(sa + A_REGION + q * B_TILE, 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)           // 4 x K16 inside the 64-wide (128-byte) swizzled row
+                                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                        }
+                        umma_commit(empty0 + 8 * s);              // frees the smem slot when these MMAs retire
                     }
-                    umma_commit(empty0 + 8 * s);                  // frees the smem slot when these MMAs retire
+                    __syncwarp();
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);                    // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -345,7 +389,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers (in both CTAs) ============================
-        if (lane == 0) {
+        {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
@@ -367,10 +411,13 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             for (int cc = 0; cc < g.kc; ++cc) {
                                 if (turn == me) {
                                     mbar_wait(empty0 + 8 * s, ph ^ 1);                  // my own smem slot is free
-                                    if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);   // bytes of BOTH CTAs
-                                    const uint32_t sa = stage0 + s * STAGE;
-                                    tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
-                                    tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
+                                    if (elect_one()) {
+                                        if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);   // bytes of BOTH CTAs
+                                        const uint32_t sa = stage0 + s * STAGE;
+                                        tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
+                                        tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
+                                    }
+                                    __syncwarp();
                                 }
                                 if (++turn == nprod) turn = 0;
                                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -380,7 +427,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else if (warp == 1) {
         // ============================ MMA issuer: leader CTA only ============================
-        if (lane == 0 && leader) {
+        if (leader) {
             uint32_t s = 0, ph = 0, it = 0;
             for (int st = pair; st < total_super; st += n_pairs, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
@@ -396,12 +443,16 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     const uint32_t sa = stage0 + s * STAGE;
                     const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
                     const uint64_t bdesc = umma_desc_sw128(sa + kATileBytes, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
-                    umma_commit_2sm(empty0 + 8 * s, 3);           // frees the slot in both CTAs
+                        for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                        umma_commit_2sm(empty0 + 8 * s, 3);       // frees the slot in both CTAs
+                    }
+                    __syncwarp();
                     if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 }
-                umma_commit_2sm(tfull0 + 8 * acc, 3);             // accumulator complete -> both epilogues
+                if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc, 3);   // accumulator complete -> both epilogues
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -539,9 +590,18 @@ static void pick_tile(int Wo, int Ho, int Do, int stride, int& tw, int& th, int&
         }
 }
 
-static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout) {
-    return 1024 + stages * ks * (kATileBytes + bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
+static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false) {
+    const int a_region = halo ? kHaloTileBytes : ks * kATileBytes;
+    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
 }
+
+// W-halo variant (see the kernel): 3x3x3, unit stride, undilated, 64 -> 64 channels; on unless MMAD_CONV_HALO=0
+static bool use_halo_kernel(int Cin, int Cout, int k, int stride, int dil) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("MMAD_CONV_HALO"); mode = e ? atoi(e) : 1; }
+    return mode != 0 && Cin == 64 && Cout == 64 && k == 3 && stride == 1 && dil == 1;
+}
+
 
 // CTA-pair kernel for 256-channel N tiles: on unless MMAD_CONV_PAIR=0
 static bool use_pair_kernel(int bn, long long m_tiles) {
@@ -590,7 +650,18 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     MMAD_CHECK_ARG(g.Do > 0 && g.Ho > 0 && g.Wo > 0, "conv3d_fwd: empty output");
+    int dev = 0, sms = 148;
+    MMAD_CUDA(cudaGetDevice(&dev));
+    MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pick_tile(g.Wo, g.Ho, g.Do, stride, g.tw, g.th, g.td);
+    bool halo = false;
+    if (use_halo_kernel(Cin, Cout, k, stride, dil)) {
+        // the halo variant needs 8 x 4 x 4 tiles; mmad_conv3d_stats_partials (which does not know Cin) sizes the statistics
+        // buffer from the regular tile, so only switch when both tilings fill every SM (grid == SM count either way)
+        const long long reg = (long long)N * ((g.Wo + g.tw - 1) / g.tw) * ((g.Ho + g.th - 1) / g.th) * ((g.Do + g.td - 1) / g.td);
+        const long long hal = (long long)N * ((g.Wo + 7) / 8) * ((g.Ho + 3) / 4) * ((g.Do + 3) / 4);
+        if (reg >= sms && hal >= sms) { halo = true; g.tw = 8; g.th = 4; g.td = 4; }
+    }
     g.lw = ilog2(g.tw); g.lh = ilog2(g.th);
     g.tiles_w = (g.Wo + g.tw - 1) / g.tw; g.tiles_h = (g.Ho + g.th - 1) / g.th; g.tiles_d = (g.Do + g.td - 1) / g.td;
     g.m_tiles = N * g.tiles_w * g.tiles_h * g.tiles_d;
@@ -601,24 +672,25 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
     static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
     if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
-    const int ks = ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1));     // K-steps per stage (one weight box per stage)
+    const int ks = halo ? 3 : (ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));     // K-steps per stage (one weight box per stage)
     g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024) --stages;
-    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
+    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024) --stages;
+    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
         g.nout = 1;                                        // trade the second epilogue buffer for pipeline depth
         stages = 8;
-        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout) > 227 * 1024) --stages;
+        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024) --stages;
     }
+    if (halo) stages = 4;                                  // the halo producers assume a 4-slot ring (fits: 4 x 44 KB + 2 x 16 KB)
     g.stages = stages;
-    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout);
+    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo);
     MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_fwd: shared memory budget exceeded");
 
     CUtensorMap tmA, tmB, tmC;
     {
         const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
         const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};
-        const uint32_t box[5] = {64, (uint32_t)(g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), 1};
+        const uint32_t box[5] = {64, (uint32_t)(halo ? g.tw + 2 : g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), 1};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_tmap_bf16(&tmA, x, 5, dims, str, box, es);
         if (rc) return rc;
@@ -643,9 +715,6 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         int rc = make_tmap_bf16(&tmC, y, 5, dims, str, box, es);
         if (rc) return rc;
     }
-    int dev = 0, sms = 148;
-    MMAD_CUDA(cudaGetDevice(&dev));
-    MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = (cudaStream_t)stream;
     if (pairk) {
         static bool attr_done = false;
@@ -660,16 +729,17 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
         return MMAD_OK;
     }
     const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
-#define MMAD_CONV_LAUNCH(BNV, KSV)                                                                                             \
+#define MMAD_CONV_LAUNCH(...)                                                                                               \
     do {                                                                                                                    \
         static bool attr_done = false;                                                                                      \
         if (!attr_done) {                                                                                                   \
-            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<BNV, KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_done = true;                                                                                               \
         }                                                                                                                   \
-        conv3d_igemm_kernel<BNV, KSV><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);                  \
+        conv3d_igemm_kernel<__VA_ARGS__><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);               \
     } while (0)
-    if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);
+    if (halo) MMAD_CONV_LAUNCH(64, 3, true);
+    else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);
     else if (bn == 64) MMAD_CONV_LAUNCH(64, 1);
     else if (bn == 128 && ks == 2) MMAD_CONV_LAUNCH(128, 2);
     else if (bn == 128) MMAD_CONV_LAUNCH(128, 1);

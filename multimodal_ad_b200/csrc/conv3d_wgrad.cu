@@ -104,7 +104,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: executed chunk i is issued by producer i % 3 ============================
-        if (lane == 0) {
+        {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kWgProducers, S);     // parity waits: a producer must not lap a slot twice, so stages >= active producers
@@ -126,18 +126,21 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 if (turn == me) {
                     const uint32_t bytes = (uint32_t)(nbox_b + 2 * (nu - __popc(skip))) * kBoxBytes;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    mbar_arrive_expect_tx(full0 + 8 * s, bytes);
-                    const uint32_t sb = base + s * STAGE;
-                    for (int j = 0; j < nbox_b; ++j) tma_load_5d(sb + j * kBoxBytes, &tmDY, full0 + 8 * s, nt * g.nb + 64 * j, ow0, oh0, od0, n);
-                    for (int a = 0; a < nu; ++a) {
-                        if ((skip >> a) & 1u) continue;
-                        const int u = u0 + a;
-                        for (int h = 0; h < 2; ++h) {
-                            const int ci0 = g.mode2 ? 0 : (u % g.cib) * 128 + 64 * h;
-                            tma_load_5d(sb + (uint32_t)(nbox_b + 2 * a + h) * kBoxBytes, &tmX, full0 + 8 * s, ci0,
-                                        ow0 * g.stride + toff[a].w[h], oh0 * g.stride + toff[a].h[h], od0 * g.stride + toff[a].d[h], n);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                        const uint32_t sb = base + s * STAGE;
+                        for (int j = 0; j < nbox_b; ++j) tma_load_5d(sb + j * kBoxBytes, &tmDY, full0 + 8 * s, nt * g.nb + 64 * j, ow0, oh0, od0, n);
+                        for (int a = 0; a < nu; ++a) {
+                            if ((skip >> a) & 1u) continue;
+                            const int u = u0 + a;
+                            for (int h = 0; h < 2; ++h) {
+                                const int ci0 = g.mode2 ? 0 : (u % g.cib) * 128 + 64 * h;
+                                tma_load_5d(sb + (uint32_t)(nbox_b + 2 * a + h) * kBoxBytes, &tmX, full0 + 8 * s, ci0,
+                                            ow0 * g.stride + toff[a].w[h], oh0 * g.stride + toff[a].h[h], od0 * g.stride + toff[a].d[h], n);
+                            }
                         }
                     }
+                    __syncwarp();
                 }
                 if (++turn == nprod) turn = 0;
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
@@ -145,7 +148,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma_idesc_bf16(128, g.nb, 1, 1);
             uint32_t s = 0, ph = 0;
             WgTapOff toff[4];
@@ -166,17 +169,21 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const uint32_t sb = base + s * STAGE;
                 // MN-major SW128: 128-byte rows are K (voxel) indices, 8-row groups 1024 B apart (SBO), 64-wide M/N atoms one box apart (LBO)
                 const uint64_t bdesc = umma_desc_sw128(sb, kBoxBytes, 1024);
-                for (int a = 0; a < nu; ++a) {
-                    if ((skip >> a) & 1u) continue;
-                    const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * kBoxBytes, kBoxBytes, 1024);
+                if (elect_one()) {
+                    for (int a = 0; a < nu; ++a) {
+                        if ((skip >> a) & 1u) continue;
+                        const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * kBoxBytes, kBoxBytes, 1024);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)                   // K16 = 16 voxel rows = 2048 bytes
-                        umma_bf16(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                        for (int j = 0; j < 4; ++j)               // K16 = 16 voxel rows = 2048 bytes
+                            umma_bf16(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);
                 }
-                umma_commit(empty0 + 8 * s);
+                __syncwarp();
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
-            umma_commit(tfull);
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ============================ epilogue: TMEM -> fp32 partials ============================
@@ -283,7 +290,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             }
         return m;
     };
-    if (lane == 0 && warp < 4) {
+    if (warp < 4) {
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -321,8 +328,8 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers (in both CTAs) ============================
-        if (lane == 0) {
-            // every producer thread takes part in EVERY stage and issues every third box of it, so that the issue time of a
+        {
+            // every producer warp takes part in EVERY stage and issues every third box of it, so that the issue time of a
             // (large, two-deep) stage stays off the critical path
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0;
@@ -331,29 +338,32 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 if (__popc(skip) == nblk) continue;
                 const int ow0 = wt * g.tw, oh0 = ht * g.th, od0 = dt * g.td, n0 = nn * g.tn;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
-                if (leader && me == 0)
-                    mbar_arrive_expect_tx(full0 + 8 * s, 2u * (uint32_t)(nbox_b + 2 * (nblk - __popc(skip))) * boxb);
-                const uint32_t sb = base + s * STAGE;
-                uint32_t q = 0;
-                for (int j = 0; j < nbox_b; ++j, ++q)
-                    if (q % kWgProducers == me)
-                        tma_load_5d_2sm(sb + j * boxb, &tmDY, full0 + 8 * s, nt * g.nb + (int)rank * (g.nb / 2) + 64 * j, ow0, oh0, od0, n0);
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    if (a >= nblk || ((skip >> a) & 1u)) continue;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h, ++q)
+                if (elect_one()) {
+                    if (leader && me == 0)
+                        mbar_arrive_expect_tx(full0 + 8 * s, 2u * (uint32_t)(nbox_b + 2 * (nblk - __popc(skip))) * boxb);
+                    const uint32_t sb = base + s * STAGE;
+                    uint32_t q = 0;
+                    for (int j = 0; j < nbox_b; ++j, ++q)
                         if (q % kWgProducers == me)
-                            tma_load_5d_2sm(sb + (uint32_t)(nbox_b + 2 * a + h) * boxb, &tmX, full0 + 8 * s, cib0[a] + 64 * h,
-                                            ow0 * g.stride + offw[a], oh0 * g.stride + offh[a], od0 * g.stride + offd[a], n0);
+                            tma_load_5d_2sm(sb + j * boxb, &tmDY, full0 + 8 * s, nt * g.nb + (int)rank * (g.nb / 2) + 64 * j, ow0, oh0, od0, n0);
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        if (a >= nblk || ((skip >> a) & 1u)) continue;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h, ++q)
+                            if (q % kWgProducers == me)
+                                tma_load_5d_2sm(sb + (uint32_t)(nbox_b + 2 * a + h) * boxb, &tmX, full0 + 8 * s, cib0[a] + 64 * h,
+                                                ow0 * g.stride + offw[a], oh0 * g.stride + offh[a], od0 * g.stride + offd[a], n0);
+                    }
                 }
+                __syncwarp();
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
         }
     }
     if (warp == 1) {
         // ============================ MMA issuer: leader CTA only ============================
-        if (lane == 0 && leader) {
+        if (leader) {
             const uint32_t idesc = umma_idesc_bf16(256, g.nb, 1, 1);
             uint32_t s = 0, ph = 0;
             for (int c = c_begin; c < c_end; ++c, next_chunk()) {
@@ -363,23 +373,27 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 tc_fence_after();
                 const uint32_t sb = base + s * STAGE;
                 const uint64_t bdesc = umma_desc_sw128(sb, boxb, 1024);
-                for (int a = 0; a < nblk; ++a) {
-                    if ((skip >> a) & 1u) continue;
-                    const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * boxb, boxb, 1024);
-                    if (g.cv == 128) {
+                if (elect_one()) {
+                    for (int a = 0; a < nblk; ++a) {
+                        if ((skip >> a) & 1u) continue;
+                        const uint64_t adesc = umma_desc_sw128(sb + (uint32_t)(nbox_b + 2 * a) * boxb, boxb, 1024);
+                        if (g.cv == 128) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)               // K16 = 16 voxel rows = 2048 bytes
-                            umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
-                    } else {
+                            for (int j = 0; j < 8; ++j)           // K16 = 16 voxel rows = 2048 bytes
+                                umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                            for (int j = 0; j < 4; ++j)
+                                umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                        }
                     }
+                    umma_commit_2sm(empty0 + 8 * s, 3);
                 }
-                umma_commit_2sm(empty0 + 8 * s, 3);
+                __syncwarp();
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
-            umma_commit_2sm(tfull, 3);
+            if (elect_one()) umma_commit_2sm(tfull, 3);
+            __syncwarp();
         }
     }
     if (warp >= 4) {

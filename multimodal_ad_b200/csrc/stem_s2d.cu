@@ -126,9 +126,12 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0) {
         // ============================ TMA producer: the weights once, then one input box per tile ============================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bfull, kStemBBytes);
-            tma_load_3d(b0, &tmB, bfull, 0, 0, 0);
+        {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bfull, kStemBBytes);
+                tma_load_3d(b0, &tmB, bfull, 0, 0, 0);
+            }
+            __syncwarp();
             uint32_t s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x) {
                 int r = tile;
@@ -136,14 +139,17 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int ht = r % g.tiles_h; r /= g.tiles_h;
                 const int dt = r % g.tiles_d; r /= g.tiles_d;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
-                mbar_arrive_expect_tx(full0 + 8 * s, kStemABox);
-                tma_load_5d(a0 + s * kStemABox, &tmA, full0 + 8 * s, 0, wt * 8, ht * 4, r * g.Ds + dt * 4, 0);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full0 + 8 * s, kStemABox);
+                    tma_load_5d(a0 + s * kStemABox, &tmA, full0 + 8 * s, 0, wt * 8, ht * 4, r * g.Ds + dt * 4, 0);
+                }
+                __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
+        {
             mbar_wait(bfull, 0);
             uint32_t s = 0, ph = 0, it = 0;
             for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, ++it) {
@@ -152,18 +158,21 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t sa = a0 + s * kStemABox;
+                if (elect_one()) {
 #pragma unroll
-                for (int kd = 0; kd < 4; ++kd)
+                    for (int kd = 0; kd < 4; ++kd)
 #pragma unroll
-                    for (int kh = 0; kh < 4; ++kh) {
-                        const uint64_t adesc = umma_desc_sw64(sa + kh * kStemAtom + kd * kStemSlab, 16, 512);
-                        const uint64_t bdesc = umma_desc_sw64(b0 + (kd * 4 + kh) * 4096, 16, 512);
+                        for (int kh = 0; kh < 4; ++kh) {
+                            const uint64_t adesc = umma_desc_sw64(sa + kh * kStemAtom + kd * kStemSlab, 16, 512);
+                            const uint64_t bdesc = umma_desc_sw64(b0 + (kd * 4 + kh) * 4096, 16, 512);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)               // 2 x K16 inside the 32-wide (64-byte) swizzled row
-                            umma_bf16(tmem_base + acc * 64, adesc + 2 * j, bdesc + 2 * j, IDESC, (kd | kh | j) ? 1u : 0u);
-                    }
-                umma_commit(empty0 + 8 * s);
-                umma_commit(tfull0 + 8 * acc);
+                            for (int j = 0; j < 2; ++j)           // 2 x K16 inside the 32-wide (64-byte) swizzled row
+                                umma_bf16(tmem_base + acc * 64, adesc + 2 * j, bdesc + 2 * j, IDESC, (kd | kh | j) ? 1u : 0u);
+                        }
+                    umma_commit(empty0 + 8 * s);
+                    umma_commit(tfull0 + 8 * acc);
+                }
+                __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
@@ -279,7 +288,7 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: chunk i is issued by producer i % 3 (S == 3) ============================
-        if (lane == 0) {
+        {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0;
             for (int c = c_begin; c < c_end; ++c) {
@@ -289,22 +298,26 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const int ht = r % g.tiles_h; r /= g.tiles_h;
                     const int dt = r % g.tiles_d; r /= g.tiles_d;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
-                    const uint32_t sb = base + s * STAGE;
-                    tma_load_5d(sb, &tmA, full0 + 8 * s, 0, wt * 8, ht * 4, r * g.Ds + dt * 4, 0);
-                    tma_load_5d(sb + kStemABox, &tmDY, full0 + 8 * s, 0, wt * 8, ht * 4, dt * 4, r);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
+                        const uint32_t sb = base + s * STAGE;
+                        tma_load_5d(sb, &tmA, full0 + 8 * s, 0, wt * 8, ht * 4, r * g.Ds + dt * 4, 0);
+                        tma_load_5d(sb + kStemABox, &tmDY, full0 + 8 * s, 0, wt * 8, ht * 4, dt * 4, r);
+                    }
+                    __syncwarp();
                 }
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
+        {
             uint32_t s = 0, ph = 0;
             for (int c = c_begin; c < c_end; ++c) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t sb = base + s * STAGE;
+                if (elect_one()) {
 #pragma unroll
                 for (int kd = 0; kd < 4; ++kd) {
                     // A, MN-major SWIZZLE_64B: 64-byte rows are voxels (K), 8-row groups 512 B apart, the four 32-wide kh atoms one
@@ -316,9 +329,12 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         umma_bf16(tmem_base + kd * 64, adesc + 64 * j, bdesc + 128 * j, IDESC, (c > c_begin || j) ? 1u : 0u);
                 }
                 umma_commit(empty0 + 8 * s);
+                }
+                __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
-            umma_commit(tfull);
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ============================ epilogue: TMEM -> fp32 partials [cta][co][K] ============================
