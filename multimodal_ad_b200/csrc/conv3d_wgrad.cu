@@ -29,6 +29,7 @@ struct WgradGeom {
     int tiles_w, tiles_h, tiles_d, n_chunks;
     int pairk;                    // 1: CTA-pair kernel (cta_group::2)
     int cv;                       // voxels per K chunk (64 or 128)
+    int halo;                     // 1: halo kernel (64 -> 64 channels, 3x3x3, unit stride, undilated)
     int mode2;                    // 1: Cin == 64, an M block is two taps x 64 ci; 0: one tap x 128 ci
     int units;                    // M blocks in total
     int cib;                      // ci blocks per tap (mode 1): Cin / 128
@@ -432,6 +433,135 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
 
+
+// ===============================================================================================================
+// Halo variant for 3x3x3, unit-stride, undilated convolutions of 64 -> 64 channels (layer1).  The kernels above load one
+// shifted copy of the input chunk per tap (9 boxes of 8 KB per 64 voxels) and are bound by the TMA box rate / L2 traffic
+// at ~0.3 PFLOP/s.  UMMA swizzles on absolute shared-memory address bits, so an operand may start at ANY 128-byte row: one
+// input box with a one-voxel halo (10 x 6 x 6 voxels, 45 KB) holds the shifted chunk of every tap.  Per 128-voxel chunk
+// (8 x 4 x 4) a CTA loads that box and one dY box and issues, per accumulator block (two taps x 64 ci) and K16 step (two W
+// lines of 8 voxels, 10 rows apart in the halo box), one MMA whose A start is the tap's row offset and whose second
+// 64-row atom (LBO) is the row distance to the next tap.  14 taps (7 blocks x 64 columns of TMEM) per CTA: grid =
+// 2 tap groups x nsplit voxel slices; group 1 recomputes tap 13 (not stored) so that both groups hold whole pairs.
+// ===============================================================================================================
+constexpr int kHaloRows = 10 * 6 * 6;                 // halo box rows (voxels)
+constexpr int kHaloBoxBytes = kHaloRows * 128;        // 46080 = 45 KB
+constexpr int kHaloDyBytes = 128 * 128;               // dY box: 128 voxels x 64 channels
+
+__device__ __forceinline__ int halo_row(int tap) {    // row of tap (a, b, c)'s first voxel in the halo box
+    return ((tap / 9) * 6 + (tap / 3) % 3) * 10 + tap % 3;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradGeom g,
+                           float* __restrict__ partials) {
+    constexpr int S = 3;
+    constexpr uint32_t STAGE = kHaloBoxBytes + kHaloDyBytes;
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)S * STAGE);   // full[S], empty[S], tfull
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull = empty0 + 8 * S;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.x & 1, ks = blockIdx.x >> 1;                   // tap group, voxel slice
+    const int tap0 = grp * 13;                                              // group 0: taps 0..13, group 1: taps 13..26
+    const int c_begin = (int)((long long)g.n_chunks * ks / g.nsplit), c_end = (int)((long long)g.n_chunks * (ks + 1) / g.nsplit);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDY);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_s), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0 || warp == 2 || warp == 3) {
+        // ============================ TMA producers: chunk i is issued by producer i % 3 (S == 3) ============================
+        const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
+        uint32_t s = 0, ph = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+            if (s == me) {
+                int r = c;
+                const int wt = r % g.tiles_w; r /= g.tiles_w;
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r % g.tiles_d; r /= g.tiles_d;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full0 + 8 * s, STAGE);
+                    const uint32_t sb = base + s * STAGE;
+                    tma_load_5d(sb, &tmX, full0 + 8 * s, 0, wt * 8 - 1, ht * 4 - 1, dt * 4 - 1, r);
+                    tma_load_5d(sb + kHaloBoxBytes, &tmDY, full0 + 8 * s, 0, wt * 8, ht * 4, dt * 4, r);
+                }
+                __syncwarp();
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ============================ MMA issuer ============================
+        uint32_t s = 0, ph = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+            mbar_wait(full0 + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t sb = base + s * STAGE;
+            if (elect_one()) {
+#pragma unroll
+                for (int blk = 0; blk < 7; ++blk) {
+                    const int t = tap0 + 2 * blk;
+                    const uint32_t r0 = (uint32_t)halo_row(t), lbo = (uint32_t)(halo_row(t + 1) - halo_row(t)) * 128u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                 // K16 = W lines (h, h+1) of slice d: 2j -> h = 2 * (j & 1), d = j >> 1
+                        const uint32_t line = (uint32_t)((j >> 1) * 6 + (j & 1) * 2) * 10u;
+                        const uint64_t adesc = umma_desc_sw128(sb + (r0 + line) * 128u, lbo, 1280);
+                        const uint64_t bdesc = umma_desc_sw128(sb + kHaloBoxBytes + j * 2048, kHaloDyBytes, 1024);
+                        umma_bf16(tmem_base + blk * 64, adesc, bdesc, IDESC, (c > c_begin || j) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ============================ epilogue: TMEM -> fp32 partials [slice][co][tap][ci] ============================
+        const int ew = warp - 4;
+        const int m = ew * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float* out = partials + (size_t)ks * 64 * 27 * 64;
+        for (int blk = 0; blk < 7; ++blk) {
+            const int tap = tap0 + 2 * blk + (m >> 6), ci = m & 63;
+            const bool store = !(grp == 1 && tap == 13);          // tap 13 belongs to group 0
+            for (int n0 = 0; n0 < 64; n0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + blk * 64 + n0, v);
+                tmem_ld_wait();
+                if (c_end == c_begin) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (store) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) out[((size_t)(n0 + j) * 27 + tap) * 64 + ci] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // (chunk, tap) pairs along one axis whose input range is not entirely padding (closed form: the stem view has millions of tiles)
 static long long axis_work(int ext_in, int ext_out, int t, int k, int stride, int pad, int dil) {
     auto ceil_div = [](long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); };
@@ -474,6 +604,20 @@ static int fill_geom_uncached(WgradGeom& g, int N, int D, int H, int W, int Cin,
     g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     if (g.Do <= 0 || g.Ho <= 0 || g.Wo <= 0) return -1;
+    static int halo_mode = -1;                         // halo kernel: on unless MMAD_WG_HALO=0
+    if (halo_mode < 0) { const char* e = getenv("MMAD_WG_HALO"); halo_mode = e ? atoi(e) : 1; }
+    if (halo_mode != 0 && Cin == 64 && Cout == 64 && k == 3 && stride == 1 && dil == 1 && pad == 1) {
+        g.halo = 1;
+        g.tw = 8; g.th = 4; g.td = 4; g.tn = 1; g.cv = 128;
+        g.tiles_w = (g.Wo + 7) / 8; g.tiles_h = (g.Ho + 3) / 4; g.tiles_d = (g.Do + 3) / 4;
+        const long long chunks = (long long)N * g.tiles_w * g.tiles_h * g.tiles_d;
+        if (chunks > 0x7fffffffLL) return -1;
+        g.n_chunks = (int)chunks;
+        g.nb = 64; g.n_tiles = 1; g.units = 14; g.nacc = 7; g.ugroups = 2; g.stages = 3;
+        g.nsplit = (int)std::max<long long>(1, std::min<long long>(chunks, sms / 2));   // 2 tap groups x nsplit slices = one wave
+        if (const char* e = getenv("MMAD_WG_NSPLIT")) g.nsplit = std::max(1, std::min(g.n_chunks, atoi(e)));
+        return 0;
+    }
     g.mode2 = Cin == 64;
     g.cib = g.mode2 ? 1 : Cin / 128;
     g.units = g.mode2 ? (g.taps + 1) / 2 : g.taps * g.cib;
@@ -599,6 +743,34 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     WgradGeom g;
     MMAD_CHECK_ARG(fill_geom(g, N, D, H, W, Cin, Cout, k, stride, pad, dil, sms) == 0, "conv3d_wgrad: empty output");
     CUtensorMap tmX, tmDY;
+    if (g.halo) {
+        {
+            const uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+            const uint64_t str[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
+            const uint32_t box[5] = {64, 10, 6, 6, 1};
+            const uint32_t es[5] = {1, 1, 1, 1, 1};
+            int rc = make_tmap_bf16(&tmX, x, 5, dims, str, box, es);
+            if (rc) return rc;
+        }
+        {
+            const uint64_t dims[5] = {64, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)N};
+            const uint64_t str[4] = {128, (uint64_t)g.Wo * 128, (uint64_t)g.Ho * g.Wo * 128, (uint64_t)g.Do * g.Ho * g.Wo * 128};
+            const uint32_t box[5] = {64, 8, 4, 4, 1};
+            const uint32_t es[5] = {1, 1, 1, 1, 1};
+            int rc = make_tmap_bf16(&tmDY, dy, 5, dims, str, box, es);
+            if (rc) return rc;
+        }
+        const int smem = 1024 + 3 * (kHaloBoxBytes + kHaloDyBytes) + 7 * 8 + 32;
+        static bool halo_attr = false;
+        if (!halo_attr) {
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            halo_attr = true;
+        }
+        conv3d_wgrad_halo64_kernel<<<2 * g.nsplit, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
+        MMAD_CUDA(cudaGetLastError());
+        count_launch();
+        return MMAD_OK;
+    }
     {
         const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
         const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};

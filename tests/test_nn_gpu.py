@@ -56,6 +56,8 @@ WG_CASES = [
     # CTA-pair kernel: odd unit count (phantom unit), batch-deep chunks + padding skips, odd batch, single unit
     (2, 16, 16, 16, 128, 128, 3, 1, 1, 1), (2, 16, 16, 16, 256, 512, 3, 1, 4, 4), (3, 8, 8, 8, 128, 256, 3, 1, 1, 1),
     (1, 16, 16, 16, 128, 256, 1, 1, 0, 1),
+    # halo kernel (64 -> 64): ragged, and the layer1 shape of a 91x109x91 volume
+    (1, 5, 7, 9, 64, 64, 3, 1, 1, 1), (2, 23, 28, 23, 64, 64, 3, 1, 1, 1),
 ]
 
 

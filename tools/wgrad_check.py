@@ -55,6 +55,8 @@ if __name__ == "__main__":
         (1, 16, 16, 16, 64, 128, 1, 2, 0, 1),    # 1x1x1 stride 2
         (1, 5, 7, 9, 256, 512, 3, 1, 4, 4),      # ragged, dilation 4, two co tiles
         (1, 1, 1, 4096, 384, 64, 1, 1, 0, 1),    # stem view: rows x 384
+        (1, 5, 7, 9, 64, 64, 3, 1, 1, 1),        # halo kernel, ragged
+        (3, 23, 28, 23, 64, 64, 3, 1, 1, 1),     # halo kernel, layer1 shape of a 91x109x91 input
         (2, 16, 16, 16, 128, 128, 3, 1, 1, 1),   # pair kernel, odd unit count (phantom unit), batch-deep chunks
         (2, 16, 16, 16, 256, 512, 3, 1, 4, 4),   # pair kernel, dilation 4 with padding skips, two co tiles
         (3, 8, 8, 8, 128, 256, 3, 1, 1, 1),      # pair kernel, odd batch
