@@ -515,6 +515,93 @@ __global__ void __launch_bounds__(512) maxpool3d_bwd_kernel(const uint4* __restr
         }
 }
 
+
+// ---- the same gather, marching along D with the pooled gradient staged in shared memory.  A block owns 4 input rows
+//      (all of W) of one sample and walks a range of input slices; the <= 3 pooled rows x Wo of gradient + argmax bytes that
+//      a pooled slice contributes are streamed into a 3-slot ring with 1-D bulk copies (each pooled slice serves 3 input
+//      slices), so the per-voxel window tests read shared memory instead of issuing dependent global loads.
+constexpr int kPoolSlots = 3;
+__global__ void __launch_bounds__(512) maxpool3d_bwd_march_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                                  uint4* __restrict__ dx, int N, int D, int H, int W, int C, int Do,
+                                                                  int Ho, int Wo, int dsplit) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    const int cv = C >> 3;
+    const int hgroups = (H + 3) >> 2;
+    int b = blockIdx.x;
+    const int ds = b % dsplit; b /= dsplit;
+    const int hg = b % hgroups; b /= hgroups;
+    const int n = b;
+    const int ih0 = hg * 4, ih1 = min(H, ih0 + 4);
+    const int oh_lo = ih0 >> 1, nrow = min(Ho, oh_lo + 3) - oh_lo;        // pooled rows touching input rows ih0..ih0+3
+    const int d_lo = (int)((long long)D * ds / dsplit), d_hi = (int)((long long)D * (ds + 1) / dsplit);   // [d_lo, d_hi)
+    const int od_start = d_lo >> 1, od_last = min(Do - 1, d_hi >> 1);      // pooled slices needed: od_start..od_last
+    const uint32_t dy_bytes = (uint32_t)nrow * Wo * cv * 16, ix_bytes = dy_bytes >> 1;
+    const uint32_t slot_bytes = (uint32_t)3 * Wo * cv * 24;               // dy tile, then idx tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(psm + kPoolSlots * slot_bytes);
+    const uint32_t full0 = smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < kPoolSlots; ++q) mbar_init(full0 + 8 * q, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto load = [&](int od) {                                              // thread 0 only
+        const int q = od - od_start, slot = q % kPoolSlots;
+        const size_t e = (((size_t)n * Do + od) * Ho + oh_lo) * Wo * cv;
+        const uint32_t dst = smem_u32(psm) + slot * slot_bytes;
+        mbar_arrive_expect_tx(full0 + 8 * slot, dy_bytes + ix_bytes);
+        bulk_g2s(dst, dy + e, dy_bytes, full0 + 8 * slot);
+        bulk_g2s(dst + 3 * Wo * cv * 16, idx + e, ix_bytes, full0 + 8 * slot);
+    };
+    if (threadIdx.x == 0)
+        for (int od = od_start; od <= min(od_last, od_start + kPoolSlots - 1); ++od) load(od);
+
+    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
+    int waited = od_start - 1;                                             // pooled slices whose arrival this thread has seen
+    for (int id = d_lo; id < d_hi; ++id) {
+        const int od0 = id >> 1;
+        const int od1 = ((id & 1) && od0 + 1 < Do) ? od0 + 1 : od0;
+        while (waited < od1) {
+            ++waited;
+            const int q = waited - od_start;
+            mbar_wait(full0 + 8 * (q % kPoolSlots), (q / kPoolSlots) & 1);
+        }
+        for (int ih = ih0; ih < ih1; ++ih) {
+            const int oha = ih >> 1;
+            const int ohb = ((ih & 1) && oha + 1 < Ho) ? oha + 1 : oha;
+            for (int iw = wl; iw < W; iw += wstep) {
+                const int owa = iw >> 1;
+                const int owb = ((iw & 1) && owa + 1 < Wo) ? owa + 1 : owa;
+                float g[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] = 0.f;
+                for (int od = od0; od <= od1; ++od) {
+                    const unsigned char* sl = psm + ((od - od_start) % kPoolSlots) * slot_bytes;
+                    const uint4* sdy = reinterpret_cast<const uint4*>(sl);
+                    const uint2* six = reinterpret_cast<const uint2*>(sl + 3 * Wo * cv * 16);
+                    for (int oh = oha; oh <= ohb; ++oh)
+                        for (int ow = owa; ow <= owb; ++ow) {
+                            const uint32_t tap = (uint32_t)(((id - 2 * od + 1) * 3 + (ih - 2 * oh + 1)) * 3 + (iw - 2 * ow + 1));
+                            const int o = ((oh - oh_lo) * Wo + ow) * cv + v;
+                            const uint2 p = six[o];
+                            const uint32_t t4 = tap * 0x01010101u;
+                            const uint32_t mlo = __vcmpeq4(p.x, t4), mhi = __vcmpeq4(p.y, t4);
+                            if (!(mlo | mhi)) continue;
+                            float a[8];
+                            unpack8(sdy[o], a);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) g[j] += (((j < 4 ? mlo : mhi) >> (8 * (j & 3))) & 1u) ? a[j] : 0.f;
+                        }
+                }
+                dx[((((size_t)n * D + id) * H + ih) * W + iw) * cv + v] = pack8(g);
+            }
+        }
+        if (id & 1) {                                                      // pooled slice od0 is done: refill its slot
+            __syncthreads();
+            if (threadIdx.x == 0 && od0 + kPoolSlots <= od_last) load(od0 + kPoolSlots);
+        }
+    }
+}
+
 // ---- fused stem (resnet.py:206-208): p = maxpool3d(relu(bn(c)), k3 s2 p1) in one pass over the conv output c; the
 //      post-ReLU tensor is never stored.  idx keeps the winning tap (first maximum in (kd,kh,kw) order).
 __global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ c, const float* __restrict__ scale,
@@ -769,6 +856,23 @@ int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, 
     int threads = 512;
     while (threads > 32 && (threads % cv != 0 || threads / cv > W)) threads >>= 1;
     MMAD_CHECK_ARG(threads % cv == 0, "maxpool3d_bwd: C/8 must divide a power of two <= 512");
+    static int march_mode = -1;                        // marching kernel: on unless MMAD_POOL_MARCH=0
+    if (march_mode < 0) { const char* e = getenv("MMAD_POOL_MARCH"); march_mode = e ? atoi(e) : 1; }
+    const long long slot = 3ll * Wo * cv * 24;
+    if (march_mode && 512 % cv == 0 && kPoolSlots * slot + 64 <= 72 * 1024 && D >= 4) {
+        const int smem = (int)(kPoolSlots * slot) + 64;
+        static bool attr_done = false;
+        if (!attr_done) {
+            MMAD_CUDA(cudaFuncSetAttribute(maxpool3d_bwd_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+            attr_done = true;
+        }
+        const int hgroups = (H + 3) / 4;
+        int dsplit = 1;                                // enough blocks for ~3 per SM
+        while ((long long)N * hgroups * dsplit < 444 && D / (dsplit * 2) >= 4) dsplit *= 2;
+        maxpool3d_bwd_march_kernel<<<(unsigned)(N * hgroups * dsplit), 512, smem, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D,
+                                                                                        H, W, C, Do, Ho, Wo, dsplit);
+        LAUNCH_OK();
+    }
     const int hrows = 4;
     maxpool3d_bwd_kernel<<<dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows)), threads, 0, ST>>>(
         (const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo, hrows);

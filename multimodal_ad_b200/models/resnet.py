@@ -311,6 +311,10 @@ class _GradDict(dict):
     def pusher(self, v):
         return (lambda: self.reducer.push(v)) if self.reducer is not None else None
 
+    def new_grad(self, param):
+        """storage for a weight gradient: a view of the reducer's current bucket when data-parallel, else a fresh tensor"""
+        return self.reducer.alloc_like(param) if self.reducer is not None else torch.empty_like(param)
+
 
 def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):
     """grad_out: gradient w.r.t. the (N,C,D',H',W')-shaped output view.  Returns {parameter: gradient}."""
@@ -338,13 +342,13 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         dc2, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, dy_is_f32=dy_f32)
         dy_f32 = False
         grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
-        gw = torch.empty_like(blk.conv2.weight)
+        gw = grads.new_grad(blk.conv2.weight)
         r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw, grads.pusher(gw))
         grads.set_quiet(blk.conv2.weight, gw)
         da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
         dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
         grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
-        gw = torch.empty_like(blk.conv1.weight)
+        gw = grads.new_grad(blk.conv1.weight)
         r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw, grads.pusher(gw))
         grads.set_quiet(blk.conv1.weight, gw)
         xin = rec["xin"]
@@ -360,7 +364,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             dcd, _, dg, db = r.bn_bwd(g2, None, None, rec["cd"], rec["vd"], dbn.weight.detach(), training, want_g=False)
             grads[dbn.weight], grads[dbn.bias] = dg, db
-            gw = torch.empty_like(dconv.weight)
+            gw = grads.new_grad(dconv.weight)
             r.wgrad(xin, dcd, planes, 1, dconv.stride[0], 0, 1, gw, grads.pusher(gw))
             grads.set_quiet(dconv.weight, gw)
             if dconv.stride[0] == 1:
@@ -390,7 +394,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
           "mmad_maxpool3d_bwd")
     dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=True, mask_from_x=True)
     grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
-    gw = torch.empty_like(model.conv1.weight)
+    gw = grads.new_grad(model.conv1.weight)
     r.stem_wgrad(stem["xs"], dc0, n, d, h, w, gw)
     r.join_side()                                          # every weight gradient is complete on the main stream from here
     grads[model.conv1.weight] = gw
@@ -424,6 +428,18 @@ class _BackboneFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         grads = _backbone_backward(ctx.model, ctx.tape, grad_out)
         ctx.tape = None
+        red = getattr(ctx.model, "grad_reducer", None)
+        if red is not None and red.active:
+            # Data parallel: the reducer's asynchronous all-reduces average these tensors IN PLACE after this function
+            # returns, so they must become the parameters' .grad themselves (autograd's AccumulateGrad would clone the
+            # not-yet-reduced values).  Standard loop (zero_grad(set_to_none=True)): assign and report "no gradient".
+            if all(p.grad is None for p in ctx.params if grads.get(p) is not None):
+                for p in ctx.params:
+                    g = grads.get(p)
+                    if g is not None:
+                        p.grad = g
+                return (None, None) + (None,) * len(ctx.params)
+            red.finish()                                   # gradient accumulation: hand autograd fully averaged tensors
         return (None, None) + tuple(grads.get(p) for p in ctx.params)
 
 

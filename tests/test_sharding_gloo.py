@@ -71,7 +71,18 @@ def _reducer_worker(rank, world, port, out):
         for t in small:
             red.push(t)
         red.push(big)                                     # pushing the same tensor twice must not reduce it twice
+        # bucketed storage: views of flat buckets, reduced per bucket once closed and complete (or at finish)
+        red.bucket_numel = 40
+        w1, w2, w3 = torch.nn.Parameter(torch.zeros(4, 6)), torch.nn.Parameter(torch.zeros(30)), torch.nn.Parameter(torch.zeros(2))
+        g1 = red.alloc_like(w1); g1.fill_(float(rank + 1))
+        red.push(g1)
+        g2 = red.alloc_like(w2); g2.fill_(float(3 * rank))   # does not fit behind g1: closes (and launches) the first bucket
+        g3 = red.alloc_like(w3); g3.fill_(7.0)                # below large_numel: plain tensor
+        assert g1.shape == (4, 6) and g2.shape == (30,) and g1.untyped_storage().data_ptr() != g2.untyped_storage().data_ptr()
+        red.push(g2)
+        red.push(g3)
         red.finish(lin.parameters())
+        assert torch.allclose(g1, torch.full((4, 6), 1.5)) and torch.allclose(g2, torch.full((30,), 1.5)) and torch.allclose(g3, torch.full((2,), 7.0))
         assert torch.allclose(big, torch.full((16,), 1.5))
         assert torch.allclose(small[0], torch.full((3,), 15.0)) and torch.allclose(small[1], torch.full((2, 2), 0.5))
         assert torch.allclose(lin.weight.grad, torch.full((1, 2), 5.5)) and torch.allclose(lin.bias.grad, torch.full((1,), 0.5))
