@@ -563,7 +563,7 @@ conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
 }
 
 // (chunk, tap) pairs along one axis whose input range is not entirely padding (closed form: the stem view has millions of tiles)
-static long long axis_work(int ext_in, int ext_out, int t, int k, int stride, int pad, int dil) {
+long long axis_work(int ext_in, int ext_out, int t, int k, int stride, int pad, int dil) {
     auto ceil_div = [](long long a, long long b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); };
     const long long tiles = (ext_out + t - 1) / t, step = (long long)t * stride;
     long long w = 0;
@@ -579,7 +579,7 @@ static long long axis_work(int ext_in, int ext_out, int t, int k, int stride, in
 
 // K-chunk box tw x th x td x tn of `cv` output voxels (powers of two; tn > 1 only when the batch divides) with the fewest
 // (chunk, tap) pairs left after padding skips; ties go to the widest box in W (longer contiguous rows).
-static void pick_chunk(int cv, int N, int W, int H, int D, int Wo, int Ho, int Do, int k, int stride, int pad, int dil, int& tw,
+void pick_chunk(int cv, int N, int W, int H, int D, int Wo, int Ho, int Do, int k, int stride, int pad, int dil, int& tw,
                        int& th, int& td, int& tn) {   // (callers may override the result: MMAD_WG_SHAPE)
     double best = 1e30;
     for (int n = 1; n <= 2; n *= 2) {

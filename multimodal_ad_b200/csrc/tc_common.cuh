@@ -23,6 +23,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap_bf16_swz(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes);
 
+// Host (conv3d_wgrad.cu): box of `cv` output voxels tw x th x td x tn (powers of two, tn samples deep) with the fewest
+// (box, tap) pairs left once the pairs whose input range is entirely padding are skipped; ties go to the widest box in W.
+void pick_chunk(int cv, int N, int W, int H, int D, int Wo, int Ho, int Do, int k, int stride, int pad, int dil, int& tw, int& th,
+                int& td, int& tn);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // Device: TMA
