@@ -336,6 +336,9 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
     sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the K steps are queued behind a short spin kernel (outside the event bracket) so that the device-side time of exactly
+    # K steps is measured even when a slow host core cannot launch a 46 us step every 46 us
+    torch.cuda._sleep(int(max(0.01, args.steps * 1.0e-4) * 1.9e9))
     ev0.record()
     for i in range(args.steps):
         out = step(i)
@@ -354,6 +357,9 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
         plan.stream_only(bufs[i % 3])
     torch.cuda.synchronize()
     ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # a ~25 ms spin kernel goes first, so the host has queued all K launches before the first one starts: the events then
+    # bracket K back-to-back kernel executions whatever the host's launch rate is (a slow host core otherwise inflates this)
+    torch.cuda._sleep(int(max(0.01, args.steps * 1.0e-4) * 1.9e9))
     ka.record()
     for i in range(args.steps):
         plan.stream_only(bufs[i % 3])
