@@ -117,3 +117,20 @@ def test_training_script_step_runs_and_loss_decreases(built_lib):
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_data_parallel_gradients_match_hand_average_on_two_gpus():
+    """torchrun x2 (NCCL): after GradReducer.finish() every parameter's .grad equals the average of the per-rank gradients
+    (bucketed, overlapped all-reduce; tools/dp_check.py).  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(root, "tools", "dp_check.py")]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert '"ok": true' in res.stdout
