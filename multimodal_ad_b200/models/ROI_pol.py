@@ -213,6 +213,9 @@ class ROIPool(nn.Module):
     >>> pool = ROIPool(aal_data)                 # (D,H,W) integer atlas, 0 = background
     >>> roi_feat = pool(feats64)                 # (B,C,D,H,W) float32 CUDA -> (B,R,C), image_features.py:114
     >>> out = pool.pool(feats64)                 # dict(mean, max, argmax (B,R,C); counts (R,))
+
+    The feature grid may be LARGER than the atlas (96x112x96 UNet features against the 91x109x91 AAL grid): the
+    reference's crop `feats64[..., :D, :H, :W]` (image_features.py:103-105) is then folded into the pooling plan.
     """
 
     def __init__(self, atlas_labels, num_rois: Optional[int] = None, *, tile: int = 256):
@@ -224,11 +227,20 @@ class ROIPool(nn.Module):
         self.register_buffer("atlas", torch.from_numpy(lab.astype(np.int32)), persistent=True)
         self._plans = {}
 
-    def _plan(self, device: torch.device) -> RoiPlan:
-        key = (device.type, device.index)
+    def _plan(self, device: torch.device, grid=None) -> RoiPlan:
+        grid = self.spatial_shape if grid is None else tuple(grid)
+        key = (device.type, device.index, grid)
         pl = self._plans.get(key)
         if pl is None:
-            pl = RoiPlan(self.atlas.cpu().numpy(), self.num_rois, tile=self.tile, device=device)
+            lab = self.atlas.cpu().numpy().reshape(self.spatial_shape)
+            if grid != self.spatial_shape:
+                # the feature map is larger than the atlas (the reference's UNet pads 91x109x91 to 96x112x96 and crops the
+                # features back, image_features.py:103-105): pool the UNCROPPED map against the atlas embedded in that grid
+                # with background labels - the same sums over the same voxels, without the 64-channel crop copy
+                big = np.zeros(grid, dtype=lab.dtype)
+                big[: lab.shape[0], : lab.shape[1], : lab.shape[2]] = lab
+                lab = big
+            pl = RoiPlan(lab, self.num_rois, tile=self.tile, device=device)
             self._plans[key] = pl
         return pl
 
@@ -238,19 +250,25 @@ class ROIPool(nn.Module):
         if not feats.is_cuda:
             raise _lib.MmadError("ROIPool runs on CUDA tensors only (no CPU fallback)")
         b, c = feats.shape[:2]
-        if feats[0, 0].numel() != self.atlas.numel():
-            raise ValueError(f"feature grid {tuple(feats.shape[2:])} does not match atlas {self.spatial_shape}")
-        return b, c, self._plan(feats.device)
+        grid = tuple(int(v) for v in feats.shape[2:])
+        if len(self.spatial_shape) != 3 or any(g < a for g, a in zip(grid, self.spatial_shape)):
+            raise ValueError(f"feature grid {grid} does not cover atlas {self.spatial_shape}")
+        return b, c, self._plan(feats.device, grid), grid
 
     def forward(self, feats: torch.Tensor) -> torch.Tensor:
-        b, c, plan = self._prep(feats)
+        b, c, plan, _ = self._prep(feats)
         mean = _RoiMeanFunction.apply(feats.reshape(b * c, -1), plan)        # (B*C, R)
         return mean.reshape(b, c, self.num_rois).permute(0, 2, 1)            # (B, R, C)  image_features.py:114
 
     @torch.no_grad()
     def pool(self, feats: torch.Tensor) -> dict:
-        b, c, plan = self._prep(feats)
+        b, c, plan, grid = self._prep(feats)
         mean, mx, arg = plan.pool(feats.reshape(b * c, -1), want_max=True)
+        if grid != self.spatial_shape:                                       # flat index in the padded grid -> in the atlas grid
+            d_, h_, w_ = self.spatial_shape
+            a = arg.long()
+            dd, hh, ww = a // (grid[1] * grid[2]), (a // grid[2]) % grid[1], a % grid[2]
+            arg = torch.where(arg >= 0, (dd * h_ + hh) * w_ + ww, a).to(arg.dtype)
         shp = lambda t: t.reshape(b, c, self.num_rois).permute(0, 2, 1)      # noqa: E731
         return dict(mean=shp(mean), max=shp(mx), argmax=shp(arg),
                     counts=torch.from_numpy(plan.counts.copy()))

@@ -134,3 +134,33 @@ def test_data_parallel_gradients_match_hand_average_on_two_gpus():
     res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert '"ok": true' in res.stdout
+
+
+def test_resnet18_and_image_encoder_dropins_share_the_accelerated_backbone():
+    """models/resnet18.py and models/ImageEncoder.py (reference: resnet18.py:167-175, ImageEncoder.py:209-220) run the same
+    kernels as models/resnet.py: identical features for identical weights, gradients reach every backbone parameter."""
+    from multimodal_ad_b200.models import ImageEncoder as enc
+    from multimodal_ad_b200.models import resnet as base
+    from multimodal_ad_b200.models import resnet18 as r18
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    a = base.resnet18(sample_input_D=32, sample_input_H=32, sample_input_W=32, num_seg_classes=2, no_cuda=False).to(dev)
+    b = r18.resnet18(sample_input_D=32, sample_input_H=32, sample_input_W=32, num_seg_classes=2).to(dev)
+    e = enc.image_encoder18(global_pool=True).to(dev)
+    sd = {k: v for k, v in a.state_dict().items() if not k.startswith("conv_seg")}
+    b.load_state_dict(sd, strict=False)
+    e.load_state_dict(sd, strict=True)
+    x = torch.rand(2, 1, 32, 32, 32, device=dev)
+    for m in (a, b, e):
+        m.eval()
+    with torch.no_grad():
+        fa, fb = a.features(x), b.features(x)
+        emb = e(x)
+    assert torch.equal(fa, fb)
+    assert emb.shape == (2, 512) and torch.allclose(emb, fa.mean(dim=(2, 3, 4)), rtol=1e-5, atol=1e-6)
+    out = b(x)
+    assert out.shape == (2, 2, 8, 8, 8)                     # conv_seg doubles the 4^3 feature map
+    e.train()
+    e(x).square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in e.parameters())

@@ -176,3 +176,31 @@ def test_autograd_matches_reference_expression(built_lib):
     r = 10
     want = roi_mean_backward_oracle(g.permute(0, 2, 1).reshape(6, r).numpy(), lab, r)
     assert np.allclose(xc.grad.cpu().numpy().reshape(6, -1), want, rtol=1e-6, atol=1e-12)
+
+
+def test_uncropped_feature_map_equals_crop_then_pool(built_lib):
+    """image_features.py:103-114 crops the padded UNet feature map to the atlas grid before pooling; ROIPool on the UNCROPPED
+    map (atlas embedded with background labels) must give the same means / max / argmax / counts and the same gradient."""
+    from multimodal_ad_b200 import ROIPool
+
+    lab = synthetic_atlas((13, 10, 7), 12, seed=11, empty=(5,))
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn((2, 3, 16, 12, 8), generator=g).cuda()          # padded grid (as 96x112x96 pads 91x109x91)
+    crop = big[..., :13, :10, :7].contiguous()
+    pool = ROIPool(lab)
+    a, b = pool.pool(crop), pool.pool(big)
+    assert torch.equal(a["argmax"], b["argmax"]) and torch.equal(a["max"], b["max"]) and torch.equal(a["counts"], b["counts"])
+    assert torch.allclose(a["mean"], b["mean"], rtol=1e-6, atol=1e-7)
+    f2 = crop.reshape(6, -1).cpu().numpy()
+    back = lambda t: t.permute(0, 2, 1).reshape(6, 12).cpu().numpy()   # noqa: E731
+    _check(back(b["mean"]), back(b["max"]), back(b["argmax"]), f2, lab, 12)
+    xb, xc = big.clone().requires_grad_(True), crop.clone().requires_grad_(True)
+    w = torch.randn((2, 12, 3), generator=g).cuda()
+    (pool(xb) * w).sum().backward()
+    (pool(xc) * w).sum().backward()
+    assert torch.allclose(xb.grad[..., :13, :10, :7], xc.grad, rtol=1e-6, atol=1e-9)
+    rest = xb.grad.clone()
+    rest[..., :13, :10, :7] = 0
+    assert rest.abs().max().item() == 0.0                              # nothing flows into the padding
+    with pytest.raises(ValueError):
+        pool(big[..., :12, :, :])                                      # smaller than the atlas
