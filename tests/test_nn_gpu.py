@@ -28,6 +28,10 @@ CONV_CASES = [
     (2, 8, 8, 8, 64, 64, 3, 1, 1, 1), (1, 8, 16, 16, 128, 256, 3, 1, 2, 2), (1, 16, 16, 16, 64, 128, 3, 2, 1, 1),
     (1, 16, 16, 16, 64, 128, 1, 2, 0, 1), (1, 5, 7, 9, 64, 64, 3, 1, 1, 1), (1, 6, 11, 23, 64, 512, 3, 1, 4, 4),
     (2, 32, 32, 32, 64, 64, 3, 1, 1, 1), (1, 1, 1, 5000, 384, 64, 1, 1, 0, 1),
+    # W-halo kernel on a ragged grid (layer1 of a 91x109x91 volume); two-sample-deep tiles with padding skips through the
+    # CTA-pair kernel (dilation 4), the single-CTA BN=256 kernel (one voxel tile) and BN=128; multi-tile BN=64 K-step groups
+    (3, 23, 28, 23, 64, 64, 3, 1, 1, 1), (2, 16, 16, 16, 64, 256, 3, 1, 4, 4), (4, 8, 8, 8, 128, 512, 3, 1, 2, 2),
+    (2, 4, 4, 4, 64, 256, 3, 1, 4, 4), (2, 16, 16, 16, 64, 128, 3, 1, 4, 4), (1, 1, 1, 40000, 128, 64, 1, 1, 0, 1),
 ]
 
 
