@@ -555,7 +555,11 @@ __global__ void __launch_bounds__(512) maxpool3d_bwd_march_kernel(const uint4* _
     if (threadIdx.x == 0)
         for (int od = od_start; od <= min(od_last, od_start + kPoolSlots - 1); ++od) load(od);
 
-    const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
+    const int v = threadIdx.x % cv, wstep = blockDim.x / cv;
+    // A warp covers 32 / cv..4 voxels of W; odd voxels look at two pooled columns, even ones at one.  Give every warp voxels
+    // of ONE parity (0,2,4,6 | 1,3,5,7 | 8,10,...) so that the w loop does not diverge.
+    int wl = threadIdx.x / cv;
+    if ((wstep & 7) == 0) wl = ((wl >> 3) << 3) + ((wl & 3) << 1) + ((wl >> 2) & 1);
     int waited = od_start - 1;                                             // pooled slices whose arrival this thread has seen
     for (int id = d_lo; id < d_hi; ++id) {
         const int od0 = id >> 1;
@@ -583,13 +587,16 @@ __global__ void __launch_bounds__(512) maxpool3d_bwd_march_kernel(const uint4* _
                             const uint32_t tap = (uint32_t)(((id - 2 * od + 1) * 3 + (ih - 2 * oh + 1)) * 3 + (iw - 2 * ow + 1));
                             const int o = ((oh - oh_lo) * Wo + ow) * cv + v;
                             const uint2 p = six[o];
+                            uint4 gy = sdy[o];
                             const uint32_t t4 = tap * 0x01010101u;
-                            const uint32_t mlo = __vcmpeq4(p.x, t4), mhi = __vcmpeq4(p.y, t4);
-                            if (!(mlo | mhi)) continue;
+                            const uint32_t mlo = __vcmpeq4(p.x, t4), mhi = __vcmpeq4(p.y, t4);      // 0xff per matching channel byte
+                            // widen the byte masks to the bf16 lanes and clear the channels this window did not pick
+                            gy.x &= __byte_perm(mlo, 0, 0x1100); gy.y &= __byte_perm(mlo, 0, 0x3322);
+                            gy.z &= __byte_perm(mhi, 0, 0x1100); gy.w &= __byte_perm(mhi, 0, 0x3322);
                             float a[8];
-                            unpack8(sdy[o], a);
+                            unpack8(gy, a);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) g[j] += (((j < 4 ? mlo : mhi) >> (8 * (j & 3))) & 1u) ? a[j] : 0.f;
+                            for (int j = 0; j < 8; ++j) g[j] += a[j];
                         }
                 }
                 dx[((((size_t)n * D + id) * H + ih) * W + iw) * cv + v] = pack8(g);
