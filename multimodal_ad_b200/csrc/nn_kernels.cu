@@ -24,6 +24,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return v;
 }
 static inline int grid_for(long long work, int block, int cap) { return (int)std::max<long long>(1, std::min<long long>((work + block - 1) / block, cap)); }
+// grid for the per-channel-vector streaming kernels: grid * 256 must be a multiple of cv = C/8 so that a thread's grid-stride
+// loop stays on one channel vector (its coefficients live in registers)
+static inline int grid_for_channels(long long nvec, int cv, int cap) {
+    int g = grid_for(nvec, 256, cap);
+    int a = 256, b = cv;
+    while (b) { const int t = a % b; a = b; b = t; }            // a = gcd(256, cv)
+    const int m = cv / a;
+    return std::max(m, g / m * m);
+}
 
 // ---- weights: torch (Cout, Cin, k,k,k) fp32 -> forward layout [Cout][taps][Cin] bf16 (pass 1: per (co, 64-ci chunk) transpose
 //      of the [ci][tap] matrix through shared memory) and dgrad layout [Cin][taps reversed][Cout] bf16 (pass 2: per tap, a
@@ -170,16 +179,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const uint4* __restrict__ res, const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, uint4* __restrict__ out_bf16,
                                                        float4* __restrict__ out_f32, long long nvec, int C) {
+    // the grid stride is a multiple of C/8 (see the launcher): a thread keeps one channel vector, coefficients in registers
     const int cv = C >> 3;
-    const bool p2 = (cv & (cv - 1)) == 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (p2 ? (int)((unsigned)i & (unsigned)(cv - 1)) : (int)(i % cv)) * 8;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c0 = (int)(i0 % cv) * 8;
+    float sc[8], sh[8], rs[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j];
+        rs[j] = rscale ? rscale[c0 + j] : 1.f; rb[j] = rscale ? rshift[c0 + j] : 0.f;
+    }
+    for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         float f[8];
         unpack8(x[i], f);
-        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(shift + c0), b1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
         if (res) {
@@ -187,7 +199,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
             unpack8(res[i], r);
             if (rscale) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], rscale[c0 + j], rshift[c0 + j]);
+                for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], rs[j], rb[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += r[j];
@@ -410,19 +422,18 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __res
 // pass 2: dx = A*g + B*x + Cc
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ coef,
                                                            uint4* __restrict__ dx, long long nvec, int C) {
+    // the grid stride (gridDim.x * 256) is a multiple of C/8, so a thread keeps ONE channel vector: its 24 coefficients are
+    // loaded once instead of per element (they cost three times the tensor bytes in L1 traffic)
     const int cv = C >> 3;
-    const bool p2 = (cv & (cv - 1)) == 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (p2 ? (int)((unsigned)i & (unsigned)(cv - 1)) : (int)(i % cv)) * 8;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c0 = (int)(i0 % cv) * 8;
+    float A[8], B[8], Cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { A[j] = coef[c0 + j]; B[j] = coef[C + c0 + j]; Cc[j] = coef[2 * C + c0 + j]; }
+    for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         float gv[8], xv[8], o[8];
         unpack8(g[i], gv);
         unpack8(x[i], xv);
-        const float4 a0 = *reinterpret_cast<const float4*>(coef + c0), a1 = *reinterpret_cast<const float4*>(coef + c0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(coef + C + c0), b1 = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
-        const float4 d0 = *reinterpret_cast<const float4*>(coef + 2 * C + c0), d1 = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
-        const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        const float Cc[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
         dx[i] = pack8(o);
@@ -804,7 +815,7 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
                   int relu, void* out_bf16, float* out_f32, int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    const int grid = grid_for(nvec, 256, 148 * 16);
+    const int grid = grid_for_channels(nvec, C / 8, 148 * 8);
     if (relu) bn_apply_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
     else bn_apply_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
     LAUNCH_OK();
@@ -845,7 +856,7 @@ int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
 int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(g && x && coef && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    bn_bwd_apply_kernel<<<grid_for(nvec, 256, 148 * 16), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
+    bn_bwd_apply_kernel<<<grid_for_channels(nvec, C / 8, 148 * 8), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {
