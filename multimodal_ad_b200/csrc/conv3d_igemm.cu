@@ -9,8 +9,8 @@
 //   K-step:      ONE 5-D TMA box of the input (tap offset, dilation and stride folded into the box origin /
 //                element strides; zero padding = TMA out-of-bounds fill) + ONE 3-D box of the weights,
 //                then 4 x tcgen05.mma (M128 x BN x K16), fp32 accumulators in TMEM.
-//   Warp roles:  warps 0, 2, 3 TMA producers (one elected thread each issues one cp.async.bulk.tensor per ~300 cycles, so
-//                K-steps are dealt round-robin to three issuing warps), warp 1 MMA issuer (one thread), warp 2 also
+//   Warp roles:  warps 0, 2, 3 TMA producers (K-steps dealt round-robin; every role loop is warp-uniform and the TMA / MMA
+//                instructions are issued under elect_one(), see common.cuh), warp 1 MMA issuer, warp 2 also
 //                allocates TMEM, warps 4-7 epilogue
 //                (tcgen05.ld -> bf16 -> swizzled smem -> TMA store; per-channel sum / sum-of-squares of the stored
 //                bf16 values for the BatchNorm that follows).  Two TMEM accumulator buffers, persistent CTAs.
@@ -54,8 +54,8 @@ constexpr int kConvProducers = 3;          // warps 0, 2, 3
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
 constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 bf16
 
-// KS = K-steps per pipeline stage.  The TMA unit spends ~350 cycles per box whatever its size, so for narrow N tiles
-// (BN = 64 / 128, MMA time 132 / 264 cycles per K-step) the box COUNT is the bound: a stage then carries KS input boxes
+// KS = K-steps per pipeline stage.  For narrow N tiles (BN = 64 / 128, MMA time 132 / 264 cycles per K-step) the per-stage
+// handshakes and copy issues weigh as much as the MMAs, so a stage carries KS input boxes
 // and ONE weight box covering the KS consecutive K-slices (weights viewed as [64 ci][co][K-slice], see the host code).
 //
 // WH ("w halo", 3x3x3 unit-stride undilated convolutions of 64 channels, KS == 3): the three kw taps of a (kd, kh) pair

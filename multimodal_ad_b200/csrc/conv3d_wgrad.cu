@@ -62,7 +62,7 @@ __device__ __forceinline__ bool wg_oob(const WgradGeom& g, const WgTapOff& o, in
 }
 
 constexpr int kWgThreads = 256;
-constexpr int kWgProducers = 3;       // warps 0, 2, 3: one elected thread issues ~1 TMA op per 300 cycles, so chunks are dealt round-robin
+constexpr int kWgProducers = 3;       // warps 0, 2, 3: chunks are dealt round-robin to three issuing warps
 constexpr int kBoxBytes = 64 * 128;   // 64 voxels x 64 channels bf16
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -230,10 +230,10 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
 // ===============================================================================================================
 // CTA-pair variant (tcgen05 cta_group::2) for Cin >= 128 and Cout >= 128.  The single-CTA kernel above is bound by the
-// NUMBER of TMA boxes it needs per MMA cycle (a box costs ~300 cycles of TMA time whatever its size): 8 boxes of 8 KB per
-// 1024 MMA cycles.  Here a K chunk is 128 voxels (16 KB boxes), an accumulator block is 256 rows x NB columns spread over the
-// two CTAs (each CTA stages the X boxes of ITS unit and only HALF of the dY columns), so a CTA issues 6 boxes per 2048 MMA
-// cycles.  Block a of a pair holds units u0 + 2a (leader) and u0 + 2a + 1 (peer).  Barrier protocol as in
+// bytes it pulls through the L2->SM fabric per MMA cycle (64 KB of operands per 1024 MMA cycles = 62 B/cycle/SM against a
+// measured cap of ~43) and by its M = 128 accumulator blocks.  Here a K chunk is 128 voxels (16 KB boxes), an accumulator block is 256 rows x NB columns spread over the
+// two CTAs (each CTA stages the X boxes of ITS unit and only HALF of the dY columns), so a CTA pulls 96 KB per 2048 MMA
+// cycles (47 B/cycle).  Block a of a pair holds units u0 + 2a (leader) and u0 + 2a + 1 (peer).  Barrier protocol as in
 // conv3d_igemm_pair_kernel: the leader's full barrier collects both CTAs' bytes, tcgen05.commit is multicast to both.
 // ===============================================================================================================
 
@@ -436,7 +436,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
 // ===============================================================================================================
 // Halo variant for 3x3x3, unit-stride, undilated convolutions of 64 -> 64 channels (layer1).  The kernels above load one
-// shifted copy of the input chunk per tap (9 boxes of 8 KB per 64 voxels) and are bound by the TMA box rate / L2 traffic
+// shifted copy of the input chunk per tap (9 boxes of 8 KB per 64 voxels) and are bound by that L2 traffic
 // at ~0.3 PFLOP/s.  UMMA swizzles on absolute shared-memory address bits, so an operand may start at ANY 128-byte row: one
 // input box with a one-voxel halo (10 x 6 x 6 voxels, 45 KB) holds the shifted chunk of every tap.  Per 128-voxel chunk
 // (8 x 4 x 4) a CTA loads that box and one dY box and issues, per accumulator block (two taps x 64 ci) and K16 step (two W
