@@ -69,6 +69,7 @@ template <int BN, int KS, bool WH = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+    pdl_launch_dependents();
     static_assert(!WH || KS == 3, "the W-halo variant stages the three kw taps of one (kd, kh) pair");
     constexpr int B_TILE = BN * 128;
     constexpr int A_REGION = WH ? kHaloTileBytes : KS * kATileBytes;
@@ -104,6 +105,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     const int total_tiles = g.m_tiles * g.n_tiles;
     const int taps = g.kd * g.kh * g.kw;
@@ -328,6 +330,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                          const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+    pdl_launch_dependents();
     constexpr int BN = 256;
     constexpr int B_HALF = (BN / 2) * 128;
     constexpr int STAGE = kATileBytes + B_HALF;             // 32 KB per CTA per K-step
@@ -364,6 +367,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     cluster_sync_all();                                     // both CTAs' barriers and TMEM exist before anyone signals the peer
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int m_super = (g.m_tiles + 1) >> 1;
@@ -721,7 +725,7 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
             attr_done = true;
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
-        conv3d_igemm_pair_kernel<<<2 * pairs, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);
+        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
@@ -734,7 +738,7 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_done = true;                                                                                               \
         }                                                                                                                   \
-        conv3d_igemm_kernel<__VA_ARGS__><<<grid, kConvThreads, smem, st>>>(tmA, tmB, tmC, g, stats_partials);               \
+        launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);               \
     } while (0)
     if (halo) MMAD_CONV_LAUNCH(64, 3, true);
     else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);

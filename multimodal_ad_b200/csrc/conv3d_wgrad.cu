@@ -68,6 +68,7 @@ constexpr int kBoxBytes = 64 * 128;   // 64 voxels x 64 channels bf16
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradGeom g,
                     float* __restrict__ partials) {
+    pdl_launch_dependents();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -102,6 +103,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: executed chunk i is issued by producer i % 3 ============================
@@ -240,6 +242,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradGeom g,
                          float* __restrict__ partials) {
+    pdl_launch_dependents();
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -275,6 +278,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     // Per accumulator block (registers, static indexing): the input-box origin offset of THIS CTA's unit, and for both
     // units of the block one bit mask per axis of the chunk tiles whose input range is entirely padding (bit i = tile i).
@@ -455,6 +459,7 @@ __device__ __forceinline__ int halo_row(int tap) {    // row of tap (a, b, c)'s 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradGeom g,
                            float* __restrict__ partials) {
+    pdl_launch_dependents();
     constexpr int S = 3;
     constexpr uint32_t STAGE = kHaloBoxBytes + kHaloDyBytes;
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);
@@ -482,6 +487,7 @@ conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: chunk i is issued by producer i % 3 (S == 3) ============================
@@ -766,7 +772,7 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             halo_attr = true;
         }
-        conv3d_wgrad_halo64_kernel<<<2 * g.nsplit, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
+        launch_pdl(conv3d_wgrad_halo64_kernel, dim3(2 * g.nsplit), dim3(kWgThreads), smem, (cudaStream_t)stream, tmX, tmDY, g, partials);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
@@ -798,8 +804,8 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
         attr_done = true;
     }
     const int grid = g.n_tiles * g.ugroups * g.nsplit;
-    if (g.pairk) conv3d_wgrad_pair_kernel<<<2 * grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
-    else conv3d_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, g, partials);
+    if (g.pairk) launch_pdl(conv3d_wgrad_pair_kernel, dim3(2 * grid), dim3(kWgThreads), smem, (cudaStream_t)stream, tmX, tmDY, g, partials);
+    else launch_pdl(conv3d_wgrad_kernel, dim3(grid), dim3(kWgThreads), smem, (cudaStream_t)stream, tmX, tmDY, g, partials);
     MMAD_CUDA(cudaGetLastError());
     count_launch();
     return MMAD_OK;

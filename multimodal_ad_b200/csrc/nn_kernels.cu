@@ -38,6 +38,8 @@ static inline int grid_for_channels(long long nvec, int cv, int cap) {
 //      of the [ci][tap] matrix through shared memory) and dgrad layout [Cin][taps reversed][Cout] bf16 (pass 2: per tap, a
 //      32x32 tiled [co][ci] -> [ci][co] transpose of the forward layout).  Both passes read and write coalesced.
 __global__ void __launch_bounds__(64) prep_weights_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cin, int taps) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     extern __shared__ float tile[];                  // [64][taps + 1]
     const int co = blockIdx.y, c0 = blockIdx.x * 64;
     const int nci = min(64, Cin - c0);
@@ -50,6 +52,8 @@ __global__ void __launch_bounds__(64) prep_weights_fwd_kernel(const float* __res
 }
 __global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wt, int Cout,
                                                                  int Cin, int taps) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     __shared__ __nv_bfloat16 tile[32][34];
     const int tap = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -65,6 +69,8 @@ __global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bflo
 }
 // stem weights (Cout, 1, 7,7,7) fp32 -> [Cout][Kpad] bf16 (a 1x1x1 conv over the im2col matrix), zero padded
 __global__ void prep_stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int K, int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int total = Cout * Kpad;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i % Kpad, co = i / Kpad;
@@ -73,6 +79,8 @@ __global__ void prep_stem_weights_kernel(const float* __restrict__ w, __nv_bfloa
 }
 // dW of the stem: [Cout][1][Kpad] fp32 (wgrad output layout with taps = 1, Cin = Kpad) -> (Cout, 1, 7,7,7) fp32
 __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int K, int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int total = Cout * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
 }
@@ -84,6 +92,8 @@ __global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __
 template <int K>
 __global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
                                                           int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     constexpr int STRIP = 32;
     extern __shared__ float seg[];                    // [K*K][segw] + one zero word for the padding columns
     const int segw = (STRIP - 1) * stride + K;
@@ -140,6 +150,8 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restric
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // one warp per channel
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -166,6 +178,8 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restric
 __global__ void bn_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ running_mean,
                                const float* __restrict__ running_var, float eps, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                float* __restrict__ scale_out, float* __restrict__ shift_out) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float invstd = rsqrtf(running_var[c] + eps);
@@ -179,6 +193,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
                                                        const uint4* __restrict__ res, const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, uint4* __restrict__ out_bf16,
                                                        float4* __restrict__ out_f32, long long nvec, int C) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     // the grid stride is a multiple of C/8 (see the launcher): a thread keeps one channel vector, coefficients in registers
     const int cv = C >> 3;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -223,6 +239,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
                                                             const float* __restrict__ invstd, const float* __restrict__ mscale,
                                                             const float* __restrict__ mshift, uint4* __restrict__ g_out,
                                                             float* __restrict__ partials, long long rows, int C) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     // each block walks rows [r0, r1); thread t handles channel vector (t % cv) of rows r0 + t / cv, + 256/cv, ...
     extern __shared__ float red[];   // [256][16]
     const int cv = C >> 3;           // vectors per row: 8, 16, 32 or 64
@@ -296,6 +314,8 @@ bn_bwd_reduce_tma_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
                          const uint4* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ mscale, const float* __restrict__ mshift, uint4* __restrict__ g_out,
                          float* __restrict__ partials, long long nvec, int C) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     extern __shared__ __align__(128) unsigned char bsm[];
     const int nin = 2 + (dy2 ? 1 : 0) + (mask ? 1 : 0);
     const uint32_t stage_bytes = (uint32_t)nin * kBnTileVec * 16;
@@ -401,6 +421,8 @@ bn_bwd_reduce_tma_kernel(const uint4* __restrict__ dy, const uint4* __restrict__
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                                        int training, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -422,6 +444,8 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __res
 // pass 2: dx = A*g + B*x + Cc
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ coef,
                                                            uint4* __restrict__ dx, long long nvec, int C) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     // the grid stride (gridDim.x * 256) is a multiple of C/8, so a thread keeps ONE channel vector: its 24 coefficients are
     // loaded once instead of per element (they cost three times the tensor bytes in L1 traffic)
     const int cv = C >> 3;
@@ -444,6 +468,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 //      for the backward pass.
 __global__ void __launch_bounds__(256) maxpool3d_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int N,
                                                             int D, int H, int W, int C, int Do, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int cv = C >> 3;
     const long long total = (long long)N * Do * Ho * Wo * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -515,6 +541,8 @@ __device__ __forceinline__ void stem_pool_gather(const uint4* __restrict__ dp, c
 // the d / h window loops are block-uniform.
 __global__ void __launch_bounds__(512) maxpool3d_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                                             int N, int D, int H, int W, int C, int Do, int Ho, int Wo, int hrows) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int cv = C >> 3;
     const int v = threadIdx.x % cv, wl = threadIdx.x / cv, wstep = blockDim.x / cv;
     const int n = blockIdx.x / D, id = blockIdx.x % D;
@@ -535,6 +563,8 @@ constexpr int kPoolSlots = 3;
 __global__ void __launch_bounds__(512) maxpool3d_bwd_march_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                   uint4* __restrict__ dx, int N, int D, int H, int W, int C, int Do,
                                                                   int Ho, int Wo, int dsplit) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     extern __shared__ __align__(128) unsigned char psm[];
     const int cv = C >> 3;
     const int hgroups = (H + 3) >> 2;
@@ -626,6 +656,8 @@ __global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uin
                                                                        const float* __restrict__ shift, uint4* __restrict__ y,
                                                                        uint2* __restrict__ idx, int N, int D, int H, int W, int C, int Do,
                                                                        int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int cv = C >> 3;
     const long long total = (long long)N * Do * Ho * Wo * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -669,6 +701,8 @@ __global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uin
 //      convolution of the zero-upsampled gradient with the flipped kernel)
 __global__ void __launch_bounds__(256) upsample_zero2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int Dx, int Hx, int Wx,
                                                              int Dy, int Hy, int Wy, int C) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int cv = C >> 3;
     const long long total = (long long)N * Dy * Hy * Wy * cv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -687,6 +721,8 @@ __global__ void __launch_bounds__(256) upsample_zero2_kernel(const uint4* __rest
 
 // ---- layout: (N, C, S) fp32 (torch NCDHW, S = D*H*W) -> (N, S, C) bf16, 32x32 shared-memory transpose
 __global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, long long S) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long s0 = (long long)blockIdx.x * 32;
@@ -710,6 +746,8 @@ __global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* _
 //      sums per thread), shared-memory transpose, coalesced [ci][tap] writes.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin,
                                                            int taps) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     extern __shared__ float tile[];                  // [taps][65]
     const int co = blockIdx.y, c0 = blockIdx.x * 64;
     const int nci = min(64, Cin - c0);
@@ -735,6 +773,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // small weight tensors (few (co, ci-chunk) blocks): one thread per element, strided write into the torch layout
 __global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout,
                                                                  int Cin, int taps) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const long long plane = (long long)Cout * taps * Cin;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= plane) return;
@@ -763,11 +803,11 @@ extern "C" {
 int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && taps > 0, "prep_weights: bad argument");
     MMAD_CHECK_ARG(w_fwd, "prep_weights: the forward layout is required (the dgrad layout is derived from it)");
-    prep_weights_fwd_kernel<<<dim3((Cin + 63) / 64, Cout), 64, 64 * (taps + 1) * sizeof(float), ST>>>(w, (__nv_bfloat16*)w_fwd, Cin, taps);
+    launch_pdl(prep_weights_fwd_kernel, dim3((Cin + 63) / 64, Cout), dim3(64), 64 * (taps + 1) * sizeof(float), ST, w, (__nv_bfloat16*)w_fwd, Cin, taps);
     MMAD_CUDA(cudaGetLastError());
     count_launch();
     if (w_dgrad) {
-        prep_weights_dgrad_kernel<<<dim3((Cin + 31) / 32, (Cout + 31) / 32, taps), 256, 0, ST>>>((const __nv_bfloat16*)w_fwd,
+        launch_pdl(prep_weights_dgrad_kernel, dim3((Cin + 31) / 32, (Cout + 31) / 32, taps), dim3(256), 0, ST, (const __nv_bfloat16*)w_fwd,
                                                                                               (__nv_bfloat16*)w_dgrad, Cout, Cin, taps);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
@@ -776,12 +816,12 @@ int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cou
 }
 int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream) {
     MMAD_CHECK_ARG(w && w_fwd && K <= Kpad && Kpad % 64 == 0, "stem_prep_weights: bad argument");
-    prep_stem_weights_kernel<<<grid_for((long long)Cout * Kpad, 256, 1024), 256, 0, ST>>>(w, (__nv_bfloat16*)w_fwd, Cout, K, Kpad);
+    launch_pdl(prep_stem_weights_kernel, dim3(grid_for((long long)Cout * Kpad, 256, 1024)), dim3(256), 0, ST, w, (__nv_bfloat16*)w_fwd, Cout, K, Kpad);
     LAUNCH_OK();
 }
 int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream) {
     MMAD_CHECK_ARG(dw_padded && dw, "stem_unpad_wgrad: null pointer");
-    unpad_stem_wgrad_kernel<<<grid_for((long long)Cout * K, 256, 1024), 256, 0, ST>>>(dw_padded, dw, Cout, K, Kpad);
+    launch_pdl(unpad_stem_wgrad_kernel, dim3(grid_for((long long)Cout * K, 256, 1024)), dim3(256), 0, ST, dw_padded, dw, Cout, K, Kpad);
     LAUNCH_OK();
 }
 int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int k, int stride, int pad, int Kpad, void* stream) {
@@ -793,22 +833,22 @@ int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int 
     const int segw = 31 * stride + k;
     MMAD_CHECK_ARG(192 % (Kpad / 8) == 0, "stem_im2col: Kpad / 8 must divide 192 (Kpad = 384)");
     const size_t smem = ((size_t)k * k * segw + 1) * sizeof(float);
-    if (k == 7) im2col_stem_kernel<7><<<(unsigned)blocks, 192, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
-    else im2col_stem_kernel<3><<<(unsigned)blocks, 192, smem, ST>>>(x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    if (k == 7) launch_pdl(im2col_stem_kernel<7>, dim3((unsigned)blocks), dim3(192), smem, ST, x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
+    else launch_pdl(im2col_stem_kernel<3>, dim3((unsigned)blocks), dim3(192), smem, ST, x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
     LAUNCH_OK();
 }
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
                      float* shift, void* stream) {
     MMAD_CHECK_ARG(partials && gamma && beta && mean && invstd && scale && shift && C > 0 && count > 0, "bn_finalize: bad argument");
-    bn_finalize_kernel<<<(C + 3) / 4, 128, 0, ST>>>(partials, nparts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+    launch_pdl(bn_finalize_kernel, dim3((C + 3) / 4), dim3(128), 0, ST, partials, nparts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
                                                    mean, invstd, scale, shift);
     LAUNCH_OK();
 }
 int mmad_bn_eval_params(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
                         float* mean, float* invstd, float* scale, float* shift, void* stream) {
     MMAD_CHECK_ARG(gamma && beta && running_mean && running_var && mean && invstd && scale && shift, "bn_eval_params: null pointer");
-    bn_eval_kernel<<<(C + 127) / 128, 128, 0, ST>>>(C, gamma, beta, running_mean, running_var, eps, mean, invstd, scale, shift);
+    launch_pdl(bn_eval_kernel, dim3((C + 127) / 128), dim3(128), 0, ST, C, gamma, beta, running_mean, running_var, eps, mean, invstd, scale, shift);
     LAUNCH_OK();
 }
 int mmad_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale, const float* rshift,
@@ -816,8 +856,8 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
     MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
     const long long nvec = rows * (C / 8);
     const int grid = grid_for_channels(nvec, C / 8, 148 * 8);
-    if (relu) bn_apply_kernel<true><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
-    else bn_apply_kernel<false><<<grid, 256, 0, ST>>>((const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
+    if (relu) launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
+    else launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
     LAUNCH_OK();
 }
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
@@ -837,12 +877,12 @@ int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2
             MMAD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_done = true;
         }
-        bn_bwd_reduce_tma_kernel<<<grid, kBnConsumers + 32, smem, ST>>>((const uint4*)dy_bf16, (const uint4*)dy2, (const uint4*)mask,
+        launch_pdl(bn_bwd_reduce_tma_kernel, dim3(grid), dim3(kBnConsumers + 32), smem, ST, (const uint4*)dy_bf16, (const uint4*)dy2, (const uint4*)mask,
                                                                          (const uint4*)x, mean, invstd, mask_scale, mask_shift,
                                                                          (uint4*)g_out, partials, (long long)rows * (C / 8), C);
         LAUNCH_OK();
     }
-    bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), ST>>>((const uint4*)dy_bf16, (const float4*)dy_f32, (const uint4*)dy2,
+    launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(256), 256 * 16 * sizeof(float), ST, (const uint4*)dy_bf16, (const float4*)dy_f32, (const uint4*)dy2,
                                                                      (const uint4*)mask, (const uint4*)x, mean, invstd, mask_scale, mask_shift,
                                                                      (uint4*)g_out, partials, rows, C);
     LAUNCH_OK();
@@ -850,20 +890,20 @@ int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2
 int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* mean,
                          const float* invstd, int training, float* dgamma, float* dbeta, float* coef, void* stream) {
     MMAD_CHECK_ARG(partials && gamma && mean && invstd && coef && C > 0, "bn_bwd_finalize: bad argument");
-    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, ST>>>(partials, nparts, C, count, gamma, mean, invstd, training, dgamma, dbeta, coef);
+    launch_pdl(bn_bwd_finalize_kernel, dim3((C + 3) / 4), dim3(128), 0, ST, partials, nparts, C, count, gamma, mean, invstd, training, dgamma, dbeta, coef);
     LAUNCH_OK();
 }
 int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(g && x && coef && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    bn_bwd_apply_kernel<<<grid_for_channels(nvec, C / 8, 148 * 8), 256, 0, ST>>>((const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
+    launch_pdl(bn_bwd_apply_kernel, dim3(grid_for_channels(nvec, C / 8, 148 * 8)), dim3(256), 0, ST, (const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {
     MMAD_CHECK_ARG(x && y && idx && C % 8 == 0, "maxpool3d_fwd: bad argument");
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * Do * Ho * Wo * (C / 8);
-    maxpool3d_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)x, (uint4*)y, (uint2*)idx, N, D, H, W, C, Do, Ho, Wo);
+    launch_pdl(maxpool3d_fwd_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, (uint2*)idx, N, D, H, W, C, Do, Ho, Wo);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream) {
@@ -887,12 +927,12 @@ int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, 
         const int hgroups = (H + 3) / 4;
         int dsplit = 1;                                // enough blocks for ~3 per SM
         while ((long long)N * hgroups * dsplit < 444 && D / (dsplit * 2) >= 4) dsplit *= 2;
-        maxpool3d_bwd_march_kernel<<<(unsigned)(N * hgroups * dsplit), 512, smem, ST>>>((const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D,
+        launch_pdl(maxpool3d_bwd_march_kernel, dim3((unsigned)(N * hgroups * dsplit)), dim3(512), smem, ST, (const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D,
                                                                                         H, W, C, Do, Ho, Wo, dsplit);
         LAUNCH_OK();
     }
     const int hrows = 4;
-    maxpool3d_bwd_kernel<<<dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows)), threads, 0, ST>>>(
+    launch_pdl(maxpool3d_bwd_kernel, dim3((unsigned)(N * D), (unsigned)((H + hrows - 1) / hrows)), dim3(threads), 0, ST, 
         (const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, D, H, W, C, Do, Ho, Wo, hrows);
     LAUNCH_OK();
 }
@@ -902,29 +942,29 @@ int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * Do * Ho * Wo * (C / 8);
     MMAD_CHECK_ARG(total < (1ll << 32), "stem_bn_relu_maxpool_fwd: tensor too large for 32-bit indexing");
-    stem_bn_relu_maxpool_fwd_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
+    launch_pdl(stem_bn_relu_maxpool_fwd_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
                                                                                     W, C, Do, Ho, Wo);
     LAUNCH_OK();
 }
 int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx, int Dy, int Hy, int Wy, int C, void* stream) {
     MMAD_CHECK_ARG(x && y && C % 8 == 0, "upsample_zero2: bad argument");
     const long long total = (long long)N * Dy * Hy * Wy * (C / 8);
-    upsample_zero2_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, ST>>>((const uint4*)x, (uint4*)y, N, Dx, Hx, Wx, Dy, Hy, Wy, C);
+    launch_pdl(upsample_zero2_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, N, Dx, Hx, Wx, Dy, Hy, Wy, C);
     LAUNCH_OK();
 }
 int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, void* stream) {
     MMAD_CHECK_ARG(x && y && N > 0 && C > 0 && S > 0, "ncs_f32_to_nsc_bf16: bad argument");
     dim3 grid((unsigned)((S + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
-    ncs_f32_to_nsc_bf16_kernel<<<grid, 256, 0, ST>>>(x, (__nv_bfloat16*)y, C, S);
+    launch_pdl(ncs_f32_to_nsc_bf16_kernel, dim3(grid), dim3(256), 0, ST, x, (__nv_bfloat16*)y, C, S);
     LAUNCH_OK();
 }
 int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
     MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
     if ((long long)((Cin + 63) / 64) * Cout < 1024) {
         const long long plane = (long long)Cout * taps * Cin;
-        wgrad_reduce_small_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+        launch_pdl(wgrad_reduce_small_kernel, dim3((unsigned)((plane + 255) / 256)), dim3(256), 0, ST, partials, nsplit, dw, Cout, Cin, taps);
     } else {
-        wgrad_reduce_kernel<<<dim3((Cin + 63) / 64, Cout), 256, taps * 65 * sizeof(float), ST>>>(partials, nsplit, dw, Cout, Cin, taps);
+        launch_pdl(wgrad_reduce_kernel, dim3((Cin + 63) / 64, Cout), dim3(256), taps * 65 * sizeof(float), ST, partials, nsplit, dw, Cout, Cin, taps);
     }
     LAUNCH_OK();
 }

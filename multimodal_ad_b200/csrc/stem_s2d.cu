@@ -44,6 +44,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t 
 // ---------------------------------------------------------------------------------------------------------------
 // x fp32 [N][D][H][W] -> xs bf16 [N][Ds][Hs][Ws][8]; one thread per s2d voxel (one 16-byte store)
 __global__ void __launch_bounds__(256) stem_s2d_pack_kernel(const float* __restrict__ x, uint4* __restrict__ xs, StemGeom g) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const long long total = (long long)g.N * g.Ds * g.Hs * g.Ws;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
@@ -70,6 +72,8 @@ __host__ __device__ __forceinline__ int stem_k_index(int td, int th, int tw) {
 
 // w fp32 [64][343] -> wk bf16 [64][512]
 __global__ void __launch_bounds__(512) stem_s2d_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wk) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int co = blockIdx.x, K = threadIdx.x;
     const int p = K & 7, kw = (K >> 3) & 3, kh = (K >> 5) & 3, kd = K >> 7;
     const int td = 2 * kd + (p >> 2), th = 2 * kh + ((p >> 1) & 1), tw = 2 * kw + (p & 1);
@@ -79,6 +83,8 @@ __global__ void __launch_bounds__(512) stem_s2d_weights_kernel(const float* __re
 
 // partials fp32 [nsplit][64][512] -> dw fp32 [64][343] (torch layout)
 __global__ void __launch_bounds__(384) stem_s2d_wgrad_reduce_kernel(const float* __restrict__ partials, int nsplit, float* __restrict__ dw) {
+    pdl_launch_dependents();
+    pdl_wait();                                        // see launch_pdl (common.cuh)
     const int co = blockIdx.x, t = threadIdx.x;
     if (t >= 343) return;
     const int K = stem_k_index(t / 49, (t / 7) % 7, t % 7);
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(384) stem_s2d_wgrad_reduce_kernel(const float*
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const StemGeom g, float* __restrict__ stats_partials) {
+    pdl_launch_dependents();
     constexpr int S = 2;
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 0, 0);
     extern __shared__ unsigned char smem_raw[];
@@ -123,6 +130,7 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     if (warp == 0) {
         // ============================ TMA producer: the weights once, then one input box per tile ============================
@@ -260,6 +268,7 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 __global__ void __launch_bounds__(kStemThreads, 1)
 stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmDY, const StemGeom g,
                       float* __restrict__ partials) {
+    pdl_launch_dependents();
     constexpr int S = 3;
     constexpr uint32_t STAGE = kStemABox + kStemDyBox;
     constexpr uint32_t IDESC = umma_idesc_bf16(128, 64, 1, 1);
@@ -285,6 +294,7 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    pdl_wait();                                             // prologue done; global memory from here on (launch_pdl, common.cuh)
 
     if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: chunk i is issued by producer i % 3 (S == 3) ============================
@@ -410,13 +420,13 @@ int mmad_stem_s2d_pack(const float* x, void* xs, int N, int D, int H, int W, voi
     MMAD_CHECK_ARG(stem_geom(g, N, D, H, W) == 0, "stem_s2d_pack: volume too large");
     const long long total = (long long)N * g.Ds * g.Hs * g.Ws;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    stem_s2d_pack_kernel<<<grid, 256, 0, ST>>>(x, (uint4*)xs, g);
+    launch_pdl(stem_s2d_pack_kernel, dim3(grid), dim3(256), 0, ST, x, (uint4*)xs, g);
     LAUNCH_OK();
 }
 
 int mmad_stem_s2d_prep_weights(const float* w, void* wk, void* stream) {
     MMAD_CHECK_ARG(w && wk, "stem_s2d_prep_weights: null pointer");
-    stem_s2d_weights_kernel<<<64, 512, 0, ST>>>(w, (__nv_bfloat16*)wk);
+    launch_pdl(stem_s2d_weights_kernel, dim3(64), dim3(512), 0, ST, w, (__nv_bfloat16*)wk);
     LAUNCH_OK();
 }
 
@@ -457,7 +467,7 @@ int mmad_stem_s2d_fwd(const void* xs, const void* wk, void* y, float* stats_part
         attr_done = true;
     }
     const int grid = std::min(g.m_tiles, sm_count());
-    stem_conv_s2d_kernel<<<grid, kStemThreads, smem, ST>>>(tmA, tmB, tmC, g, stats_partials);
+    launch_pdl(stem_conv_s2d_kernel, dim3(grid), dim3(kStemThreads), smem, ST, tmA, tmB, tmC, g, stats_partials);
     LAUNCH_OK();
 }
 
@@ -492,13 +502,13 @@ int mmad_stem_s2d_wgrad(const void* xs, const void* dy, float* partials, int N, 
         attr_done = true;
     }
     const int grid = std::min(g.m_tiles, sm_count());
-    stem_wgrad_s2d_kernel<<<grid, kStemThreads, smem, ST>>>(tmA, tmDY, g, partials);
+    launch_pdl(stem_wgrad_s2d_kernel, dim3(grid), dim3(kStemThreads), smem, ST, tmA, tmDY, g, partials);
     LAUNCH_OK();
 }
 
 int mmad_stem_s2d_wgrad_reduce(const float* partials, int nsplit, float* dw, void* stream) {
     MMAD_CHECK_ARG(partials && dw && nsplit > 0, "stem_s2d_wgrad_reduce: bad argument");
-    stem_s2d_wgrad_reduce_kernel<<<64, 384, 0, ST>>>(partials, nsplit, dw);
+    launch_pdl(stem_s2d_wgrad_reduce_kernel, dim3(64), dim3(384), 0, ST, partials, nsplit, dw);
     LAUNCH_OK();
 }
 
