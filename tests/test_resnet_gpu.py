@@ -36,7 +36,10 @@ def _model(depth, size, seed=0):
     return model
 
 
-@pytest.mark.parametrize("depth,n,shape", [(10, 2, (32, 32, 32)), (18, 2, (64, 64, 64)), (18, 1, (45, 54, 45)), (34, 1, (32, 32, 32))])
+# the last two cases are the reference's own volume (BASELINE configs[0]: 91x109x91, ragged in every tile) and the
+# bench volume (configs[2]: 128^3), batch 2
+@pytest.mark.parametrize("depth,n,shape", [(10, 2, (32, 32, 32)), (18, 2, (64, 64, 64)), (18, 1, (45, 54, 45)), (34, 1, (32, 32, 32)),
+                                           (18, 2, (91, 109, 91)), (18, 2, (128, 128, 128))])
 def test_forward_backward_vs_oracle(depth, n, shape, built_lib):
     from multimodal_ad_b200.models.resnet import tape_stages
 
