@@ -30,6 +30,7 @@ struct WgradGeom {
     int pairk;                    // 1: CTA-pair kernel (cta_group::2)
     int cv;                       // voxels per K chunk (64 or 128)
     int halo;                     // 1: halo kernel (64 -> 64 channels, 3x3x3, unit stride, undilated)
+    unsigned char ug_order[64];   // pair kernel: unit groups in decreasing order of work (padding skips), heaviest launched first
     int mode2;                    // 1: Cin == 64, an M block is two taps x 64 ci; 0: one tap x 128 ci
     int units;                    // M blocks in total
     int cib;                      // ci blocks per tap (mode 1): Cin / 128
@@ -260,7 +261,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const bool leader = rank == 0;
 
     int item = blockIdx.x >> 1;
-    const int ug = item % g.ugroups; item /= g.ugroups;
+    const int ug = g.ugroups <= 64 ? (int)g.ug_order[item % g.ugroups] : item % g.ugroups; item /= g.ugroups;
     const int nt = item % g.n_tiles; item /= g.n_tiles;
     const int ks = item;
     const int u0 = ug * 2 * g.nacc;
@@ -683,6 +684,33 @@ static int fill_geom_uncached(WgradGeom& g, int N, int D, int H, int W, int Cin,
             const double t = waves * (((g.n_chunks + sp - 1) / sp) * t_chunk * f + 25.0) + sp * plane_mb * 0.25;
             if (t < best_t) { best_t = t; best_s = sp; }
         }
+    }
+    if (g.pairk && g.ugroups <= 64) {
+        // Unit groups whose taps fall into the padding skip chunks and finish early.  Blocks are handed to SMs in index order,
+        // so within every voxel slice the groups are launched heaviest first: the light ones fill the tail of the last wave.
+        double work[64];
+        for (int ug = 0; ug < g.ugroups; ++ug) {
+            work[ug] = 0.0;
+            for (int u = ug * 2 * g.nacc; u < std::min(g.units, (ug + 1) * 2 * g.nacc); ++u) {
+                const int tap = u / g.cib;
+                const int off[3] = {(tap % k) * dil - pad, ((tap / k) % k) * dil - pad, (tap / (k * k)) * dil - pad};
+                const int ext[3] = {W, H, D}, tl[3] = {g.tw, g.th, g.td}, nt[3] = {g.tiles_w, g.tiles_h, g.tiles_d};
+                double wtap = 1.0;
+                for (int ax = 0; ax < 3; ++ax) {
+                    int ok = 0;
+                    for (int i = 0; i < nt[ax]; ++i) {
+                        const int lo = i * tl[ax] * stride + off[ax];
+                        if (!(lo + (tl[ax] - 1) * stride < 0 || lo >= ext[ax])) ++ok;
+                    }
+                    wtap *= (double)ok / nt[ax];
+                }
+                work[ug] += wtap;
+            }
+        }
+        int idx[64];
+        for (int i = 0; i < g.ugroups; ++i) idx[i] = i;
+        std::stable_sort(idx, idx + g.ugroups, [&](int a, int b) { return work[a] > work[b]; });
+        for (int i = 0; i < g.ugroups; ++i) g.ug_order[i] = (unsigned char)idx[i];
     }
     g.nsplit = best_s;
     if (const char* e = getenv("MMAD_WG_NSPLIT")) g.nsplit = std::max(1, std::min(g.n_chunks, atoi(e)));   // tuning knob
