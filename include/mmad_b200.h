@@ -134,6 +134,15 @@ int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw,
 int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad,
                              int Cout, int Cin, int taps, void* stream);
 
+/* Data gradient of a 3x3x3, stride-2, padding-1 convolution (resnet.py:18-23 with
+ * stride 2: layer2.0.conv1) without zero insertion: dx (N,D,H,W,Cdx) bf16 from
+ * dy (N,(D-1)/2+1,..,Cdy) bf16 as 8 interleaved stride-1 phase convolutions.
+ * w_phases (27*Cdx*Cdy bf16) comes from mmad_conv3d_prep_weights_s2 on the
+ * torch weight (Cdy, Cdx, 3,3,3) fp32.  Cdx: 64/128/256/k*256, Cdy % 64 == 0. */
+int mmad_conv3d_prep_weights_s2(const float* w, void* w_phases, int Cdy, int Cdx, void* stream);
+int mmad_conv3d_dgrad_s2_bf16(const void* dy, const void* w_phases, void* dx,
+                              int N, int D, int H, int W, int Cdx, int Cdy, void* stream);
+
 /* Stem (resnet.py:126-132: Conv3d(1, 64, 7, stride 2, pad 3)) as im2col + GEMM:
  * x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, column (kd*k+kh)*k+kw,
  * zero padded to Kpad (384); the GEMM is mmad_conv3d_fwd_bf16 with k = 1 on the

@@ -65,6 +65,8 @@ def load() -> ctypes.CDLL:
         "mmad_conv3d_wgrad_bf16": [P, P, P] + [I] * 10 + [P],
         "mmad_wgrad_reduce": [P, I, P, I, I, I, P],
         "mmad_conv3d_prep_weights": [P, P, P, I, I, I, P],
+        "mmad_conv3d_prep_weights_s2": [P, P, I, I, P],
+        "mmad_conv3d_dgrad_s2_bf16": [P, P, P, I, I, I, I, I, I, P],
         "mmad_stem_im2col": [P, P] + [I] * 8 + [P],
         "mmad_stem_prep_weights": [P, P, I, I, I, P],
         "mmad_stem_unpad_wgrad": [P, P, I, I, I, P],

@@ -633,8 +633,13 @@ int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout, int k, int 
     return (int)std::min<long long>(tiles, sms);
 }
 
-int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W,
-                         int Cin, int Cout, int k, int stride, int pad, int dil, void* stream) {
+// Shared launcher.  (kd, kh, kw) taps, output extents and the output's voxel strides (in ELEMENTS; 0 = dense NDHWC) are explicit
+// so that the phase convolutions of the stride-2 data gradient (rectangular kernels, outputs interleaved into dx) use the same
+// kernels as the public forward entry point.
+struct ConvOut { int Do, Ho, Wo; long long sw, sh, sd, sn; };
+static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W, int Cin, int Cout,
+                         int kd, int kh, int kw, int stride, int pad, int dil, const ConvOut* ov, void* stream) {
+    const int k = std::max(kd, std::max(kh, kw));
     MMAD_CHECK_ARG(x && w && y, "conv3d_fwd: null pointer");
     MMAD_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: empty input");
     MMAD_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv3d_fwd: Cin must be a multiple of 64");
@@ -646,17 +651,17 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
                    "conv3d_fwd: pointers must be 16-byte aligned");
     ConvGeom g = {};
     g.N = N; g.D = D; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
-    g.kd = g.kh = g.kw = k; g.stride = stride; g.pad = pad; g.dil = dil;
-    g.Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1;
-    g.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
-    g.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    g.kd = kd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.dil = dil;
+    g.Do = ov ? ov->Do : (D + 2 * pad - dil * (kd - 1) - 1) / stride + 1;
+    g.Ho = ov ? ov->Ho : (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1;
+    g.Wo = ov ? ov->Wo : (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
     MMAD_CHECK_ARG(g.Do > 0 && g.Ho > 0 && g.Wo > 0, "conv3d_fwd: empty output");
     int dev = 0, sms = 148;
     MMAD_CUDA(cudaGetDevice(&dev));
     MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pick_tile(N, D, H, W, g.Wo, g.Ho, g.Do, k, stride, pad, dil, g.tw, g.th, g.td, g.tn);
     bool halo = false;
-    if (use_halo_kernel(Cin, Cout, k, stride, dil)) {
+    if (!ov && kd == kh && kh == kw && use_halo_kernel(Cin, Cout, k, stride, dil)) {
         // the halo variant needs 8 x 4 x 4 tiles; mmad_conv3d_stats_partials (which does not know Cin) sizes the statistics
         // buffer from the regular tile, so only switch when both tilings fill every SM (grid == SM count either way)
         const long long reg = (long long)(N / g.tn) * ((g.Wo + g.tw - 1) / g.tw) * ((g.Ho + g.th - 1) / g.th) * ((g.Do + g.td - 1) / g.td);
@@ -700,7 +705,7 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     {
         // weights [Cout][taps][Cin] viewed as [64 ci][co][K-slice]: K-slice = tap * (Cin/64) + ci block, 128 bytes apart, so a
         // box of KS consecutive K-slices lands as KS consecutive canonical K-major B tiles
-        const int taps = k * k * k;
+        const int taps = kd * kh * kw;
         const uint64_t dims[3] = {64, (uint64_t)Cout, (uint64_t)taps * (Cin / 64)};
         const uint64_t str[2] = {(uint64_t)taps * Cin * 2, 128};
         const uint32_t box[3] = {64, (uint32_t)bn_stage, (uint32_t)ks};
@@ -710,8 +715,11 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     }
     {
         const uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.Do, (uint64_t)N};
-        const uint64_t str[4] = {(uint64_t)Cout * 2, (uint64_t)g.Wo * Cout * 2, (uint64_t)g.Ho * g.Wo * Cout * 2,
-                                 (uint64_t)g.Do * g.Ho * g.Wo * Cout * 2};
+        const uint64_t dense[4] = {(uint64_t)Cout * 2, (uint64_t)g.Wo * Cout * 2, (uint64_t)g.Ho * g.Wo * Cout * 2,
+                                   (uint64_t)g.Do * g.Ho * g.Wo * Cout * 2};
+        const uint64_t strided[4] = {(uint64_t)(ov ? ov->sw : 0) * 2, (uint64_t)(ov ? ov->sh : 0) * 2, (uint64_t)(ov ? ov->sd : 0) * 2,
+                                     (uint64_t)(ov ? ov->sn : 0) * 2};
+        const uint64_t* str = (ov && ov->sw) ? strided : dense;
         const uint32_t box[5] = {64, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.td, (uint32_t)g.tn};
         const uint32_t es[5] = {1, 1, 1, 1, 1};
         int rc = make_tmap_bf16(&tmC, y, 5, dims, str, box, es);
@@ -751,5 +759,37 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     count_launch();
     return MMAD_OK;
 }
+
+int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W,
+                         int Cin, int Cout, int k, int stride, int pad, int dil, void* stream) {
+    return conv_fwd_impl(x, w, y, stats_partials, N, D, H, W, Cin, Cout, k, k, k, stride, pad, dil, nullptr, stream);
+}
+
+// Data gradient of a 3x3x3, stride-2, padding-1 convolution WITHOUT zero insertion: dx positions of parity (pd, ph, pw) only
+// see the taps of matching parity (1 tap on an even axis, 2 on an odd one), so dx is 8 interleaved stride-1 convolutions of
+// dy with (1+pd) x (1+ph) x (1+pw) kernels - 27 taps over 1/8 of the voxels each instead of 27 taps over all of them.
+// w_phases: mmad_conv3d_prep_weights_s2.  dx (N,D,H,W,Cdx) bf16, dy (N,Do,Ho,Wo,Cdy) bf16, Do = (D-1)/2+1 etc.
+int mmad_conv3d_dgrad_s2_bf16(const void* dy, const void* w_phases, void* dx, int N, int D, int H, int W, int Cdx, int Cdy,
+                              void* stream) {
+    MMAD_CHECK_ARG(dy && w_phases && dx && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_dgrad_s2: bad argument");
+    const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    size_t woff = 0;
+    for (int p = 0; p < 8; ++p) {
+        const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        ConvOut ov;
+        ov.Do = (D - pd + 1) / 2; ov.Ho = (H - ph + 1) / 2; ov.Wo = (W - pw + 1) / 2;
+        ov.sw = 2ll * Cdx; ov.sh = 2ll * W * Cdx; ov.sd = 2ll * H * W * Cdx; ov.sn = (long long)D * H * W * Cdx;
+        const int taps = (1 + pd) * (1 + ph) * (1 + pw);
+        if (ov.Do > 0 && ov.Ho > 0 && ov.Wo > 0) {
+            char* out = static_cast<char*>(dx) + (((size_t)pd * H + ph) * W + pw) * Cdx * 2;
+            const int rc = conv_fwd_impl(dy, static_cast<const char*>(w_phases) + woff, out, nullptr, N, Do, Ho, Wo, Cdy, Cdx, 1 + pd,
+                                         1 + ph, 1 + pw, 1, 0, 1, &ov, stream);
+            if (rc) return rc;
+        }
+        woff += (size_t)taps * Cdx * Cdy * 2;
+    }
+    return MMAD_OK;
+}
+
 
 }  // extern "C"

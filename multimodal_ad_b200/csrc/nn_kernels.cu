@@ -68,6 +68,34 @@ __global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bflo
     }
 }
 // stem weights (Cout, 1, 7,7,7) fp32 -> [Cout][Kpad] bf16 (a 1x1x1 conv over the im2col matrix), zero padded
+// ---- weights of the phase convolutions of mmad_conv3d_dgrad_s2_bf16: torch (Cdy, Cdx, 3,3,3) fp32 -> for phase p = pd*4+ph*2+pw
+//      a block [Cdx][taps_p][Cdy] bf16, tap (a, b, c) of the phase = original tap t with t = 1 on an even axis, t = 2 - 2*a on an
+//      odd one (dx[2j+1] = dy[j] w[2] + dy[j+1] w[0]).  Blocks are concatenated in phase order.
+__global__ void __launch_bounds__(256) prep_weights_s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cdy, int Cdx) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = 27ll * Cdx * Cdy;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i, base = 0;
+        int p = 0, taps = 1;
+        for (; p < 8; ++p) {                                   // locate the phase block
+            taps = (1 + (p >> 2)) * (1 + ((p >> 1) & 1)) * (1 + (p & 1));
+            const long long sz = (long long)taps * Cdx * Cdy;
+            if (r < base + sz) break;
+            base += sz;
+        }
+        r -= base;
+        const int cdy = (int)(r % Cdy); r /= Cdy;
+        const int tap = (int)(r % taps); r /= taps;
+        const int cdx = (int)r;
+        const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        const int kwp = 1 + pw, khp = 1 + ph;
+        const int c = tap % kwp, b = (tap / kwp) % khp, a = tap / (kwp * khp);
+        const int td = pd ? 2 - 2 * a : 1, th = ph ? 2 - 2 * b : 1, tw = pw ? 2 - 2 * c : 1;
+        wp[i] = __float2bfloat16(w[((size_t)cdy * Cdx + cdx) * 27 + (td * 3 + th) * 3 + tw]);
+    }
+}
+
 __global__ void prep_stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int K, int Kpad) {
     pdl_launch_dependents();
     pdl_wait();                                        // see launch_pdl (common.cuh)
@@ -813,6 +841,11 @@ int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cou
         count_launch();
     }
     return MMAD_OK;
+}
+int mmad_conv3d_prep_weights_s2(const float* w, void* w_phases, int Cdy, int Cdx, void* stream) {
+    MMAD_CHECK_ARG(w && w_phases && Cdy > 0 && Cdx > 0, "prep_weights_s2: bad argument");
+    launch_pdl(prep_weights_s2_kernel, dim3(grid_for(27ll * Cdx * Cdy, 256, 1184)), dim3(256), 0, ST, w, (__nv_bfloat16*)w_phases, Cdy, Cdx);
+    LAUNCH_OK();
 }
 int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream) {
     MMAD_CHECK_ARG(w && w_fwd && K <= Kpad && Kpad % 64 == 0, "stem_prep_weights: bad argument");

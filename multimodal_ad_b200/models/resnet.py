@@ -355,6 +355,14 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         # dgrad of conv1
         if st == 1:
             dx1, _ = r.conv(dc1, rec["w1t"], inpl, 3, 1, dil, dil, False)
+        elif st == 2 and dil == 1:
+            # stride 2: eight interleaved phase convolutions of dc1 (no zero insertion, 1/8 of the MACs)
+            wph = r.empty((27 * inpl * planes,))
+            r.chk(lib.mmad_conv3d_prep_weights_s2(_p(blk.conv1.weight.detach()), _p(wph), planes, inpl, r.stream),
+                  "mmad_conv3d_prep_weights_s2")
+            dx1 = r.empty(tuple(xin.shape))
+            r.chk(lib.mmad_conv3d_dgrad_s2_bf16(_p(dc1), _p(wph), _p(dx1), xin.shape[0], xin.shape[1], xin.shape[2], xin.shape[3], inpl,
+                                                planes, r.stream), "mmad_conv3d_dgrad_s2_bf16")
         else:
             up = r.empty(tuple(xin.shape[:4]) + (planes,))
             r.chk(lib.mmad_upsample_zero2(_p(dc1), _p(up), xin.shape[0], dc1.shape[1], dc1.shape[2], dc1.shape[3], xin.shape[1],

@@ -62,6 +62,8 @@ WG_CASES = [
     (1, 16, 16, 16, 128, 256, 1, 1, 0, 1),
     # halo kernel (64 -> 64): ragged, and the layer1 shape of a 91x109x91 volume
     (1, 5, 7, 9, 64, 64, 3, 1, 1, 1), (2, 23, 28, 23, 64, 64, 3, 1, 1, 1),
+    # stride 2 on odd extents (phase convolutions with ragged phases), and on the layer2.0 shape of a 32^3 pooled grid
+    (1, 9, 11, 13, 64, 128, 3, 2, 1, 1), (2, 32, 32, 32, 64, 128, 3, 2, 1, 1),
 ]
 
 
@@ -97,6 +99,13 @@ def test_conv3d_wgrad_and_dgrad(cfg, run):
     dx, _ = run.conv(src, wtr, cin, k, 1, dil * (k - 1) - pad, dil, False)
     ref = xr.grad.permute(0, 2, 3, 4, 1)
     assert torch.all((dx.float() - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
+    if stride == 2 and k == 3 and pad == 1 and dil == 1:
+        # the phase-decomposed data gradient (no zero insertion) gives the same tensor
+        wph = run.empty((27 * cin * cout,))
+        run.chk(run.lib.mmad_conv3d_prep_weights_s2(_p(wt), _p(wph), cout, cin, run.stream), "prep s2")
+        dx2 = torch.full((n, d, h, w, cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+        run.chk(run.lib.mmad_conv3d_dgrad_s2_bf16(_p(dy), _p(wph), _p(dx2), n, d, h, w, cin, cout, run.stream), "dgrad s2")
+        assert torch.all((dx2.float() - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
 
 
 @pytest.mark.parametrize("c,rows", [(64, 4099), (128, 513), (256, 70), (512, 1000)])
