@@ -678,6 +678,116 @@ __global__ void __launch_bounds__(512) maxpool3d_bwd_march_kernel(const uint4* _
     }
 }
 
+
+// ---- the same fused stem pass, marching along D with the conv output staged in shared memory.  A block owns two pooled rows
+//      (all of W) of one sample and a range of pooled slices; the five input rows x W x C of every input slice are streamed once
+//      into a 5-slot ring (1-D bulk copy), turned IN PLACE into the stored activation bf16(relu(bn(c))) - once per element
+//      instead of once per window that contains it (3.4x) - and pooled with packed 16-bit compares (the activations are
+//      non-negative, so their bf16 bit patterns order like the values; +1 per lane makes "no tap yet" = 0).
+constexpr int kSpSlots = 5;
+__global__ void __launch_bounds__(512, 1)
+stem_pool_march_kernel(const uint4* __restrict__ c, const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ y,
+                       uint2* __restrict__ idx, int N, int D, int H, int W, int C, int Do, int Ho, int Wo, int dsplit) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(128) unsigned char ssm[];
+    const int cv = C >> 3;
+    const int hgroups = (Ho + 1) >> 1;
+    int b = blockIdx.x;
+    const int ds = b % dsplit; b /= dsplit;
+    const int hg = b % hgroups; b /= hgroups;
+    const int n = b;
+    const int oh0 = hg * 2, nro = min(2, Ho - oh0);                       // pooled rows of this block
+    const int ihb = 2 * oh0 - 1;                                          // input row of tile row 0 (may be -1)
+    const int ih_lo = max(0, ihb), ih_hi = min(H - 1, 2 * (oh0 + nro - 1) + 1);
+    const int od_lo = (int)((long long)Do * ds / dsplit), od_hi = (int)((long long)Do * (ds + 1) / dsplit);
+    if (od_lo >= od_hi) return;
+    const int id_lo = max(0, 2 * od_lo - 1), id_hi = min(D - 1, 2 * (od_hi - 1) + 1);   // input slices needed
+    const uint32_t row_bytes = (uint32_t)W * cv * 16, slot_bytes = 5u * row_bytes;
+    const uint32_t copy_bytes = (uint32_t)(ih_hi - ih_lo + 1) * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ssm + kSpSlots * slot_bytes);
+    const uint32_t full0 = smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < kSpSlots; ++q) mbar_init(full0 + 8 * q, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto load = [&](int id) {                                             // thread 0 only
+        const int slot = (id - id_lo) % kSpSlots;
+        mbar_arrive_expect_tx(full0 + 8 * slot, copy_bytes);
+        bulk_g2s(smem_u32(ssm) + slot * slot_bytes + (uint32_t)(ih_lo - ihb) * row_bytes,
+                 c + (((size_t)n * D + id) * H + ih_lo) * W * cv, copy_bytes, full0 + 8 * slot);
+    };
+    if (threadIdx.x == 0)
+        for (int id = id_lo; id <= min(id_hi, id_lo + kSpSlots - 1); ++id) load(id);
+
+    const int tv = threadIdx.x % cv;                                      // 512 % cv == 0: one channel vector per thread
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[tv * 8 + j]; sh[j] = shift[tv * 8 + j]; }
+    const int row_vec = W * cv, n_in = (ih_hi - ih_lo + 1) * row_vec, in_off = (ih_lo - ihb) * row_vec;
+
+    int ready = id_lo - 1;                                                // input slices already transformed
+    for (int od = od_lo; od < od_hi; ++od) {
+        const int s_hi = min(D - 1, 2 * od + 1);
+        // 1. transform the slices that arrived since the last step
+        for (int id = ready + 1; id <= s_hi; ++id) {
+            const int q = id - id_lo;
+            mbar_wait(full0 + 8 * (q % kSpSlots), (q / kSpSlots) & 1);
+            uint4* sl = reinterpret_cast<uint4*>(ssm + (q % kSpSlots) * slot_bytes) + in_off;
+            for (int i = threadIdx.x; i < n_in; i += 512) {
+                float f[8];
+                unpack8(sl[i], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                uint4 a = pack8(f);
+                a.x &= 0x7fff7fffu; a.y &= 0x7fff7fffu; a.z &= 0x7fff7fffu; a.w &= 0x7fff7fffu;     // -0 -> +0
+                sl[i] = a;
+            }
+        }
+        ready = s_hi;
+        __syncthreads();
+        // 2. pool: one pooled vector (8 channels) per thread and iteration
+        for (int o = threadIdx.x; o < nro * Wo * cv; o += 512) {
+            const int v = o % cv, ow = (o / cv) % Wo, ohl = o / (cv * Wo);
+            uint32_t best[4] = {0u, 0u, 0u, 0u}, bi[4] = {0u, 0u, 0u, 0u};
+            uint32_t tap = 0;
+            for (int kd = 0; kd < 3; ++kd) {
+                const int id = 2 * od + kd - 1;
+                if ((unsigned)id >= (unsigned)D) { tap += 9; continue; }
+                const uint4* sl = reinterpret_cast<const uint4*>(ssm + ((id - id_lo) % kSpSlots) * slot_bytes);
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int r = 2 * ohl + kh;                           // tile row; input row ihb + r
+                    if ((unsigned)(ihb + r) >= (unsigned)H) { tap += 3; continue; }
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw, ++tap) {
+                        const int iw = 2 * ow + kw - 1;
+                        if ((unsigned)iw >= (unsigned)W) continue;
+                        const uint4 a = sl[(r * W + iw) * cv + v];
+                        const uint32_t t2 = tap * 0x00010001u;
+                        const uint32_t av[4] = {a.x + 0x00010001u, a.y + 0x00010001u, a.z + 0x00010001u, a.w + 0x00010001u};
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            const uint32_t m = __vcmpgtu2(av[w4], best[w4]);   // strictly greater: the first maximum wins
+                            best[w4] = __vmaxu2(av[w4], best[w4]);
+                            bi[w4] = (bi[w4] & ~m) | (t2 & m);
+                        }
+                    }
+                }
+            }
+            const size_t oi = ((((size_t)n * Do + od) * Ho + oh0 + ohl) * Wo + ow) * cv + v;
+            y[oi] = make_uint4(best[0] - 0x00010001u, best[1] - 0x00010001u, best[2] - 0x00010001u, best[3] - 0x00010001u);
+            idx[oi] = make_uint2(__byte_perm(bi[0], bi[1], 0x6420), __byte_perm(bi[2], bi[3], 0x6420));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // in-place (generic) writes before the refilling bulk copies
+        __syncthreads();
+        // 3. slices 2od-1 and 2od are dead: refill their slots with the slices two steps ahead
+        if (threadIdx.x == 0)
+            for (int id = 2 * od - 1; id <= 2 * od; ++id)
+                if (id >= id_lo && id + kSpSlots <= id_hi) load(id + kSpSlots);
+    }
+}
+
 // ---- fused stem (resnet.py:206-208): p = maxpool3d(relu(bn(c)), k3 s2 p1) in one pass over the conv output c; the
 //      post-ReLU tensor is never stored.  idx keeps the winning tap (first maximum in (kd,kh,kw) order).
 __global__ void __launch_bounds__(256) stem_bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ c, const float* __restrict__ scale,
@@ -975,6 +1085,24 @@ int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * Do * Ho * Wo * (C / 8);
     MMAD_CHECK_ARG(total < (1ll << 32), "stem_bn_relu_maxpool_fwd: tensor too large for 32-bit indexing");
+    static int march_mode = -1;                        // marching kernel: on unless MMAD_STEM_POOL_MARCH=0
+    if (march_mode < 0) { const char* e = getenv("MMAD_STEM_POOL_MARCH"); march_mode = e ? atoi(e) : 1; }
+    const int cv = C / 8;
+    const long long slot = 5ll * W * cv * 16;
+    if (march_mode && 512 % cv == 0 && kSpSlots * slot + 64 <= 220 * 1024 && Do >= 2) {
+        const int smem = (int)(kSpSlots * slot) + 64;
+        static bool attr_done = false;
+        if (!attr_done) {
+            MMAD_CUDA(cudaFuncSetAttribute(stem_pool_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attr_done = true;
+        }
+        const int hgroups = (Ho + 1) / 2;
+        int dsplit = 1;                                // several blocks per SM over the run, at least 4 pooled slices each
+        while ((long long)N * hgroups * dsplit < 148 * 6 && Do / (dsplit * 2) >= 4) dsplit *= 2;
+        launch_pdl(stem_pool_march_kernel, dim3((unsigned)(N * hgroups * dsplit)), dim3(512), smem, ST, (const uint4*)c, scale, shift, (uint4*)y,
+                   (uint2*)idx, N, D, H, W, C, Do, Ho, Wo, dsplit);
+        LAUNCH_OK();
+    }
     launch_pdl(stem_bn_relu_maxpool_fwd_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
                                                                                     W, C, Do, Ho, Wo);
     LAUNCH_OK();
