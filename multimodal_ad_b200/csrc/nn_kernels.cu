@@ -1009,7 +1009,7 @@ int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2
                        const float* invstd, const float* mask_scale, const float* mask_shift, void* g_out, float* partials, int64_t rows,
                        int C, void* stream) {
     MMAD_CHECK_ARG((dy_bf16 || dy_f32) && x && mean && invstd && partials && rows > 0, "bn_bwd_reduce: bad argument");
-    MMAD_CHECK_ARG(C % 64 == 0 && C <= 512, "bn_bwd_reduce: C must be 64, 128, 256 or 512");
+    MMAD_CHECK_ARG(C % 64 == 0 && C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_reduce: C must be 64, 128, 256, 512, 1024 or 2048");
     const int grid = mmad_bn_bwd_partials(rows);
     static int tma_mode = -1;                          // TMA-staged kernel for bf16 gradients: on unless MMAD_BN_TMA=0
     if (tma_mode < 0) { const char* e = getenv("MMAD_BN_TMA"); tma_mode = e ? atoi(e) : 1; }

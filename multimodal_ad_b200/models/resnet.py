@@ -262,26 +262,47 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     blocks = [b for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer]
     for bi, blk in enumerate(blocks):
         last = bi == len(blocks) - 1
-        st, dil = blk.conv1.stride[0], blk.conv1.dilation[0]
-        planes = blk.conv1.out_channels
-        w1f, w1t = r.prep_weights(blk.conv1, need_grad)
-        w2f, w2t = r.prep_weights(blk.conv2, need_grad)
-        c1, part1 = r.conv(cur, w1f, planes, 3, st, dil, dil, training)
-        cnt = c1.numel() // planes
-        v1 = r.bn_params(blk.bn1, part1, cnt, training)
-        a1 = r.bn_apply(c1, v1, relu=True)
-        c2, part2 = r.conv(a1, w2f, planes, 3, 1, dil, dil, training)
-        v2 = r.bn_params(blk.bn2, part2, cnt, training)
-        rec = dict(blk=blk, xin=cur, c1=c1, v1=v1, a1=a1, c2=c2, v2=v2, w1t=w1t, w2t=w2t, stride=st, dil=dil)
+        if isinstance(blk, Bottleneck):
+            # resnet.py:89-109: 1x1x1 reduce, 3x3x3 (stride / dilation), 1x1x1 expand (x4), residual
+            st, dil = blk.conv2.stride[0], blk.conv2.dilation[0]
+            planes, outc = blk.conv1.out_channels, blk.conv3.out_channels
+            w1f, w1t = r.prep_weights(blk.conv1, need_grad)
+            w2f, w2t = r.prep_weights(blk.conv2, need_grad and st == 1)
+            w3f, w3t = r.prep_weights(blk.conv3, need_grad)
+            c1, part1 = r.conv(cur, w1f, planes, 1, 1, 0, 1, training)
+            v1 = r.bn_params(blk.bn1, part1, c1.numel() // planes, training)
+            a1 = r.bn_apply(c1, v1, relu=True)
+            c2, part2 = r.conv(a1, w2f, planes, 3, st, dil, dil, training)
+            cnt = c2.numel() // planes
+            v2 = r.bn_params(blk.bn2, part2, cnt, training)
+            a2 = r.bn_apply(c2, v2, relu=True)
+            c3, part3 = r.conv(a2, w3f, outc, 1, 1, 0, 1, training)
+            v3 = r.bn_params(blk.bn3, part3, cnt, training)
+            rec = dict(blk=blk, xin=cur, c1=c1, v1=v1, a1=a1, c2=c2, v2=v2, a2=a2, c3=c3, v3=v3, w1t=w1t, w2t=w2t, w3t=w3t,
+                       stride=st, dil=dil)
+            pre, vpre, width = c3, v3, outc
+        else:
+            st, dil = blk.conv1.stride[0], blk.conv1.dilation[0]
+            planes = blk.conv1.out_channels
+            w1f, w1t = r.prep_weights(blk.conv1, need_grad)
+            w2f, w2t = r.prep_weights(blk.conv2, need_grad)
+            c1, part1 = r.conv(cur, w1f, planes, 3, st, dil, dil, training)
+            cnt = c1.numel() // planes
+            v1 = r.bn_params(blk.bn1, part1, cnt, training)
+            a1 = r.bn_apply(c1, v1, relu=True)
+            c2, part2 = r.conv(a1, w2f, planes, 3, 1, dil, dil, training)
+            v2 = r.bn_params(blk.bn2, part2, cnt, training)
+            rec = dict(blk=blk, xin=cur, c1=c1, v1=v1, a1=a1, c2=c2, v2=v2, w1t=w1t, w2t=w2t, stride=st, dil=dil)
+            pre, vpre, width = c2, v2, planes
         if blk.downsample is not None:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             wdf, wdt = r.prep_weights(dconv, need_grad)
-            cd, partd = r.conv(cur, wdf, planes, 1, dconv.stride[0], 0, 1, training)
+            cd, partd = r.conv(cur, wdf, width, 1, dconv.stride[0], 0, 1, training)
             vd = r.bn_params(dbn, partd, cnt, training)
-            out = r.bn_apply(c2, v2, relu=True, res=cd, res_vec=vd, also_f32=last)
+            out = r.bn_apply(pre, vpre, relu=True, res=cd, res_vec=vd, also_f32=last)
             rec.update(cd=cd, vd=vd, wdt=wdt)
         else:
-            out = r.bn_apply(c2, v2, relu=True, res=cur, also_f32=last)
+            out = r.bn_apply(pre, vpre, relu=True, res=cur, also_f32=last)
         out32 = None
         if last:
             out, out32 = out
@@ -334,40 +355,68 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         r.chk(lib.mmad_ncs_f32_to_nsc_bf16(_p(src), _p(dy), n, c, do * ho * wo, r.stream), "mmad_ncs_f32_to_nsc_bf16")
         dy_f32 = False
     dy2 = None
+    def dgrad_3x3(dc, weight_t, conv, xin_shape, cin, cout, st, dil):
+        """data gradient of a 3x3x3 convolution `conv` (cin -> cout): dc (N,Do,Ho,Wo,cout) -> (N,D,H,W,cin)"""
+        if st == 1:
+            return r.conv(dc, weight_t, cin, 3, 1, dil, dil, False)[0]
+        if st == 2 and dil == 1:
+            # stride 2: eight interleaved phase convolutions of dc (no zero insertion, 1/8 of the MACs)
+            wph = r.empty((27 * cin * cout,))
+            r.chk(lib.mmad_conv3d_prep_weights_s2(_p(conv.weight.detach()), _p(wph), cout, cin, r.stream), "mmad_conv3d_prep_weights_s2")
+            dx = r.empty(tuple(xin_shape[:4]) + (cin,))
+            r.chk(lib.mmad_conv3d_dgrad_s2_bf16(_p(dc), _p(wph), _p(dx), xin_shape[0], xin_shape[1], xin_shape[2], xin_shape[3], cin, cout,
+                                                r.stream), "mmad_conv3d_dgrad_s2_bf16")
+            return dx
+        if weight_t is None:
+            weight_t = r.prep_weights(conv, True)[1]
+        up = r.empty(tuple(xin_shape[:4]) + (cout,))
+        r.chk(lib.mmad_upsample_zero2(_p(dc), _p(up), xin_shape[0], dc.shape[1], dc.shape[2], dc.shape[3], xin_shape[1], xin_shape[2],
+                                      xin_shape[3], cout, r.stream), "mmad_upsample_zero2")
+        return r.conv(up, weight_t, cin, 3, 1, 2 * dil - dil, dil, False)[0]      # pad' = dil*(k-1) - pad
+
     for rec in reversed(tape["blocks"]):
         blk, st, dil = rec["blk"], rec["stride"], rec["dil"]
         planes = blk.conv1.out_channels
         inpl = blk.conv1.in_channels
-        # out = relu(bn2(c2) + res): g2 = dy * (out > 0)
-        dc2, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, dy_is_f32=dy_f32)
-        dy_f32 = False
-        grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
-        gw = grads.new_grad(blk.conv2.weight)
-        r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw, grads.pusher(gw))
-        grads.set_quiet(blk.conv2.weight, gw)
-        da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
-        dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
-        grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
-        gw = grads.new_grad(blk.conv1.weight)
-        r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw, grads.pusher(gw))
-        grads.set_quiet(blk.conv1.weight, gw)
         xin = rec["xin"]
-        # dgrad of conv1
-        if st == 1:
-            dx1, _ = r.conv(dc1, rec["w1t"], inpl, 3, 1, dil, dil, False)
-        elif st == 2 and dil == 1:
-            # stride 2: eight interleaved phase convolutions of dc1 (no zero insertion, 1/8 of the MACs)
-            wph = r.empty((27 * inpl * planes,))
-            r.chk(lib.mmad_conv3d_prep_weights_s2(_p(blk.conv1.weight.detach()), _p(wph), planes, inpl, r.stream),
-                  "mmad_conv3d_prep_weights_s2")
-            dx1 = r.empty(tuple(xin.shape))
-            r.chk(lib.mmad_conv3d_dgrad_s2_bf16(_p(dc1), _p(wph), _p(dx1), xin.shape[0], xin.shape[1], xin.shape[2], xin.shape[3], inpl,
-                                                planes, r.stream), "mmad_conv3d_dgrad_s2_bf16")
+        if isinstance(blk, Bottleneck):
+            outc = blk.conv3.out_channels
+            # out = relu(bn3(c3) + res): g3 = dy * (out > 0)
+            dc3, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c3"], rec["v3"], blk.bn3.weight.detach(), training, dy_is_f32=dy_f32)
+            dy_f32 = False
+            grads[blk.bn3.weight], grads[blk.bn3.bias] = dg, db
+            gw = grads.new_grad(blk.conv3.weight)
+            r.wgrad(rec["a2"], dc3, outc, 1, 1, 0, 1, gw, grads.pusher(gw))
+            grads.set_quiet(blk.conv3.weight, gw)
+            da2, _ = r.conv(dc3, rec["w3t"], planes, 1, 1, 0, 1, False)
+            dc2, _, dg, db = r.bn_bwd(da2, None, rec["a2"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, want_g=True)
+            grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
+            gw = grads.new_grad(blk.conv2.weight)
+            r.wgrad(rec["a1"], dc2, planes, 3, st, dil, dil, gw, grads.pusher(gw))
+            grads.set_quiet(blk.conv2.weight, gw)
+            da1 = dgrad_3x3(dc2, rec["w2t"], blk.conv2, rec["a1"].shape, planes, planes, st, dil)
+            dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
+            grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
+            gw = grads.new_grad(blk.conv1.weight)
+            r.wgrad(xin, dc1, planes, 1, 1, 0, 1, gw, grads.pusher(gw))
+            grads.set_quiet(blk.conv1.weight, gw)
+            dx1, _ = r.conv(dc1, rec["w1t"], inpl, 1, 1, 0, 1, False)
+            planes = outc                                  # width of the residual branch below
         else:
-            up = r.empty(tuple(xin.shape[:4]) + (planes,))
-            r.chk(lib.mmad_upsample_zero2(_p(dc1), _p(up), xin.shape[0], dc1.shape[1], dc1.shape[2], dc1.shape[3], xin.shape[1],
-                                          xin.shape[2], xin.shape[3], planes, r.stream), "mmad_upsample_zero2")
-            dx1, _ = r.conv(up, rec["w1t"], inpl, 3, 1, 2 * dil - dil, dil, False)    # pad' = dil*(k-1) - pad
+            # out = relu(bn2(c2) + res): g2 = dy * (out > 0)
+            dc2, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, dy_is_f32=dy_f32)
+            dy_f32 = False
+            grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
+            gw = grads.new_grad(blk.conv2.weight)
+            r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw, grads.pusher(gw))
+            grads.set_quiet(blk.conv2.weight, gw)
+            da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
+            dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
+            grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
+            gw = grads.new_grad(blk.conv1.weight)
+            r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw, grads.pusher(gw))
+            grads.set_quiet(blk.conv1.weight, gw)
+            dx1 = dgrad_3x3(dc1, rec["w1t"], blk.conv1, xin.shape, inpl, planes, st, dil)      # dgrad of conv1
         if "cd" in rec:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             dcd, _, dg, db = r.bn_bwd(g2, None, None, rec["cd"], rec["vd"], dbn.weight.detach(), training, want_g=False)
@@ -417,7 +466,7 @@ def tape_stages(model: "ResNet", tape) -> dict:
     names = [f"layer{li}.{bi}" for li, layer in enumerate((model.layer1, model.layer2, model.layer3, model.layer4), 1)
              for bi in range(len(layer))]
     for pre, rec in zip(names, tape["blocks"]):
-        for k in ("c1", "a1", "c2", "cd", "out"):
+        for k in ("c1", "a1", "c2", "a2", "c3", "cd", "out"):
             if k in rec:
                 out[f"{pre}.{k}"] = f(rec[k])
     return out
@@ -504,6 +553,8 @@ class ResNet(nn.Module):
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:
                 ps += [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias]
+                if isinstance(blk, Bottleneck):
+                    ps += [blk.conv3.weight, blk.bn3.weight, blk.bn3.bias]
                 if blk.downsample is not None:
                     ps += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
         return ps
@@ -512,8 +563,8 @@ class ResNet(nn.Module):
         """conv1 … layer4 (resnet.py:205-212) -> (N, 512, D/8.., H/8.., W/8..) fp32."""
         if not x.is_cuda:
             raise _lib.MmadError("multimodal_ad_b200 ResNet runs on CUDA tensors only (no CPU fallback)")
-        if self.block_type is not BasicBlock or self.shortcut_type != 'B':
-            raise _lib.MmadError("accelerated path covers BasicBlock networks (resnet10/18/34) with shortcut type 'B'")
+        if self.block_type not in (BasicBlock, Bottleneck) or self.shortcut_type != 'B':
+            raise _lib.MmadError("accelerated path covers BasicBlock / Bottleneck networks with shortcut type 'B'")
         with torch.cuda.device(x.device):
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.backbone_parameters()):
                 return _BackboneFunction.apply(x, self, *self.backbone_parameters())

@@ -26,7 +26,7 @@ def _model(depth, size, seed=0):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(seed)
-    fn = {10: resnet.resnet10, 18: resnet.resnet18, 34: resnet.resnet34}[depth]
+    fn = {10: resnet.resnet10, 18: resnet.resnet18, 34: resnet.resnet34, 50: resnet.resnet50}[depth]
     model = fn(sample_input_D=size, sample_input_H=size, sample_input_W=size, num_seg_classes=1).cuda()
     with torch.no_grad():
         for m in model.modules():
@@ -39,7 +39,10 @@ def _model(depth, size, seed=0):
 # the last two cases are the reference's own volume (BASELINE configs[0]: 91x109x91, ragged in every tile) and the
 # bench volume (configs[2]: 128^3), batch 2
 @pytest.mark.parametrize("depth,n,shape", [(10, 2, (32, 32, 32)), (18, 2, (64, 64, 64)), (18, 1, (45, 54, 45)), (34, 1, (32, 32, 32)),
-                                           (18, 2, (91, 109, 91)), (18, 2, (128, 128, 128))])
+                                           (18, 2, (91, 109, 91)), (18, 2, (128, 128, 128)),
+                                           # Bottleneck network (resnet.py:72-109; the depth of the reference's config/cfg_denseNet.json) at that
+                                           # config's 80x98x80 volume, and a cube
+                                           (50, 2, (32, 32, 32)), (50, 1, (80, 98, 80))])
 def test_forward_backward_vs_oracle(depth, n, shape, built_lib):
     from multimodal_ad_b200.models.resnet import tape_stages
 
@@ -67,11 +70,17 @@ def test_forward_backward_vs_oracle(depth, n, shape, built_lib):
     errs = {k: _rel(named[k].grad, v.grad) for k, v in leaves.items() if v.grad is not None and not k.startswith("conv_seg")}
     assert len(errs) >= 30 and all(named[k].grad is not None for k in errs)
     worst = max(errs, key=errs.get)
-    assert errs[worst] < 4e-2, (worst, errs[worst])                      # bf16 storage noise accumulated over the depth
+    # bf16 storage noise accumulated over the depth (resnet50: 53 convolutions deep, and on these small test grids layer4's
+    # BatchNorms see only 8-16 values per channel)
+    assert errs[worst] < (4e-2 if depth < 50 else 0.15), (worst, errs[worst])
     assert float(np.median(list(errs.values()))) < 2e-2                  # north star: 2e-2 in bf16
     ref_e, _ = oracle(emulate_bf16=True)
     ref_f, _ = oracle()
-    assert _rel(feats, ref_e) < 5e-2 and _rel(feats, ref_f) < 8e-2
+    # free-running comparisons (no pinned activations): one-ulp differences flip ReLU masks and move BatchNorm statistics, the
+    # more so the deeper the net and the fewer values a BatchNorm sees; reported bounds, the forced comparison above is the gate
+    free_e, free_f = _rel(feats, ref_e), _rel(feats, ref_f)
+    gap = _rel(ref_e, ref_f)                                             # what bf16 storage alone does to the fp32 network
+    assert (free_e < 5e-2 and free_f < 8e-2) if depth < 50 else (free_e < 0.6 * gap + 5e-2 and free_f < 1.2 * gap + 8e-2), (free_e, free_f, gap)
     # running statistics follow nn.BatchNorm3d
     c0 = F.conv3d(x.to(torch.bfloat16).float(), sd["conv1.weight"].to(torch.bfloat16).float(), stride=2, padding=3)
     assert _rel(model.bn1.running_mean, 0.9 * sd["bn1.running_mean"] + 0.1 * c0.mean(dim=(0, 2, 3, 4))) < 5e-3

@@ -83,6 +83,33 @@ def test_emulated_and_forced_modes_are_consistent_on_cpu():
     assert not torch.allclose(c, b)                                       # the substituted stage feeds the rest of the net
 
 
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted on this box")
+def test_bottleneck_oracle_is_bit_exact_with_the_live_reference():
+    """resnet50 (Bottleneck, resnet.py:72-109): the oracle's forward equals the reference module's bit for bit on CPU, and
+    this repo's resnet50 reproduces the reference's initialisation and state_dict keys."""
+    import importlib.util
+    import warnings
+
+    from multimodal_ad_b200.models import resnet as mine
+
+    spec = importlib.util.spec_from_file_location("ref_resnet_b", REF)
+    ref = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(ref)
+        torch.manual_seed(11)
+        m = ref.resnet50(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True)
+        torch.manual_seed(11)
+        mm = mine.resnet50(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True)
+    sr, sm = m.state_dict(), mm.state_dict()
+    assert list(sr.keys()) == list(sm.keys()) and all(torch.equal(sr[k], sm[k]) for k in sr)
+    m.train()
+    x = torch.rand(2, 1, 16, 16, 16)
+    feats = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+    out = resnet_features_oracle({k: v.detach().clone() for k, v in sr.items()}, x, [3, 4, 6, 3], True)
+    assert torch.equal(feats, out)
+
+
 def test_accelerated_model_refuses_cpu_and_unsupported_variants(built_lib):
     from multimodal_ad_b200 import _lib
     from multimodal_ad_b200.models import resnet
