@@ -294,7 +294,14 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
             v2 = r.bn_params(blk.bn2, part2, cnt, training)
             rec = dict(blk=blk, xin=cur, c1=c1, v1=v1, a1=a1, c2=c2, v2=v2, w1t=w1t, w2t=w2t, stride=st, dil=dil)
             pre, vpre, width = c2, v2, planes
-        if blk.downsample is not None:
+        if blk.downsample is not None and not isinstance(blk.downsample, nn.Module):
+            # shortcut 'A' (resnet.py:26-37): subsample and zero-pad the channels - no parameters, plain tensor plumbing
+            ra = r.empty(pre.shape)
+            ra.zero_()
+            ra[..., : cur.shape[-1]] = cur[:, ::st, ::st, ::st, :]
+            out = r.bn_apply(pre, vpre, relu=True, res=ra, also_f32=last)
+            rec.update(short_a=True)
+        elif blk.downsample is not None:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             wdf, wdt = r.prep_weights(dconv, need_grad)
             cd, partd = r.conv(cur, wdf, width, 1, dconv.stride[0], 0, 1, training)
@@ -431,6 +438,10 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
                 r.chk(lib.mmad_upsample_zero2(_p(dcd), _p(up), xin.shape[0], dcd.shape[1], dcd.shape[2], dcd.shape[3], xin.shape[1],
                                               xin.shape[2], xin.shape[3], planes, r.stream), "mmad_upsample_zero2")
                 dx2, _ = r.conv(up, rec["wdt"], inpl, 1, 1, 0, 1, False)
+        elif rec.get("short_a"):
+            dx2 = r.empty(tuple(xin.shape))                                         # shortcut 'A': the subsampled voxels / first channels
+            dx2.zero_()
+            dx2[:, ::st, ::st, ::st, :] = g2[..., : xin.shape[-1]]
         else:
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
@@ -555,7 +566,7 @@ class ResNet(nn.Module):
                 ps += [blk.conv1.weight, blk.bn1.weight, blk.bn1.bias, blk.conv2.weight, blk.bn2.weight, blk.bn2.bias]
                 if isinstance(blk, Bottleneck):
                     ps += [blk.conv3.weight, blk.bn3.weight, blk.bn3.bias]
-                if blk.downsample is not None:
+                if isinstance(blk.downsample, nn.Module):                  # shortcut 'B'; type 'A' is a parameter-free partial
                     ps += [blk.downsample[0].weight, blk.downsample[1].weight, blk.downsample[1].bias]
         return ps
 
@@ -563,8 +574,8 @@ class ResNet(nn.Module):
         """conv1 … layer4 (resnet.py:205-212) -> (N, 512, D/8.., H/8.., W/8..) fp32."""
         if not x.is_cuda:
             raise _lib.MmadError("multimodal_ad_b200 ResNet runs on CUDA tensors only (no CPU fallback)")
-        if self.block_type not in (BasicBlock, Bottleneck) or self.shortcut_type != 'B':
-            raise _lib.MmadError("accelerated path covers BasicBlock / Bottleneck networks with shortcut type 'B'")
+        if self.block_type not in (BasicBlock, Bottleneck):
+            raise _lib.MmadError("accelerated path covers BasicBlock / Bottleneck networks")
         with torch.cuda.device(x.device):
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.backbone_parameters()):
                 return _BackboneFunction.apply(x, self, *self.backbone_parameters())

@@ -87,6 +87,32 @@ def test_forward_backward_vs_oracle(depth, n, shape, built_lib):
     assert int(model.bn1.num_batches_tracked) == 1
 
 
+def test_shortcut_type_a_forward_backward_vs_oracle(built_lib):
+    """Shortcut 'A' (resnet.py:26-37, the variant MedicalNet's resnet10/18/34 checkpoints were trained with): subsample + zero
+    channel padding instead of a 1x1x1 convolution."""
+    from multimodal_ad_b200.models import resnet
+    from multimodal_ad_b200.models.resnet import tape_stages
+
+    torch.manual_seed(1)
+    model = resnet.resnet18(sample_input_D=32, sample_input_H=32, sample_input_W=32, num_seg_classes=1, shortcut_type="A").cuda()
+    assert not any("downsample" in k for k in model.state_dict())
+    x = torch.rand((2, 1, 32, 40, 24), device="cuda")
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.train()
+    model.keep_tape = True
+    feats = model.features(x)
+    wgt = torch.randn_like(feats) / feats.numel() ** 0.5
+    (feats * wgt).sum().backward()
+    forced = tape_stages(model, model._last_tape)
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    ref = resnet_features_oracle(leaves, x, [2, 2, 2, 2], True, emulate_bf16=True, forced=forced)
+    (ref * wgt).sum().backward()
+    assert _rel(feats, ref.detach()) < 4e-3
+    named = dict(model.named_parameters())
+    errs = {k: _rel(named[k].grad, v.grad) for k, v in leaves.items() if v.grad is not None and not k.startswith("conv_seg")}
+    assert len(errs) >= 30 and max(errs.values()) < 4e-2 and float(np.median(list(errs.values()))) < 2e-2
+
+
 def test_eval_mode_and_state_dict_roundtrip(built_lib):
     model = _model(10, 32, seed=3)
     x = torch.rand(2, 1, 32, 32, 32, device="cuda")

@@ -169,3 +169,29 @@ def test_image_encoder_dropin_structure():
     assert enc.image_encoder34().layer3[5].conv1.dilation == (2, 2, 2)
     with pytest.raises(Exception):
         e(torch.zeros(1, 1, 16, 16, 16))                    # CPU tensors are refused (no fallback)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference not mounted on this box")
+def test_shortcut_a_oracle_is_bit_exact_with_the_live_reference():
+    """shortcut type 'A' (resnet.py:26-37): oracle forward equals the reference module's on CPU, same init and keys."""
+    import importlib.util
+    import warnings
+
+    from multimodal_ad_b200.models import resnet as mine
+
+    spec = importlib.util.spec_from_file_location("ref_resnet_a", REF)
+    ref = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(ref)
+        torch.manual_seed(5)
+        m = ref.resnet18(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True, shortcut_type="A")
+        torch.manual_seed(5)
+        mm = mine.resnet18(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True, shortcut_type="A")
+    sr, sm = m.state_dict(), mm.state_dict()
+    assert list(sr.keys()) == list(sm.keys()) and all(torch.equal(sr[k], sm[k]) for k in sr)
+    m.train()
+    x = torch.rand(2, 1, 16, 20, 12)
+    feats = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+    out = resnet_features_oracle({k: v.detach().clone() for k, v in sr.items()}, x, [2, 2, 2, 2], True)
+    assert torch.equal(feats, out)
