@@ -155,7 +155,7 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
         opt.step()
         return loss
 
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 20))
     for i in range(3):
         step(i)
     torch.cuda.synchronize()

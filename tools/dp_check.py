@@ -39,9 +39,17 @@ def main():
     for p, w in zip(model.parameters(), want):
         if w is None: continue
         worst = max(worst, ((p.grad - w).norm() / (w.norm() + 1e-20)).item()); nb += 1
-    ok = worst < 1e-5
+    # gradient accumulation: a second backward WITHOUT zero_grad must add the averaged gradients once more
+    crit(model(x), y).backward()
+    red.finish(model.parameters())
+    torch.cuda.synchronize()
+    worst2 = 0.0
+    for p, w in zip(model.parameters(), want):
+        if w is None: continue
+        worst2 = max(worst2, ((p.grad - 2 * w).norm() / (2 * w.norm() + 1e-20)).item())
+    ok = worst < 1e-5 and worst2 < 1e-5
     if rank == 0:
-        print(json.dumps(dict(world=world, params=nb, worst_rel=worst, ok=ok)), flush=True)
+        print(json.dumps(dict(world=world, params=nb, worst_rel=worst, worst_rel_accumulated=worst2, ok=ok)), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
