@@ -292,31 +292,34 @@ __global__ void __launch_bounds__((NW + kProducerWarps) * 32, 1) roi_stream_kern
     }
 }
 
-// Second pass: one warp per (volume group, ROI), lane = volume.  The ROI's partial slots are contiguous and in
-// ascending tile order; sums are added in that fixed order, keys are max-reduced (order independent).
+// Second pass: one block of four warps per (volume group, ROI), lane = volume.  The ROI's partial slots are contiguous and
+// in ascending tile order; warp q adds slots q, q+4, ... in that order and the four warp sums are combined in warp order (a
+// fixed association: results are reproducible run to run), keys are max-reduced (order independent).  Four warps instead of
+// one shorten the dependent load chain of this latency-bound pass.
 __global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restrict__ slot_sum,
                                                            const unsigned long long* __restrict__ slot_key,
                                                            const int32_t* __restrict__ fin_ptr,
                                                            const int32_t* __restrict__ counts, int n_groups, int R,
                                                            long long n_vols, float* __restrict__ mean,
                                                            float* __restrict__ mx_out, int32_t* __restrict__ arg_out) {
-    const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ double sh_s[4][32];
+    __shared__ unsigned long long sh_k[4][32];
+    const int w = blockIdx.x;
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
     pdl_launch_dependents();
     pdl_wait();
-    if (w >= n_groups * R) return;
     const int g = w / R, r = w - g * R;
     double s = 0.0;
     unsigned long long key = 0ull;
     const int k0 = fin_ptr[w], k1 = fin_ptr[w + 1];
-    int k = k0;
-    for (; k + 4 <= k1; k += 4) {
+    int k = k0 + q;
+    for (; k + 12 < k1; k += 16) {
         double sv[4];
         unsigned long long kv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            sv[u] = slot_sum[(size_t)(k + u) * 32 + lane];
-            kv[u] = slot_key[(size_t)(k + u) * 32 + lane];
+            sv[u] = slot_sum[(size_t)(k + 4 * u) * 32 + lane];
+            kv[u] = slot_key[(size_t)(k + 4 * u) * 32 + lane];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -324,11 +327,18 @@ __global__ void __launch_bounds__(128) roi_finalize_kernel(const double* __restr
             key = kv[u] > key ? kv[u] : key;
         }
     }
-    for (; k < k1; ++k) {
+    for (; k < k1; k += 4) {
         s += slot_sum[(size_t)k * 32 + lane];
         const unsigned long long kk = slot_key[(size_t)k * 32 + lane];
         key = kk > key ? kk : key;
     }
+    sh_s[q][lane] = s;
+    sh_k[q][lane] = key;
+    __syncthreads();
+    if (q != 0) return;
+    s = ((sh_s[0][lane] + sh_s[1][lane]) + sh_s[2][lane]) + sh_s[3][lane];
+#pragma unroll
+    for (int u = 1; u < 4; ++u) key = sh_k[u][lane] > key ? sh_k[u][lane] : key;
     const long long vol = (long long)g * 32 + lane;
     if (vol >= n_vols) return;
     const int cnt = counts[r];
@@ -578,7 +588,7 @@ static int launch_pool(mmad_roi_plan* pl, const float* vols_dev, long long n_vol
         return MMAD_OK;
     }
     const int warps = b->n_groups * pl->R;
-    cfg.gridDim = dim3((warps + 3) / 4);
+    cfg.gridDim = dim3(warps);                            // one block (four warps) per (group, ROI)
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = 0;
     MMAD_CUDA(cudaLaunchKernelEx(&cfg, roi_finalize_kernel, (const double*)b->d_slot_sum,
