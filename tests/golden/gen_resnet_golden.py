@@ -47,6 +47,22 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
+    # Bottleneck network (resnet.py:72-109) and shortcut type 'A' (resnet.py:26-37): features and init checksums only
+    for name, kw, layers in (("resnet50", dict(), "resnet50"), ("resnet18a", dict(shortcut_type="A"), "resnet18")):
+        torch.manual_seed(4321)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = getattr(ref, layers)(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True, **kw)
+        init_cs = np.float64(sum(float(p.detach().double().abs().sum()) for p in m.parameters()))
+        g = torch.Generator().manual_seed(77)
+        x = torch.rand(2, 1, 16, 20, 12, generator=g)
+        m.train()
+        with torch.no_grad():
+            feats = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+        path = os.path.join(os.path.dirname(__file__), name + "_golden.npz")
+        np.savez_compressed(path, x=x.numpy(), features=feats.numpy(), init_checksum=init_cs)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -195,3 +195,20 @@ def test_shortcut_a_oracle_is_bit_exact_with_the_live_reference():
     feats = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
     out = resnet_features_oracle({k: v.detach().clone() for k, v in sr.items()}, x, [2, 2, 2, 2], True)
     assert torch.equal(feats, out)
+
+
+@pytest.mark.parametrize("name,factory,kw,layers", [("resnet50", "resnet50", {}, [3, 4, 6, 3]),
+                                                    ("resnet18a", "resnet18", {"shortcut_type": "A"}, [2, 2, 2, 2])])
+def test_bottleneck_and_shortcut_a_match_committed_fixtures(name, factory, kw, layers):
+    """Fixtures generated from the live reference (tests/golden/gen_resnet_golden.py): Bottleneck blocks and shortcut 'A' stay
+    pinned on boxes where /root/reference is not mounted - same initialisation, same forward."""
+    from multimodal_ad_b200.models import resnet
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", name + "_golden.npz"))
+    torch.manual_seed(4321)
+    m = getattr(resnet, factory)(sample_input_D=16, sample_input_H=16, sample_input_W=16, num_seg_classes=1, no_cuda=True, **kw)
+    cs = sum(float(p.detach().double().abs().sum()) for p in m.parameters())
+    assert abs(cs - float(gold["init_checksum"])) < 1e-6 * cs
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    feats = resnet_features_oracle(sd, torch.from_numpy(gold["x"]), layers, True)
+    assert torch.allclose(feats, torch.from_numpy(gold["features"]), rtol=1e-5, atol=1e-6)
