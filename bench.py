@@ -256,6 +256,119 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
     return res
 
 
+def resnet_conv_flops_model(model, batch, size):
+    """Algorithmic conv FLOPs of one training step of any models/resnet.py network on 1 x size^3 volumes: forward + wgrad for
+    every convolution, + dgrad for all but the stem (walks the module tree, resnet.py:126-143)."""
+    def out(n, k, s, p, d):
+        return (n + 2 * p - d * (k - 1) - 1) // s + 1
+    sp = out(out(size, 7, 2, 3, 1), 3, 2, 1, 1)                      # after conv1 and the max-pool
+    total = 2 * 2.0 * batch * out(size, 7, 2, 3, 1) ** 3 * 64 * 343
+    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+        for blk in layer:
+            cur = sp
+            for name in ("conv1", "conv2", "conv3"):
+                conv = getattr(blk, name, None)
+                if conv is None:
+                    continue
+                k, st, dil, pad = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+                cur = out(cur, k, st, pad, dil)
+                total += 3 * 2.0 * batch * cur ** 3 * conv.out_channels * conv.in_channels * k ** 3
+            ds = blk.downsample
+            if ds is not None and not callable(getattr(ds, "func", None)):
+                total += 3 * 2.0 * batch * cur ** 3 * ds[0].out_channels * ds[0].in_channels
+            sp = cur
+    return total
+
+
+def run_resnet50_train(args, rank, local_rank, world, dev, dist):
+    """BASELINE.json configs[3] as the reference can actually run it: config/cfg_denseNet.json selects model_type "resnet",
+    depth 50 (models/denseNet.py is a 2-D network and train_denseNet.py is empty) - Bottleneck ResNet3D-50, bf16, batch 8 per
+    GPU, synthetic 1x128^3 volumes, data parallel."""
+    import torch
+    import torch.nn as nn
+
+    from multimodal_ad_b200.models.Resnet3D import generate_model
+    from multimodal_ad_b200.sharding import GradReducer, max_over_ranks
+
+    batch, size = 8, 128
+    torch.manual_seed(0)
+    model = generate_model(model_depth=50, input_W=size, input_H=size, input_D=size, nb_class=2, pretrain_path=None,
+                           dropout_rate=0.5, device=dev)
+    model.train()
+    reducer = GradReducer()
+    model.grad_reducer = reducer
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True, capturable=True)
+    crit = nn.CrossEntropyLoss()
+    g = torch.Generator(device=dev).manual_seed(200 + rank)
+    x = torch.rand((batch, 1, size, size, size), device=dev, generator=g)
+    y = torch.randint(0, 2, (batch,), device=dev, generator=g)
+
+    def step():
+        loss = crit(model(x), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer.finish(model.parameters())
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return loss
+
+    steps = max(1, min(args.steps, 8))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    launch = "eager"
+    if world == 1 and not getattr(args, "no_graph", False):            # same single-GPU graph replay as the headline model
+        try:
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gloss = crit(model(x), y)
+                gloss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+                opt.step()
+            graph.replay()
+            torch.cuda.synchronize()
+
+            def step():                                                # noqa: F811
+                graph.replay()
+                return gloss
+            launch = "cuda graph replay"
+        except Exception as e:                                         # noqa: BLE001
+            launch = f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b), dev) / steps
+    flops = resnet_conv_flops_model(model.module if hasattr(model, "module") else model, batch, size)
+    peaks = {}
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peaks = json.load(f)
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = flops / (ms * 1e-3) / 1e12
+    res = {"metric": "resnet3d50_train_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms,
+           "steps": steps, "dtype": "bf16", "scaling": "weak",
+           "config": {"workload": "resnet3d50_bottleneck_bf16_train_batch8_1x128^3 (cfg_denseNet.json: model_type resnet, depth 50)",
+                      "batch_per_gpu": batch, "parallelism": f"data parallel x{world}", "launch": launch},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "algorithmic_flops_per_step": flops},
+           "loss": float(loss.detach())}
+    del model, opt, x
+    torch.cuda.empty_cache()
+    return res
+
+
 def resnet_cpu_baseline(seconds_cap=60.0):
     """BASELINE.json configs[0]: the reference's PyTorch CPU path - ResNet3D-18 forward+backward, batch 2, 1x91x109x91, fp32
     (oracle/resnet_oracle.py restates resnet.py and is pinned bit-exact against it)."""
@@ -438,9 +551,10 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
                         "sample": f"{n} single-volume passes (~10 s) of the reference torch expression "
                                   "(image_features.py:80-82,111-114) on the host cores"}
 
-    resnet = None
+    resnet = resnet50 = None
     if not args.no_resnet:
         resnet = run_resnet_train(args, rank, local_rank, world, dev, dist)
+        resnet50 = run_resnet50_train(args, rank, local_rank, world, dev, dist)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             resnet["cpu_baseline"] = resnet_cpu_baseline()
 
@@ -460,6 +574,7 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
             "gpu_launches": launches,
             "clocks": clocks,
             "resnet3d18_train": resnet,
+            "resnet3d50_train": resnet50,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
