@@ -89,6 +89,21 @@ int mmad_roi_pool_host_f32(mmad_roi_plan* plan, const float* vols_host, int64_t 
 int mmad_roi_pool_mean_backward_f32(mmad_roi_plan* plan, const float* grad_mean_dev,
                                     int64_t n_vols, float* grad_vols_dev, void* stream);
 
+/* Tuning / introspection entry points of the plan (the Python host code and the CPU test-suite use them).
+ * mmad_roi_plan_create_ex: as mmad_roi_plan_create with an explicit tile (128/256/512 voxels), ring depth (0 = as many
+ * stages as fit, <= 4), consumer warps (0 = 16; 8 or 16) and host_only != 0 to build the run programme without touching
+ * a GPU.  mmad_roi_plan_programme copies the run programme (any pointer may be NULL; sizes come back through n_words /
+ * n_tiles): words = per tile a 4-word header {records, 0, 0, 0} + records `label<<24 | start<<12 | len-1`, offs =
+ * n_tiles+1 offsets in 16-byte units.  mmad_roi_plan_binding returns the work-item / partial-slot layout the plan uses
+ * for n_vols volumes on a GPU with `sms` SMs (host arithmetic only; arrays may be NULL to query the sizes first). */
+int mmad_roi_plan_create_ex(const int32_t* labels_host, int64_t n_voxels, int32_t n_rois, int32_t tile,
+                            int32_t stages, int32_t consumer_warps, int32_t host_only, mmad_roi_plan** plan_out);
+int mmad_roi_plan_programme(const mmad_roi_plan* plan, uint32_t* words, int64_t* n_words, int32_t* offs,
+                            int32_t* n_tiles, int32_t* stages, int64_t* smem_bytes, int32_t* consumer_warps);
+int mmad_roi_plan_binding(mmad_roi_plan* plan, int64_t n_vols, int32_t sms, int32_t* n_items, int32_t* n_slots,
+                          int32_t* grid, int32_t* item_group, int32_t* item_t0, int32_t* item_t1,
+                          int32_t* item_slot_ptr, uint8_t* slot_label, int32_t* slot_dst, int32_t* fin_ptr);
+
 /* Algorithmic HBM bytes one mmad_roi_pool_f32 launch over n_vols volumes must
  * move (volume bytes + run programme + outputs); bench.py's roofline uses it. */
 int64_t mmad_roi_pool_algorithmic_bytes(const mmad_roi_plan* plan, int64_t n_vols);
@@ -142,15 +157,6 @@ int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad,
 int mmad_conv3d_prep_weights_s2(const float* w, void* w_phases, int Cdy, int Cdx, void* stream);
 int mmad_conv3d_dgrad_s2_bf16(const void* dy, const void* w_phases, void* dx,
                               int N, int D, int H, int W, int Cdx, int Cdy, void* stream);
-
-/* Stem (resnet.py:126-132: Conv3d(1, 64, 7, stride 2, pad 3)) as im2col + GEMM:
- * x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, column (kd*k+kh)*k+kw,
- * zero padded to Kpad (384); the GEMM is mmad_conv3d_fwd_bf16 with k = 1 on the
- * (1,1,1,rows,Kpad) view, its wgrad mmad_conv3d_wgrad_bf16 on the same view. */
-int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W,
-                     int k, int stride, int pad, int Kpad, void* stream);
-int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream);
-int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream);
 
 /* Stem without a materialised im2col matrix (the path the model uses).  The
  * stride-2 7^3 convolution of one channel is rewritten as a stride-1 4^3

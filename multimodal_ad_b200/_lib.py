@@ -27,10 +27,13 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
-        _build.build()
+    try:
+        _build.build()                                     # digest check; recompiles only when csrc/ or include/ changed
+    except RuntimeError:
+        if not os.path.exists(_LIB_PATH):                  # no nvcc on this box and nothing prebuilt
+            raise
     if not os.path.exists(_LIB_PATH):
         raise MmadError(f"CUDA library not found at {_LIB_PATH}; run python -m multimodal_ad_b200.build")
     lib = ctypes.CDLL(_LIB_PATH)
@@ -67,9 +70,6 @@ def load() -> ctypes.CDLL:
         "mmad_conv3d_prep_weights": [P, P, P, I, I, I, P],
         "mmad_conv3d_prep_weights_s2": [P, P, I, I, P],
         "mmad_conv3d_dgrad_s2_bf16": [P, P, P, I, I, I, I, I, I, P],
-        "mmad_stem_im2col": [P, P] + [I] * 8 + [P],
-        "mmad_stem_prep_weights": [P, P, I, I, I, P],
-        "mmad_stem_unpad_wgrad": [P, P, I, I, I, P],
         "mmad_stem_s2d_elems": [I, I, I, I],
         "mmad_stem_s2d_pack": [P, P, I, I, I, I, P],
         "mmad_stem_s2d_prep_weights": [P, P, P],

@@ -33,6 +33,31 @@ inline int fail(int code, const std::string& msg) {
         if (!(cond)) return ::mmad::fail(MMAD_EINVAL, std::string(msg));             \
     } while (0)
 
+// "done once per device" flag (function attributes such as MaxDynamicSharedMemorySize are per device, not per process)
+struct DevOnce {
+    std::atomic<uint64_t> mask{0};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const uint64_t bit = 1ull << (d & 63);
+        if (mask.load(std::memory_order_relaxed) & bit) return false;
+        mask.fetch_or(bit, std::memory_order_relaxed);
+        return true;
+    }
+};
+// SM count of the current device (cached per device)
+inline int sm_count() {
+    static std::atomic<int> cache[64];
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return 148;
+    int v = cache[d & 63].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+        cache[d & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- device-side PTX wrappers (mbarrier / bulk async copy) ---------------------

@@ -727,10 +727,9 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (pairk) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
         launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);
@@ -741,10 +740,9 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
 #define MMAD_CONV_LAUNCH(...)                                                                                               \
     do {                                                                                                                    \
-        static bool attr_done = false;                                                                                      \
-        if (!attr_done) {                                                                                                   \
+        static DevOnce attr_done;                                                                                      \
+        if (attr_done.need()) {                                                                                                   \
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-            attr_done = true;                                                                                               \
         }                                                                                                                   \
         launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);               \
     } while (0)

@@ -795,10 +795,9 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
             if (rc) return rc;
         }
         const int smem = 1024 + 3 * (kHaloBoxBytes + kHaloDyBytes) + 7 * 8 + 32;
-        static bool halo_attr = false;
-        if (!halo_attr) {
+        static DevOnce halo_attr;
+        if (halo_attr.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            halo_attr = true;
         }
         launch_pdl(conv3d_wgrad_halo64_kernel, dim3(2 * g.nsplit), dim3(kWgThreads), smem, (cudaStream_t)stream, tmX, tmDY, g, partials);
         MMAD_CUDA(cudaGetLastError());
@@ -825,11 +824,10 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     const int stage = g.pairk ? (g.nb / 128 + 2 * g.nacc) * g.cv * 128 : (g.nb / 64 + 2 * g.nacc) * kBoxBytes;
     const int smem = 1024 + g.stages * stage + (2 * g.stages + 1) * 8 + 32;
     MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_wgrad: shared memory budget exceeded");
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevOnce attr_done;
+    if (attr_done.need()) {
         MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MMAD_CUDA(cudaFuncSetAttribute(conv3d_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     const int grid = g.n_tiles * g.ugroups * g.nsplit;
     if (g.pairk) launch_pdl(conv3d_wgrad_pair_kernel, dim3(2 * grid), dim3(kWgThreads), smem, (cudaStream_t)stream, tmX, tmDY, g, partials);

@@ -1,4 +1,4 @@
-// Bandwidth-bound companions of the Conv3d implicit GEMM (sm_100a): weight re-layout, stem im2col, BatchNorm3d
+// Bandwidth-bound companions of the Conv3d implicit GEMM (sm_100a): weight re-layout, BatchNorm3d
 // statistics / apply / backward, ReLU, residual add, MaxPool3d, zero-insertion upsampling, layout conversion.
 // Replaces nn.BatchNorm3d / nn.ReLU / nn.MaxPool3d / `out += residual` of /root/reference/models/resnet.py:46-69,
 // :134-136, :204-213 (forward and backward).  All activations are NDHWC bf16 with C % 8 == 0; every kernel moves
@@ -67,7 +67,6 @@ __global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bflo
         if (co < Cout && ci < Cin) wt[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = tile[tx][j];
     }
 }
-// stem weights (Cout, 1, 7,7,7) fp32 -> [Cout][Kpad] bf16 (a 1x1x1 conv over the im2col matrix), zero padded
 // ---- weights of the phase convolutions of mmad_conv3d_dgrad_s2_bf16: torch (Cdy, Cdx, 3,3,3) fp32 -> for phase p = pd*4+ph*2+pw
 //      a block [Cdx][taps_p][Cdy] bf16, tap (a, b, c) of the phase = original tap t with t = 1 on an even axis, t = 2 - 2*a on an
 //      odd one (dx[2j+1] = dy[j] w[2] + dy[j+1] w[0]).  Blocks are concatenated in phase order.
@@ -93,77 +92,6 @@ __global__ void __launch_bounds__(256) prep_weights_s2_kernel(const float* __res
         const int c = tap % kwp, b = (tap / kwp) % khp, a = tap / (kwp * khp);
         const int td = pd ? 2 - 2 * a : 1, th = ph ? 2 - 2 * b : 1, tw = pw ? 2 - 2 * c : 1;
         wp[i] = __float2bfloat16(w[((size_t)cdy * Cdx + cdx) * 27 + (td * 3 + th) * 3 + tw]);
-    }
-}
-
-__global__ void prep_stem_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cout, int K, int Kpad) {
-    pdl_launch_dependents();
-    pdl_wait();                                        // see launch_pdl (common.cuh)
-    const int total = Cout * Kpad;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int k = i % Kpad, co = i / Kpad;
-        wf[i] = __float2bfloat16_rn(k < K ? w[co * K + k] : 0.f);
-    }
-}
-// dW of the stem: [Cout][1][Kpad] fp32 (wgrad output layout with taps = 1, Cin = Kpad) -> (Cout, 1, 7,7,7) fp32
-__global__ void unpad_stem_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int K, int Kpad) {
-    pdl_launch_dependents();
-    pdl_wait();                                        // see launch_pdl (common.cuh)
-    const int total = Cout * K;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dw[i] = dwp[(i / K) * Kpad + (i % K)];
-}
-
-// ---- stem im2col: x (N,1,D,H,W) fp32 -> col [N*Do*Ho*Wo][Kpad] bf16, column = (kd*K+kh)*K+kw, zero padded to Kpad.
-//      A block produces a strip of 32 consecutive output voxels along W: the K*K input row segments the strip touches
-//      are staged once in shared memory (coalesced, zero filled outside the volume), then every thread assembles
-//      16-byte chunks (8 columns) of the strip's rows from shared memory; rows are written as contiguous 768-byte lines.
-template <int K>
-__global__ void __launch_bounds__(192) im2col_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int D,
-                                                          int H, int W, int Do, int Ho, int Wo, int stride, int pad, int Kpad) {
-    pdl_launch_dependents();
-    pdl_wait();                                        // see launch_pdl (common.cuh)
-    constexpr int STRIP = 32;
-    extern __shared__ float seg[];                    // [K*K][segw] + one zero word for the padding columns
-    const int segw = (STRIP - 1) * stride + K;
-    const int strips = (Wo + STRIP - 1) / STRIP;
-    int b = blockIdx.x;
-    const int sw = b % strips; b /= strips;
-    const int oh = b % Ho; b /= Ho;
-    const int od = b % Do; b /= Do;
-    const int n = b;
-    const int ow0 = sw * STRIP;
-    const int iw0 = ow0 * stride - pad, ih0 = oh * stride - pad, id0 = od * stride - pad;
-    const float* xn = x + (long long)n * D * H * W;
-    const int nseg = K * K * segw;
-    for (int r = threadIdx.x / 32; r < K * K; r += 6) {          // one warp per (kd,kh) row segment: coalesced reads
-        const int id = id0 + r / K, ih = ih0 + r % K;
-        const bool rowok = (unsigned)id < (unsigned)D && (unsigned)ih < (unsigned)H;
-        const float* src = xn + ((long long)id * H + ih) * W;
-        for (int c = threadIdx.x & 31; c < segw; c += 32) {
-            const int iw = iw0 + c;
-            seg[r * segw + c] = (rowok && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
-        }
-    }
-    if (threadIdx.x == 0) seg[nseg] = 0.f;
-    // this thread's chunk (8 columns) and their shared-memory offsets, fixed for the whole strip
-    const int cpr = Kpad >> 3;                        // 48 chunks per row, 192 threads = 4 rows at a time
-    const int chunk = threadIdx.x % cpr, rsub = threadIdx.x / cpr, rstep = 192 / cpr;
-    int off[8], mul[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = chunk * 8 + j;
-        const bool real = c < K * K * K;
-        off[j] = real ? (c / K) * segw + c % K : nseg;           // c / K == kd*K + kh
-        mul[j] = real ? stride : 0;
-    }
-    __syncthreads();
-    const int nrows = min(STRIP, Wo - ow0);
-    __nv_bfloat16* dst = col + ((((long long)n * Do + od) * Ho + oh) * Wo + ow0) * Kpad + chunk * 8;
-    for (int r = rsub; r < nrows; r += rstep) {
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = seg[off[j] + r * mul[j]];
-        *reinterpret_cast<uint4*>(dst + (long long)r * Kpad) = pack8(f);
     }
 }
 
@@ -957,29 +885,6 @@ int mmad_conv3d_prep_weights_s2(const float* w, void* w_phases, int Cdy, int Cdx
     launch_pdl(prep_weights_s2_kernel, dim3(grid_for(27ll * Cdx * Cdy, 256, 1184)), dim3(256), 0, ST, w, (__nv_bfloat16*)w_phases, Cdy, Cdx);
     LAUNCH_OK();
 }
-int mmad_stem_prep_weights(const float* w, void* w_fwd, int Cout, int K, int Kpad, void* stream) {
-    MMAD_CHECK_ARG(w && w_fwd && K <= Kpad && Kpad % 64 == 0, "stem_prep_weights: bad argument");
-    launch_pdl(prep_stem_weights_kernel, dim3(grid_for((long long)Cout * Kpad, 256, 1024)), dim3(256), 0, ST, w, (__nv_bfloat16*)w_fwd, Cout, K, Kpad);
-    LAUNCH_OK();
-}
-int mmad_stem_unpad_wgrad(const float* dw_padded, float* dw, int Cout, int K, int Kpad, void* stream) {
-    MMAD_CHECK_ARG(dw_padded && dw, "stem_unpad_wgrad: null pointer");
-    launch_pdl(unpad_stem_wgrad_kernel, dim3(grid_for((long long)Cout * K, 256, 1024)), dim3(256), 0, ST, dw_padded, dw, Cout, K, Kpad);
-    LAUNCH_OK();
-}
-int mmad_stem_im2col(const float* x, void* col, int N, int D, int H, int W, int k, int stride, int pad, int Kpad, void* stream) {
-    MMAD_CHECK_ARG(x && col && Kpad % 8 == 0 && k * k * k <= Kpad, "stem_im2col: bad argument");
-    const int Do = (D + 2 * pad - k) / stride + 1, Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    MMAD_CHECK_ARG(k == 7 || k == 3, "stem_im2col: kernel size 7 (resnet.py:126-132) or 3 supported");
-    const long long blocks = (long long)N * Do * Ho * ((Wo + 31) / 32);
-    MMAD_CHECK_ARG(blocks < (1ll << 31), "stem_im2col: too many output strips");
-    const int segw = 31 * stride + k;
-    MMAD_CHECK_ARG(192 % (Kpad / 8) == 0, "stem_im2col: Kpad / 8 must divide 192 (Kpad = 384)");
-    const size_t smem = ((size_t)k * k * segw + 1) * sizeof(float);
-    if (k == 7) launch_pdl(im2col_stem_kernel<7>, dim3((unsigned)blocks), dim3(192), smem, ST, x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
-    else launch_pdl(im2col_stem_kernel<3>, dim3((unsigned)blocks), dim3(192), smem, ST, x, (__nv_bfloat16*)col, N, D, H, W, Do, Ho, Wo, stride, pad, Kpad);
-    LAUNCH_OK();
-}
 int mmad_bn_finalize(const float* partials, int nparts, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
                      float* shift, void* stream) {
@@ -998,13 +903,13 @@ int mmad_bn_apply(const void* x, const float* scale, const float* shift, const v
                   int relu, void* out_bf16, float* out_f32, int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    const int grid = grid_for_channels(nvec, C / 8, 148 * 8);
+    const int grid = grid_for_channels(nvec, C / 8, sm_count() * 8);
     if (relu) launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
     else launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
     LAUNCH_OK();
 }
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
-int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, 148)); }
+int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, sm_count())); }
 int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2, const void* mask, const void* x, const float* mean,
                        const float* invstd, const float* mask_scale, const float* mask_shift, void* g_out, float* partials, int64_t rows,
                        int C, void* stream) {
@@ -1015,10 +920,9 @@ int mmad_bn_bwd_reduce(const void* dy_bf16, const float* dy_f32, const void* dy2
     if (tma_mode < 0) { const char* e = getenv("MMAD_BN_TMA"); tma_mode = e ? atoi(e) : 1; }
     if (dy_bf16 && tma_mode) {
         const int smem = kBnStages * 4 * kBnTileVec * 16 + 2 * kBnStages * 8;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_done = true;
         }
         launch_pdl(bn_bwd_reduce_tma_kernel, dim3(grid), dim3(kBnConsumers + 32), smem, ST, (const uint4*)dy_bf16, (const uint4*)dy2, (const uint4*)mask,
                                                                          (const uint4*)x, mean, invstd, mask_scale, mask_shift,
@@ -1039,14 +943,14 @@ int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
 int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(g && x && coef && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
     const long long nvec = rows * (C / 8);
-    launch_pdl(bn_bwd_apply_kernel, dim3(grid_for_channels(nvec, C / 8, 148 * 8)), dim3(256), 0, ST, (const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
+    launch_pdl(bn_bwd_apply_kernel, dim3(grid_for_channels(nvec, C / 8, sm_count() * 8)), dim3(256), 0, ST, (const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {
     MMAD_CHECK_ARG(x && y && idx && C % 8 == 0, "maxpool3d_fwd: bad argument");
     const int Do = (D - 1) / 2 + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     const long long total = (long long)N * Do * Ho * Wo * (C / 8);
-    launch_pdl(maxpool3d_fwd_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, (uint2*)idx, N, D, H, W, C, Do, Ho, Wo);
+    launch_pdl(maxpool3d_fwd_kernel, dim3(grid_for(total, 256, sm_count() * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, (uint2*)idx, N, D, H, W, C, Do, Ho, Wo);
     LAUNCH_OK();
 }
 int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream) {
@@ -1062,10 +966,9 @@ int mmad_maxpool3d_bwd(const void* dy, const void* idx, void* dx, int N, int D, 
     const long long slot = 3ll * Wo * cv * 24;
     if (march_mode && 512 % cv == 0 && kPoolSlots * slot + 64 <= 72 * 1024 && D >= 4) {
         const int smem = (int)(kPoolSlots * slot) + 64;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(maxpool3d_bwd_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-            attr_done = true;
         }
         const int hgroups = (H + 3) / 4;
         int dsplit = 1;                                // enough blocks for ~3 per SM
@@ -1091,26 +994,25 @@ int mmad_stem_bn_relu_maxpool_fwd(const void* c, const float* scale, const float
     const long long slot = 5ll * W * cv * 16;
     if (march_mode && 512 % cv == 0 && kSpSlots * slot + 64 <= 220 * 1024 && Do >= 2) {
         const int smem = (int)(kSpSlots * slot) + 64;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DevOnce attr_done;
+        if (attr_done.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(stem_pool_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            attr_done = true;
         }
         const int hgroups = (Ho + 1) / 2;
         int dsplit = 1;                                // several blocks per SM over the run, at least 4 pooled slices each
-        while ((long long)N * hgroups * dsplit < 148 * 6 && Do / (dsplit * 2) >= 4) dsplit *= 2;
+        while ((long long)N * hgroups * dsplit < sm_count() * 6 && Do / (dsplit * 2) >= 4) dsplit *= 2;
         launch_pdl(stem_pool_march_kernel, dim3((unsigned)(N * hgroups * dsplit)), dim3(512), smem, ST, (const uint4*)c, scale, shift, (uint4*)y,
                    (uint2*)idx, N, D, H, W, C, Do, Ho, Wo, dsplit);
         LAUNCH_OK();
     }
-    launch_pdl(stem_bn_relu_maxpool_fwd_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
+    launch_pdl(stem_bn_relu_maxpool_fwd_kernel, dim3(grid_for(total, 256, sm_count() * 16)), dim3(256), 0, ST, (const uint4*)c, scale, shift, (uint4*)y, (uint2*)idx, N, D, H,
                                                                                     W, C, Do, Ho, Wo);
     LAUNCH_OK();
 }
 int mmad_upsample_zero2(const void* x, void* y, int N, int Dx, int Hx, int Wx, int Dy, int Hy, int Wy, int C, void* stream) {
     MMAD_CHECK_ARG(x && y && C % 8 == 0, "upsample_zero2: bad argument");
     const long long total = (long long)N * Dy * Hy * Wy * (C / 8);
-    launch_pdl(upsample_zero2_kernel, dim3(grid_for(total, 256, 148 * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, N, Dx, Hx, Wx, Dy, Hy, Wy, C);
+    launch_pdl(upsample_zero2_kernel, dim3(grid_for(total, 256, sm_count() * 16)), dim3(256), 0, ST, (const uint4*)x, (uint4*)y, N, Dx, Hx, Wx, Dy, Hy, Wy, C);
     LAUNCH_OK();
 }
 int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, void* stream) {

@@ -392,12 +392,6 @@ static int stem_input_map(CUtensorMap* tm, const void* xs, const StemGeom& g) {
     return make_tmap_bf16_swz(tm, xs, 5, dims, str, box, es, 64);
 }
 
-static int sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-}
-
 }  // namespace mmad
 
 using namespace mmad;
@@ -419,7 +413,7 @@ int mmad_stem_s2d_pack(const float* x, void* xs, int N, int D, int H, int W, voi
     StemGeom g;
     MMAD_CHECK_ARG(stem_geom(g, N, D, H, W) == 0, "stem_s2d_pack: volume too large");
     const long long total = (long long)N * g.Ds * g.Hs * g.Ws;
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32);
     launch_pdl(stem_s2d_pack_kernel, dim3(grid), dim3(256), 0, ST, x, (uint4*)xs, g);
     LAUNCH_OK();
 }
@@ -461,10 +455,9 @@ int mmad_stem_s2d_fwd(const void* xs, const void* wk, void* y, float* stats_part
         if (rc) return rc;
     }
     const int smem = 1024 + kStemBBytes + 2 * kStemABox + kStemOutBytes + 9 * 8 + 16 + 256 * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevOnce attr_done;
+    if (attr_done.need()) {
         MMAD_CUDA(cudaFuncSetAttribute(stem_conv_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     const int grid = std::min(g.m_tiles, sm_count());
     launch_pdl(stem_conv_s2d_kernel, dim3(grid), dim3(kStemThreads), smem, ST, tmA, tmB, tmC, g, stats_partials);
@@ -496,10 +489,9 @@ int mmad_stem_s2d_wgrad(const void* xs, const void* dy, float* partials, int N, 
         if (rc) return rc;
     }
     const int smem = 1024 + 3 * (kStemABox + kStemDyBox) + 7 * 8 + 32;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevOnce attr_done;
+    if (attr_done.need()) {
         MMAD_CUDA(cudaFuncSetAttribute(stem_wgrad_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
     }
     const int grid = std::min(g.m_tiles, sm_count());
     launch_pdl(stem_wgrad_s2d_kernel, dim3(grid), dim3(kStemThreads), smem, ST, tmA, tmDY, g, partials);

@@ -9,8 +9,8 @@ tcgen05/TMEM (csrc/conv3d_igemm.cu, csrc/conv3d_wgrad.cu) and the bandwidth kern
 torch module applied to the backbone's output.
 
 The nn.Conv3d / nn.BatchNorm3d objects are parameter containers only: their own forward is never called.  Activations
-live as NDHWC bf16 between kernels; convolutions accumulate in fp32.  There is no CPU / cuDNN fallback: a CPU tensor, a
-non-BasicBlock network or shortcut type 'A' raises.
+live as NDHWC bf16 between kernels; convolutions accumulate in fp32.  There is no CPU / cuDNN fallback: a CPU tensor raises.
+BasicBlock and Bottleneck networks, shortcut types 'A' (detached, as in the reference) and 'B' are covered.
 """
 from __future__ import annotations
 
@@ -25,8 +25,6 @@ import torch.nn.functional as F
 from .. import _lib
 
 __all__ = ['ResNet', 'resnet10', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152', 'resnet200']
-
-STEM_KPAD = 384      # 7*7*7 = 343 im2col columns, zero padded to a multiple of 64
 
 
 def conv3x3x3(in_planes, out_planes, stride=1, dilation=1):
@@ -241,7 +239,10 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     k, s, p = 7, 2, 3
     do, ho, wo = (d + 2 * p - k) // s + 1, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     rows = n * do * ho * wo
-    xs = r.empty((lib.mmad_stem_s2d_elems(n, d, h, w),))
+    xs_elems = lib.mmad_stem_s2d_elems(n, d, h, w)
+    if xs_elems <= 0:
+        raise _lib.MmadError(f"mmad_stem_s2d_elems: unsupported input geometry {(n, d, h, w)}")
+    xs = r.empty((xs_elems,))
     r.chk(lib.mmad_stem_s2d_pack(_p(x), _p(xs), n, d, h, w, r.stream), "mmad_stem_s2d_pack")
     wstem = r.empty((64, 512))
     r.chk(lib.mmad_stem_s2d_prep_weights(_p(model.conv1.weight.detach()), _p(wstem), r.stream), "mmad_stem_s2d_prep_weights")
@@ -323,11 +324,17 @@ class _GradDict(dict):
     """{parameter: gradient}; hands each gradient to the model's GradReducer (if any) the moment it is enqueued, so
     the data-parallel all-reduce overlaps the rest of the backward pass."""
 
-    def __init__(self, reducer):
+    def __init__(self, reducer, wanted=None):
         super().__init__()
         self.reducer = reducer
+        self._wanted = wanted                              # ids of the parameters that require a gradient (None: all)
+
+    def wanted(self, param) -> bool:
+        return self._wanted is None or id(param) in self._wanted
 
     def __setitem__(self, k, v):
+        if not self.wanted(k):
+            return                                         # frozen parameter: no .grad, no all-reduce
         super().__setitem__(k, v)
         if self.reducer is not None:
             self.reducer.push(v)
@@ -344,12 +351,12 @@ class _GradDict(dict):
         return self.reducer.alloc_like(param) if self.reducer is not None else torch.empty_like(param)
 
 
-def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False):
+def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input_grad=False, wanted=None):
     """grad_out: gradient w.r.t. the (N,C,D',H',W')-shaped output view.  Returns {parameter: gradient}."""
     r = _Run(grad_out.device, use_side_stream=getattr(model, "wgrad_side_stream", True))
     lib = r.lib
     training = tape["training"]
-    grads = _GradDict(getattr(model, "grad_reducer", None))
+    grads = _GradDict(getattr(model, "grad_reducer", None), wanted)
     last = tape["blocks"][-1]
     n, do, ho, wo, c = last["out"].shape
     # gradient of the NDHWC fp32 output; accept either memory order of the NCDHW-shaped gradient
@@ -362,6 +369,15 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         r.chk(lib.mmad_ncs_f32_to_nsc_bf16(_p(src), _p(dy), n, c, do * ho * wo, r.stream), "mmad_ncs_f32_to_nsc_bf16")
         dy_f32 = False
     dy2 = None
+
+    def wgrad_of(weight, x, dyc, cout, k, st, pad, dil):
+        """weight gradient of one convolution, skipped (no kernels, no all-reduce bucket space) for a frozen parameter"""
+        if not grads.wanted(weight):
+            return
+        gw = grads.new_grad(weight)
+        r.wgrad(x, dyc, cout, k, st, pad, dil, gw, grads.pusher(gw))
+        grads.set_quiet(weight, gw)
+
     def dgrad_3x3(dc, weight_t, conv, xin_shape, cin, cout, st, dil):
         """data gradient of a 3x3x3 convolution `conv` (cin -> cout): dc (N,Do,Ho,Wo,cout) -> (N,D,H,W,cin)"""
         if st == 1:
@@ -392,21 +408,15 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dc3, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c3"], rec["v3"], blk.bn3.weight.detach(), training, dy_is_f32=dy_f32)
             dy_f32 = False
             grads[blk.bn3.weight], grads[blk.bn3.bias] = dg, db
-            gw = grads.new_grad(blk.conv3.weight)
-            r.wgrad(rec["a2"], dc3, outc, 1, 1, 0, 1, gw, grads.pusher(gw))
-            grads.set_quiet(blk.conv3.weight, gw)
+            wgrad_of(blk.conv3.weight, rec["a2"], dc3, outc, 1, 1, 0, 1)
             da2, _ = r.conv(dc3, rec["w3t"], planes, 1, 1, 0, 1, False)
             dc2, _, dg, db = r.bn_bwd(da2, None, rec["a2"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, want_g=True)
             grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
-            gw = grads.new_grad(blk.conv2.weight)
-            r.wgrad(rec["a1"], dc2, planes, 3, st, dil, dil, gw, grads.pusher(gw))
-            grads.set_quiet(blk.conv2.weight, gw)
+            wgrad_of(blk.conv2.weight, rec["a1"], dc2, planes, 3, st, dil, dil)
             da1 = dgrad_3x3(dc2, rec["w2t"], blk.conv2, rec["a1"].shape, planes, planes, st, dil)
             dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
             grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
-            gw = grads.new_grad(blk.conv1.weight)
-            r.wgrad(xin, dc1, planes, 1, 1, 0, 1, gw, grads.pusher(gw))
-            grads.set_quiet(blk.conv1.weight, gw)
+            wgrad_of(blk.conv1.weight, xin, dc1, planes, 1, 1, 0, 1)
             dx1, _ = r.conv(dc1, rec["w1t"], inpl, 1, 1, 0, 1, False)
             planes = outc                                  # width of the residual branch below
         else:
@@ -414,23 +424,17 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dc2, g2, dg, db = r.bn_bwd(dy, dy2, rec["out"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, dy_is_f32=dy_f32)
             dy_f32 = False
             grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
-            gw = grads.new_grad(blk.conv2.weight)
-            r.wgrad(rec["a1"], dc2, planes, 3, 1, dil, dil, gw, grads.pusher(gw))
-            grads.set_quiet(blk.conv2.weight, gw)
+            wgrad_of(blk.conv2.weight, rec["a1"], dc2, planes, 3, 1, dil, dil)
             da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
             dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
             grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
-            gw = grads.new_grad(blk.conv1.weight)
-            r.wgrad(rec["xin"], dc1, planes, 3, st, dil, dil, gw, grads.pusher(gw))
-            grads.set_quiet(blk.conv1.weight, gw)
+            wgrad_of(blk.conv1.weight, rec["xin"], dc1, planes, 3, st, dil, dil)
             dx1 = dgrad_3x3(dc1, rec["w1t"], blk.conv1, xin.shape, inpl, planes, st, dil)      # dgrad of conv1
         if "cd" in rec:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             dcd, _, dg, db = r.bn_bwd(g2, None, None, rec["cd"], rec["vd"], dbn.weight.detach(), training, want_g=False)
             grads[dbn.weight], grads[dbn.bias] = dg, db
-            gw = grads.new_grad(dconv.weight)
-            r.wgrad(xin, dcd, planes, 1, dconv.stride[0], 0, 1, gw, grads.pusher(gw))
-            grads.set_quiet(dconv.weight, gw)
+            wgrad_of(dconv.weight, xin, dcd, planes, 1, dconv.stride[0], 0, 1)
             if dconv.stride[0] == 1:
                 dx2, _ = r.conv(dcd, rec["wdt"], inpl, 1, 1, 0, 1, False)
             else:
@@ -439,9 +443,9 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
                                               xin.shape[2], xin.shape[3], planes, r.stream), "mmad_upsample_zero2")
                 dx2, _ = r.conv(up, rec["wdt"], inpl, 1, 1, 0, 1, False)
         elif rec.get("short_a"):
-            dx2 = r.empty(tuple(xin.shape))                                         # shortcut 'A': the subsampled voxels / first channels
-            dx2.zero_()
-            dx2[:, ::st, ::st, ::st, :] = g2[..., : xin.shape[-1]]
+            # shortcut 'A': the reference rebuilds the shortcut from `.data` (resnet.py:35, Variable(torch.cat([out.data, ...]))),
+            # which DETACHES it - no gradient flows through the shortcut branch
+            dx2 = None
         else:
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
@@ -462,10 +466,13 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
           "mmad_maxpool3d_bwd")
     dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=True, mask_from_x=True)
     grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
-    gw = grads.new_grad(model.conv1.weight)
-    r.stem_wgrad(stem["xs"], dc0, n, d, h, w, gw)
+    gw = None
+    if grads.wanted(model.conv1.weight):
+        gw = grads.new_grad(model.conv1.weight)
+        r.stem_wgrad(stem["xs"], dc0, n, d, h, w, gw)
     r.join_side()                                          # every weight gradient is complete on the main stream from here
-    grads[model.conv1.weight] = gw
+    if gw is not None:
+        grads[model.conv1.weight] = gw
     return grads
 
 
@@ -486,7 +493,6 @@ def tape_stages(model: "ResNet", tape) -> dict:
 class _BackboneFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, model, *params):
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         feats, tape = _backbone_forward(model, x, model.training, True)
         ctx.model, ctx.tape, ctx.params = model, tape, params
         model._last_tape = tape if getattr(model, "keep_tape", False) else None
@@ -494,8 +500,15 @@ class _BackboneFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        grads = _backbone_backward(ctx.model, ctx.tape, grad_out)
-        ctx.tape = None
+        # ctx.needs_input_grad[2:] follows the parameters' requires_grad: frozen layers get no wgrad kernels, no .grad and no
+        # all-reduce (an optimizer over model.parameters() must not see - and weight-decay - a frozen tensor)
+        wanted = {id(p) for p, need in zip(ctx.params, ctx.needs_input_grad[2:]) if need}
+        if ctx.tape is None:
+            raise RuntimeError("the activation tape of this forward pass was released by the first backward; set "
+                               "model.retain_tape = True before the forward to run backward(retain_graph=True) twice")
+        grads = _backbone_backward(ctx.model, ctx.tape, grad_out, wanted=wanted)
+        if not getattr(ctx.model, "retain_tape", False):
+            ctx.tape = None                                # like autograd's saved tensors without retain_graph: freed after one use
         red = getattr(ctx.model, "grad_reducer", None)
         if red is not None and red.active:
             # Data parallel: the reducer's asynchronous all-reduces average these tensors IN PLACE after this function

@@ -183,21 +183,13 @@ def test_maxpool_forward_backward(shape, run):
     assert torch.all((dx.float() - ref).abs() <= 2 ** -7 * ref.abs() + 1e-6)      # sum of <= 8 bf16 terms, rounded once
 
 
-def test_layout_transpose_and_stem_im2col(run):
-    from multimodal_ad_b200.models.resnet import STEM_KPAD, _p
+def test_layout_transpose(run):
+    from multimodal_ad_b200.models.resnet import _p
 
     x = torch.randn((2, 70, 5 * 6 * 7), device="cuda")
     y = run.empty((2, 5 * 6 * 7, 70))
     run.chk(run.lib.mmad_ncs_f32_to_nsc_bf16(_p(x), _p(y), 2, 70, 5 * 6 * 7, run.stream), "transpose")
     assert torch.equal(y, x.permute(0, 2, 1).to(torch.bfloat16))
-    v = torch.rand((2, 1, 9, 12, 10), device="cuda")
-    do, ho, wo = [(s + 6 - 7) // 2 + 1 for s in (9, 12, 10)]
-    col = run.empty((2 * do * ho * wo, STEM_KPAD))
-    run.chk(run.lib.mmad_stem_im2col(_p(v), _p(col), 2, 9, 12, 10, 7, 2, 3, STEM_KPAD, run.stream), "im2col")
-    ref = F.unfold(F.pad(v, (3, 3, 3, 3, 3, 3)).reshape(2, 1, 15, 18 * 16), 1)  # placeholder shape use
-    unf = F.pad(v, (3, 3, 3, 3, 3, 3)).unfold(2, 7, 2).unfold(3, 7, 2).unfold(4, 7, 2)        # (2,1,do,ho,wo,7,7,7)
-    unf = unf.reshape(2 * do * ho * wo, 343).to(torch.bfloat16)
-    assert torch.equal(col[:, :343], unf) and torch.all(col[:, 343:] == 0)
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 8, 8), (1, 7, 9, 11)])

@@ -193,8 +193,17 @@ def test_shortcut_a_oracle_is_bit_exact_with_the_live_reference():
     m.train()
     x = torch.rand(2, 1, 16, 20, 12)
     feats = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
-    out = resnet_features_oracle({k: v.detach().clone() for k, v in sr.items()}, x, [2, 2, 2, 2], True)
+    leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sr.items()}
+    out = resnet_features_oracle(leaves, x, [2, 2, 2, 2], True)
     assert torch.equal(feats, out)
+    # gradients too: the reference DETACHES the type-'A' shortcut (resnet.py:35 goes through `.data`), so must the oracle
+    wgt = torch.randn_like(feats)
+    (feats * wgt).sum().backward()
+    (out * wgt).sum().backward()
+    named = dict(m.named_parameters())
+    for k, v in leaves.items():
+        if v.grad is not None and not k.startswith("conv_seg"):
+            assert torch.equal(named[k].grad, v.grad), k
 
 
 @pytest.mark.parametrize("name,factory,kw,layers", [("resnet50", "resnet50", {}, [3, 4, 6, 3]),

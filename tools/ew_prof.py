@@ -2,7 +2,7 @@
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from multimodal_ad_b200.models.resnet import _Run, _p, STEM_KPAD
+from multimodal_ad_b200.models.resnet import _Run, _p
 
 def timeit(f, reps=5):
     for _ in range(2): f()
@@ -19,9 +19,6 @@ def main():
     x = torch.rand(n, 1, s, s, s, device="cuda")
     so = 64
     rows = n * so ** 3
-    col = r.empty((rows, STEM_KPAD))
-    ms = timeit(lambda: r.chk(lib.mmad_stem_im2col(_p(x), _p(col), n, s, s, s, 7, 2, 3, STEM_KPAD, r.stream), "im2col"))
-    print(json.dumps(dict(k="im2col", ms=round(ms, 3), gbs=round(col.numel() * 2 / ms / 1e6, 1))))
     a0 = torch.randn((n, so, so, so, 64), device="cuda").to(torch.bfloat16)
     p0 = r.empty((n, 32, 32, 32, 64)); idx = torch.empty((n, 32, 32, 32, 64), dtype=torch.uint8, device="cuda")
     ms = timeit(lambda: r.chk(lib.mmad_maxpool3d_fwd(_p(a0), _p(p0), _p(idx), n, so, so, so, 64, r.stream), "mpf"))
