@@ -91,3 +91,43 @@ def test_synthetic_atlas_is_aal3_like():
     assert lab.shape == (91, 109, 91) and lab.max() == 170
     assert set(np.unique(lab)) == set(range(171)) - {35, 36, 81, 82}
     assert 0.15 < (lab > 0).mean() < 0.35
+
+
+REF_SCRIPT = "/root/reference/image_features.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SCRIPT), reason="reference not mounted on this box")
+def test_oracle_is_pinned_to_the_reference_source_text():
+    """The script cannot be imported (it runs at import, absolute paths, MONAI), so the pin works on its TEXT: lines 80-82
+    (one-hot mask) and 111-114 (masked sum / clamped count) are read from /root/reference/image_features.py, dedented and
+    exec'd on a small case; the restatement in oracle/roi_oracle.py and the numpy oracle must reproduce the result."""
+    import textwrap
+
+    import torch
+    import torch.nn.functional as F
+
+    from oracle.roi_oracle import reference_onehot_torch, reference_pool_torch
+
+    lines = open(REF_SCRIPT, encoding="utf-8").read().split("\n")
+    mask_src = textwrap.dedent("\n".join(lines[79:82]))
+    pool_src = textwrap.dedent("\n".join(lines[110:114]))
+    assert "F.one_hot" in mask_src and "permute(3,0,1,2)" in mask_src, mask_src
+    assert "feats64[:,None" in pool_src and "clamp_min(1e-6)" in pool_src and "roi_feat" in pool_src, pool_src
+    lab = synthetic_atlas((9, 11, 8), 12, seed=3, empty=(5,))
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn((2, 3, 9, 11, 8), generator=g)
+    aal_data = np.asarray(lab).astype(int)
+    roi_ids = np.unique(aal_data)
+    roi_ids = roi_ids[roi_ids > 0]                                       # image_features.py:68
+    env = {"F": F, "torch": torch, "aal_data": aal_data, "roi_ids": roi_ids}
+    exec(mask_src, env)                                                  # noqa: S102 - the reference's own lines
+    env["feats64"] = feats
+    exec(pool_src, env)                                                  # noqa: S102
+    want = env["roi_feat"]
+    assert torch.equal(env["onehot"], reference_onehot_torch(lab))
+    assert torch.equal(want, reference_pool_torch(feats, reference_onehot_torch(lab)))
+    r = int(lab.max())
+    mean, _, _, _ = roi_pool_oracle(feats.numpy().reshape(6, -1), lab, r)
+    got = mean.reshape(2, 3, r).transpose(0, 2, 1)
+    tol = mean_tolerance(feats.numpy().reshape(6, -1), lab, r).reshape(2, 3, r).transpose(0, 2, 1)
+    assert np.all(np.abs(got.astype(np.float64) - want.numpy()) <= tol + 1e-7 * np.abs(want.numpy()))
