@@ -1,12 +1,19 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native hot path.
 
-Workload (BASELINE.json configs[1]): AAL3-style ROI mean/max pooling, 170 labels,
-batch 64 of synthetic 1x91x109x91 volumes per GPU; subject-sharded (weak
-scaling, no data-path collective) across N GPUs.
+Top-level line (BASELINE.json configs[2], the metric BASELINE.json leads with): ResNet3D-18 bf16 TRAINING, batch 16 per
+GPU, synthetic 1x128^3 volumes, 3 classes, data parallel across N GPUs (gradient all-reduce overlapped with backward).
+One step = forward + CE loss + backward + gradient all-reduce + clip + Adam (train_ResNet3D.py:207-218).
+
+Nested objects on the same JSON line (each with its own roofline):
+  roi_pool                    configs[1]: AAL3-style ROI mean/max pooling, 170 labels, batch 64 x 1x91x109x91 per GPU
+  resnet3d18_train_91x109x91  the same training step on the reference's own volume (config/config_unet.json input_D/H/W)
+  resnet3d50_train            configs[3] as the reference can run it (cfg_denseNet.json: model_type resnet, depth 50)
+  unet3d_roi_extract          configs[4]'s image branch: UNet3D forward (eval) + on-device ROI pooling of the 64-channel map
+  torch_gpu_baseline          stock PyTorch / cuDNN on the same GPU for the same ResNet3D-18 step (context, not the target)
 
     python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference ...                     # reference torch-CPU expression on host cores
+    python bench.py --impl reference ...                     # the reference's PyTorch CPU path on the host cores
     torchrun ... bench.py --gpus N ...                       # N > 1, one rank per GPU
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
@@ -14,6 +21,8 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key
 from __future__ import annotations
 
 import argparse
+import csv
+import glob
 import json
 import os
 import sys
@@ -27,19 +36,60 @@ if ROOT not in sys.path:
 SHAPE = (91, 109, 91)
 N_ROIS = 170
 BATCH = 64
-WORKLOAD = "roi_pool_aal3like_170labels_batch64_1x91x109x91_f32"
-# dram__bytes_read.sum + dram__bytes_write.sum of one roi_stream_kernel launch, from the committed
-# ncu --set full capture (profiles/); None until a capture of the current kernel is committed.
-TRAFFIC_NCU = 238.5e6   # profiles/r01_roi_stream_ncu_full.csv: 231.95 MB read + 6.6 MB written per launch
+ROI_WORKLOAD = "roi_pool_aal3like_170labels_batch64_1x91x109x91_f32"
+RESNET_WORKLOAD = "resnet3d18_bf16_train_batch16_1x128^3_3class"
+RESNET_BATCH, RESNET_SIZE = 16, 128
 
 
-def measured_peaks():
+def peaks_json():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            d = json.load(f)
+            return json.load(f)
+    return {}
+
+
+def measured_peaks():
+    d = peaks_json()
+    if "hbm_gbs" in d:
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def tensor_peak():
+    d = peaks_json()
+    if "bf16_tflops_sustained" in d:
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+
+
+def roi_traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one roi_stream_kernel launch, read from the newest committed
+    `ncu --set full` summary under profiles/ (None when there is none)."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_roi_stream_ncu_full.csv"))):
+        rd = wr = None
+        with open(path) as f:
+            for row in csv.reader(l for l in f if not l.startswith("#")):
+                if len(row) >= 3 and row[0] == "dram__bytes_read.sum":
+                    rd = float(row[2]) * (1e6 if row[1] == "Mbyte" else 1.0)
+                if len(row) >= 3 and row[0] == "dram__bytes_write.sum":
+                    wr = float(row[2]) * (1e6 if row[1] == "Mbyte" else 1.0)
+        if rd is not None and wr is not None:
+            best = (rd + wr, os.path.relpath(path, ROOT))
+    return best if best else (None, None)
+
+
+def step_tensor_pipe_from_profile():
+    """Step-level sm__pipe_tensor_cycles_active (time-weighted over every launch of one training step), written by
+    tools/step_tensor_pipe.py from an ncu pass and committed under profiles/; None when absent."""
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_resnet_step_tensor_pipe.json")))
+    if not paths:
+        return None
+    with open(paths[-1]) as f:
+        d = json.load(f)
+    d["source"] = os.path.relpath(paths[-1], ROOT)
+    return d
 
 
 class ClockSampler:
@@ -100,31 +150,44 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def resnet18_conv_flops(batch, size):
-    """Algorithmic conv FLOPs of one ResNet3D-18 training step on 1 x size^3 volumes (resnet.py:126-143): forward +
-    weight gradient for every convolution, + data gradient for all but the stem (its input is data)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# ResNet3D training step (configs[2], configs[0]'s volume, configs[3])
+# ---------------------------------------------------------------------------------------------------------------------
+def resnet_conv_flops_model(model, batch, shape):
+    """Algorithmic conv FLOPs of one training step of any models/resnet.py network on 1 x D x H x W volumes: forward + wgrad
+    for every convolution, + dgrad for all but the stem (walks the module tree, resnet.py:126-143).  Counts every tap of
+    every output voxel, including the taps that fall into the zero padding (which the kernels skip)."""
     def out(n, k, s, p, d):
         return (n + 2 * p - d * (k - 1) - 1) // s + 1
-    s1 = out(size, 7, 2, 3, 1)
-    fwd = 2.0 * batch * s1 ** 3 * 64 * 343
-    total = 2 * fwd                                   # stem: forward + wgrad
-    sp = out(s1, 3, 2, 1, 1)                          # maxpool
-    cin = 64
-    for planes, stride, dil in ((64, 1, 1), (128, 2, 1), (256, 1, 2), (512, 1, 4)):
-        for b in range(2):
-            st = stride if b == 0 else 1
-            so = out(sp, 3, st, dil, dil)
-            c1 = 2.0 * batch * so ** 3 * planes * cin * 27
-            c2 = 2.0 * batch * so ** 3 * planes * planes * 27
-            total += 3 * (c1 + c2)
-            if b == 0 and (st != 1 or cin != planes):
-                total += 3 * 2.0 * batch * so ** 3 * planes * cin
-            cin, sp = planes, so
+
+    def vox(sp):
+        return sp[0] * sp[1] * sp[2]
+
+    s1 = tuple(out(n, 7, 2, 3, 1) for n in shape)
+    sp = tuple(out(n, 3, 2, 1, 1) for n in s1)                        # after conv1 and the max-pool
+    total = 2 * 2.0 * batch * vox(s1) * 64 * 343
+    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+        for blk in layer:
+            cur = sp
+            for name in ("conv1", "conv2", "conv3"):
+                conv = getattr(blk, name, None)
+                if conv is None:
+                    continue
+                k, st, dil, pad = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+                cur = tuple(out(n, k, st, pad, dil) for n in cur)
+                total += 3 * 2.0 * batch * vox(cur) * conv.out_channels * conv.in_channels * k ** 3
+            ds = blk.downsample
+            if ds is not None and not callable(getattr(ds, "func", None)):
+                total += 3 * 2.0 * batch * vox(cur) * ds[0].out_channels * ds[0].in_channels
+            sp = cur
     return total
 
 
-def run_resnet_train(args, rank, local_rank, world, dev, dist):
-    """BASELINE.json configs[2]: ResNet3D-18 bf16 training, batch 16 per GPU, synthetic 1x128^3, 3 classes, data parallel."""
+def run_resnet_train(args, rank, world, dev, dist, *, depth=18, batch=RESNET_BATCH, shape=(RESNET_SIZE,) * 3, nb_class=3,
+                     steps=20, warmup=5, workload=RESNET_WORKLOAD, metric="resnet3d18_train_volumes_per_sec", do_e2e=True,
+                     sample_clocks=False, local_rank=0):
+    """One ResNet3D training workload: `warmup` untimed steps, then exactly `steps` timed steps (CUDA events, barrier +
+    synchronize on both sides, max over ranks)."""
     import torch
     import torch.nn as nn
 
@@ -132,18 +195,17 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
     from multimodal_ad_b200.models.Resnet3D import generate_model
     from multimodal_ad_b200.sharding import GradReducer, max_over_ranks
 
-    batch, size = 16, 128
     torch.manual_seed(0)                               # same initial weights on every rank
-    model = generate_model(model_depth=18, input_W=size, input_H=size, input_D=size, nb_class=3, pretrain_path=None,
-                           dropout_rate=0.5, device=dev)
+    model = generate_model(model_depth=depth, input_W=shape[2], input_H=shape[1], input_D=shape[0], nb_class=nb_class,
+                           pretrain_path=None, dropout_rate=0.5, device=dev)
     model.train()
     reducer = GradReducer()
     model.grad_reducer = reducer
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True, capturable=True)
     crit = nn.CrossEntropyLoss()
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    xs = [torch.rand((batch, 1, size, size, size), device=dev, generator=g) for _ in range(2)]   # 2 x 134 MB
-    ys = [torch.randint(0, 3, (batch,), device=dev, generator=g) for _ in range(2)]
+    xs = [torch.rand((batch, 1) + tuple(shape), device=dev, generator=g) for _ in range(2)]   # 2 x 134 MB at 16 x 128^3
+    ys = [torch.randint(0, nb_class, (batch,), device=dev, generator=g) for _ in range(2)]
 
     def step(i, x=None, y=None):
         out = model(xs[i % 2] if x is None else x)
@@ -155,14 +217,13 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
         opt.step()
         return loss
 
-    steps = max(1, min(args.steps, 20))
-    for i in range(3):
+    for i in range(max(3, warmup)):
         step(i)
     torch.cuda.synchronize()
 
-    # Single GPU: the whole step (221 of our launches + the torch loss / clip / Adam kernels) is captured once into a CUDA
-    # graph and replayed, so the step time does not depend on the host's launch rate (eager enqueue costs 8-11 ms per
-    # step).  The eager step is kept when capture is unavailable and under data parallel (NCCL collectives stay eager).
+    # Single GPU: the whole step (our launches + the torch loss / clip / Adam kernels) is captured once into a CUDA graph
+    # and replayed, so the step time does not depend on the host's launch rate (eager enqueue costs 8-11 ms per step).
+    # The eager step is kept when capture is unavailable and under data parallel (NCCL collectives stay eager).
     graph, graph_note, graph_launches = None, "eager", 0
     if world == 1 and not getattr(args, "no_graph", False):
         try:
@@ -195,6 +256,11 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+    f0 = _lib.executed_mma_flops()
     l0 = _lib.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -204,196 +270,179 @@ def run_resnet_train(args, rank, local_rank, world, dev, dist):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
     ms = max_over_ranks(a.elapsed_time(b), dev) / steps
-    launches = graph_launches if graph is not None else (_lib.launch_count() - l0) / steps   # graph: launches captured per step
-    # end to end: pinned host batch -> device, step, loss back on the host EVERY step (float(loss) synchronises, as the
-    # reference's `loss.item()` does).  The copy of batch i+1 runs on a copy stream under step i, the way a pinned-memory
-    # prefetching loader feeds a training loop; all copies are inside the timed region.
-    xh, yh = torch.rand((batch, 1, size, size, size)).pin_memory(), torch.randint(0, 3, (batch,)).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty((batch, 1, size, size, size), device=dev), torch.empty((batch,), dtype=torch.int64, device=dev)) for _ in range(2)]
-    evs = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def fetch(j):
-        with torch.cuda.stream(copy_stream):
-            bufs[j % 2][0].copy_(xh, non_blocking=True)
-            bufs[j % 2][1].copy_(yh, non_blocking=True)
-            evs[j % 2].record(copy_stream)
-
-    torch.cuda.synchronize()
-    n_e2e = max(1, min(steps, 10))
-    t0 = time.perf_counter()
-    fetch(0)
-    for i in range(n_e2e):
-        torch.cuda.current_stream().wait_event(evs[i % 2])
-        if i + 1 < n_e2e:
-            fetch(i + 1)                               # buffer (i+1) % 2 was last read by step i-1, which has completed
-        float(step(i, bufs[i % 2][0], bufs[i % 2][1]).detach())
-    dt = max_over_ranks(time.perf_counter() - t0, dev)
-    flops = resnet18_conv_flops(batch, size)
-    peaks = {}
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            peaks = json.load(f)
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    executed = (_lib.executed_mma_flops() - f0) / steps
+    launches = graph_launches * steps if graph is not None else (_lib.launch_count() - l0)
+    flops = resnet_conv_flops_model(model, batch, shape)
+    peak, peak_src = tensor_peak()
     ach = flops / (ms * 1e-3) / 1e12
     res = {
-        "metric": "resnet3d18_train_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s",
-        "ms_per_step": ms, "steps": steps, "dtype": "bf16", "scaling": "weak",
-        "config": {"workload": "resnet3d18_bf16_train_batch16_1x128^3_3class", "batch_per_gpu": batch,
+        "metric": metric, "value": world * batch / (ms * 1e-3), "unit": "volumes/s",
+        "ms_per_step": ms, "steps": steps, "warmup": max(3, warmup), "dtype": "bf16", "scaling": "weak",
+        "config": {"workload": workload, "batch_per_gpu": batch, "volume": list(shape),
                    "parallelism": f"data parallel x{world}, gradient all-reduce overlapped with backward",
-                   "step": "forward + CE loss + backward + grad clip + Adam (train_ResNet3D.py:207-218)", "launch": graph_note},
+                   "step": "forward + CE loss + backward + grad clip + Adam (train_ResNet3D.py:207-218)", "launch": graph_note,
+                   "l2": f"2 input batches of {batch * shape[0] * shape[1] * shape[2] * 4 / 1e6:.0f} MB alternate; the step's "
+                         "activations (several GB) stream through HBM every step"},
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                     "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained",
-                     "algorithmic_flops_per_step": flops},
-        "e2e": {"value": world * batch * n_e2e / dt, "unit": "volumes/s", "h2d_bytes_per_step": batch * size ** 3 * 4 + batch * 8,
-                "d2h_bytes_per_step": 4, "steps": n_e2e},
+                     "peak_source": peak_src, "algorithmic_flops_per_step": flops,
+                     "executed_flops_per_step": executed, "executed_tflops": executed / (ms * 1e-3) / 1e12,
+                     "executed_frac": executed / (ms * 1e-3) / 1e12 / peak,
+                     "note": "algorithmic = every tap of every output voxel (zero-padding taps included); executed = 2*M*N*16 per "
+                             "tcgen05.mma actually issued (padding taps skipped, partially filled tiles counted whole)"},
         "gpu_launches": launches, "loss": float(loss.detach()),
     }
+    if clocks is not None:
+        res["clocks"] = clocks
+    if do_e2e:
+        # end to end: pinned host batch -> device, step, loss back on the host EVERY step (float(loss) synchronises, as the
+        # reference's `loss.item()` does).  The copy of batch i+1 runs on a copy stream under step i, the way a pinned-memory
+        # prefetching loader feeds a training loop; all copies are inside the timed region.
+        xh = torch.rand((batch, 1) + tuple(shape)).pin_memory()
+        yh = torch.randint(0, nb_class, (batch,)).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [(torch.empty((batch, 1) + tuple(shape), device=dev), torch.empty((batch,), dtype=torch.int64, device=dev)) for _ in range(2)]
+        evs = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def fetch(j):
+            with torch.cuda.stream(copy_stream):
+                bufs[j % 2][0].copy_(xh, non_blocking=True)
+                bufs[j % 2][1].copy_(yh, non_blocking=True)
+                evs[j % 2].record(copy_stream)
+
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n_e2e = max(1, min(steps, 10))
+        t0 = time.perf_counter()
+        fetch(0)
+        for i in range(n_e2e):
+            torch.cuda.current_stream().wait_event(evs[i % 2])
+            if i + 1 < n_e2e:
+                fetch(i + 1)                               # buffer (i+1) % 2 was last read by step i-1, which has completed
+            float(step(i, bufs[i % 2][0], bufs[i % 2][1]).detach())
+        dt = max_over_ranks(time.perf_counter() - t0, dev)
+        res["e2e"] = {"value": world * batch * n_e2e / dt, "unit": "volumes/s",
+                      "h2d_bytes_per_step": batch * shape[0] * shape[1] * shape[2] * 4 + batch * 8, "d2h_bytes_per_step": 4, "steps": n_e2e}
     del model, opt, xs
     torch.cuda.empty_cache()
     return res
 
 
-def resnet_conv_flops_model(model, batch, size):
-    """Algorithmic conv FLOPs of one training step of any models/resnet.py network on 1 x size^3 volumes: forward + wgrad for
-    every convolution, + dgrad for all but the stem (walks the module tree, resnet.py:126-143)."""
-    def out(n, k, s, p, d):
-        return (n + 2 * p - d * (k - 1) - 1) // s + 1
-    sp = out(out(size, 7, 2, 3, 1), 3, 2, 1, 1)                      # after conv1 and the max-pool
-    total = 2 * 2.0 * batch * out(size, 7, 2, 3, 1) ** 3 * 64 * 343
-    for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
+def stock_torch_forward(m, x):
+    """The reference's ResNet forward (resnet.py:54-69, 204-213) through the nn.Conv3d / BatchNorm3d / MaxPool3d modules'
+    OWN forward (stock PyTorch / cuDNN kernels) - the model object is the drop-in's parameter container, nothing of this
+    repo's CUDA library runs here.  BasicBlock networks only."""
+    x = m.maxpool(m.relu(m.bn1(m.conv1(x))))
+    for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
         for blk in layer:
-            cur = sp
-            for name in ("conv1", "conv2", "conv3"):
-                conv = getattr(blk, name, None)
-                if conv is None:
-                    continue
-                k, st, dil, pad = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
-                cur = out(cur, k, st, pad, dil)
-                total += 3 * 2.0 * batch * cur ** 3 * conv.out_channels * conv.in_channels * k ** 3
-            ds = blk.downsample
-            if ds is not None and not callable(getattr(ds, "func", None)):
-                total += 3 * 2.0 * batch * cur ** 3 * ds[0].out_channels * ds[0].in_channels
-            sp = cur
-    return total
+            res = x
+            out = blk.relu(blk.bn1(blk.conv1(x)))
+            out = blk.bn2(blk.conv2(out))
+            if blk.downsample is not None:
+                res = blk.downsample(x)
+            x = blk.relu(out + res)
+    return m.conv_seg(x)
 
 
-def run_resnet50_train(args, rank, local_rank, world, dev, dist):
-    """BASELINE.json configs[3] as the reference can actually run it: config/cfg_denseNet.json selects model_type "resnet",
-    depth 50 (models/denseNet.py is a 2-D network and train_denseNet.py is empty) - Bottleneck ResNet3D-50, bf16, batch 8 per
-    GPU, synthetic 1x128^3 volumes, data parallel."""
+def torch_gpu_baseline(dev, batch=RESNET_BATCH, size=RESNET_SIZE, steps=5):
+    """Same-box context number: the same ResNet3D-18 training step (same module tree, loss, clip, Adam) run by stock
+    PyTorch + cuDNN on this GPU, (a) fp32 with TF32 allowed, (b) bf16 autocast with channels_last_3d.  Not the target and
+    not the --impl reference arm: it tells what train_ResNet3D.py:73 (`net.to(device)`) gets for free on a B200."""
     import torch
     import torch.nn as nn
 
     from multimodal_ad_b200.models.Resnet3D import generate_model
-    from multimodal_ad_b200.sharding import GradReducer, max_over_ranks
 
-    batch, size = 8, 128
-    torch.manual_seed(0)
-    model = generate_model(model_depth=50, input_W=size, input_H=size, input_D=size, nb_class=2, pretrain_path=None,
-                           dropout_rate=0.5, device=dev)
-    model.train()
-    reducer = GradReducer()
-    model.grad_reducer = reducer
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True, capturable=True)
-    crit = nn.CrossEntropyLoss()
-    g = torch.Generator(device=dev).manual_seed(200 + rank)
-    x = torch.rand((batch, 1, size, size, size), device=dev, generator=g)
-    y = torch.randint(0, 2, (batch,), device=dev, generator=g)
-
-    def step():
-        loss = crit(model(x), y)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        reducer.finish(model.parameters())
-        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
-        opt.step()
-        return loss
-
-    steps = max(1, min(args.steps, 8))
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    launch = "eager"
-    if world == 1 and not getattr(args, "no_graph", False):            # same single-GPU graph replay as the headline model
+    out = {"workload": RESNET_WORKLOAD, "batch": batch, "steps": steps,
+           "what": "stock torch.nn modules (cuDNN) fwd + CE + bwd + clip + Adam, same module tree as the accelerated model"}
+    x = torch.rand((batch, 1, size, size, size), device=dev)
+    y = torch.randint(0, 3, (batch,), device=dev)
+    for name, autocast, cl in (("tf32", False, False), ("bf16_autocast_channels_last_3d", True, True)):
         try:
-            opt.zero_grad(set_to_none=True)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                gloss = crit(model(x), y)
-                gloss.backward()
+            torch.manual_seed(0)
+            model = generate_model(model_depth=18, input_W=size, input_H=size, input_D=size, nb_class=3, pretrain_path=None,
+                                   dropout_rate=0.5, device=dev).train()
+            if cl:
+                model = model.to(memory_format=torch.channels_last_3d)
+            opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True)
+            crit = nn.CrossEntropyLoss()
+            old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.benchmark = True
+            xin = x.contiguous(memory_format=torch.channels_last_3d) if cl else x
+
+            def step():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    loss = crit(stock_torch_forward(model, xin).float(), y)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
                 torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
                 opt.step()
-            graph.replay()
+                return loss
+
+            for _ in range(3):
+                step()
             torch.cuda.synchronize()
-
-            def step():                                                # noqa: F811
-                graph.replay()
-                return gloss
-            launch = "cuda graph replay"
-        except Exception as e:                                         # noqa: BLE001
-            launch = f"eager (graph capture failed: {type(e).__name__})"
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                step()
+            b.record()
             torch.cuda.synchronize()
-            opt.zero_grad(set_to_none=True)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        loss = step()
-    b.record()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = max_over_ranks(a.elapsed_time(b), dev) / steps
-    flops = resnet_conv_flops_model(model.module if hasattr(model, "module") else model, batch, size)
-    peaks = {}
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            peaks = json.load(f)
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    ach = flops / (ms * 1e-3) / 1e12
-    res = {"metric": "resnet3d50_train_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms,
-           "steps": steps, "dtype": "bf16", "scaling": "weak",
-           "config": {"workload": "resnet3d50_bottleneck_bf16_train_batch8_1x128^3 (cfg_denseNet.json: model_type resnet, depth 50)",
-                      "batch_per_gpu": batch, "parallelism": f"data parallel x{world}", "launch": launch},
-           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "algorithmic_flops_per_step": flops},
-           "loss": float(loss.detach())}
-    del model, opt, x
-    torch.cuda.empty_cache()
-    return res
+            ms = a.elapsed_time(b) / steps
+            out[name] = {"ms_per_step": ms, "volumes_per_sec": batch / (ms * 1e-3)}
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+            del model, opt
+        except Exception as e:                             # noqa: BLE001 - a context number must not take the bench down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    return out
 
 
-def resnet_cpu_baseline(seconds_cap=60.0):
-    """BASELINE.json configs[0]: the reference's PyTorch CPU path - ResNet3D-18 forward+backward, batch 2, 1x91x109x91, fp32
-    (oracle/resnet_oracle.py restates resnet.py and is pinned bit-exact against it)."""
+def resnet_cpu_reference(steps, warmup, size=RESNET_SIZE, batch=2, seconds_cap=None):
+    """The reference's PyTorch CPU path for the headline workload: ResNet3D-18 forward + CE loss + backward, fp32, on the
+    host cores (oracle/resnet_oracle.py restates resnet.py and is pinned bit-exact against it).  One step = a BOUNDED
+    SAMPLE of the workload: batch `batch` instead of 16 of the same 1 x size^3 volumes (per-volume cost is batch
+    independent on a CPU).  Returns volumes/s over exactly `steps` timed steps (or as many as fit in seconds_cap)."""
     import torch
     import torch.nn.functional as F
 
     from multimodal_ad_b200.models import resnet
     from oracle.resnet_oracle import classifier_head_oracle, resnet_features_oracle
 
+    torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     torch.manual_seed(0)
-    m = resnet.resnet18(sample_input_D=91, sample_input_H=109, sample_input_W=91, num_seg_classes=1)
+    m = resnet.resnet18(sample_input_D=size, sample_input_H=size, sample_input_W=size, num_seg_classes=1)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
     fw, fb = torch.randn(3, 512, requires_grad=True), torch.zeros(3, requires_grad=True)
-    x, y = torch.rand(2, 1, 91, 109, 91), torch.tensor([0, 2])
-    t0 = time.perf_counter()
-    n = 0
-    while n < 1 or (time.perf_counter() - t0 < seconds_cap / 3 and n < 3):
+    x, y = torch.rand(batch, 1, size, size, size), torch.randint(0, 3, (batch,))
+
+    def step():
         loss = F.cross_entropy(classifier_head_oracle(resnet_features_oracle(sd, x, [2, 2, 2, 2], True), fw, fb), y)
         loss.backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps:
+        step()
         n += 1
+        if seconds_cap is not None and time.perf_counter() - t0 > seconds_cap:
+            break
     dt = time.perf_counter() - t0
-    return {"value": 2 * n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} step(s) of batch 2 x 1x91x109x91 fp32 forward+backward (BASELINE configs[0]) on the host cores"}
+    return {"value": batch * n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "ms_per_step": 1e3 * dt / n, "steps": n,
+            "sample": f"{n} step(s) of batch {batch} (instead of 16) x 1x{size}^3 fp32 forward + CE + backward through the pinned "
+                      "restatement of models/resnet.py on the host cores"}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# ROI pooling (configs[1])
+# ---------------------------------------------------------------------------------------------------------------------
 def reference_step(feats, onehot):
     """One pass of the reference's own per-batch ROI expression on host cores
     (image_features.py:111-114, restated verbatim in oracle/roi_oracle.py; the one-hot
@@ -403,51 +452,140 @@ def reference_step(feats, onehot):
     return reference_pool_torch(feats, onehot)
 
 
-def run_reference_arm(args, rank: int):
-    import numpy as np
+def roi_cpu_reference(seconds=8.0):
     import torch
 
     from oracle.roi_oracle import reference_onehot_torch, synthetic_atlas
 
-    if rank != 0:
-        return
-    lab = reference_onehot_torch(synthetic_atlas(SHAPE, N_ROIS))
-    sample = 1                                   # volumes per step: the (B,R,C,D,H,W) product is 614 MB per volume
-    g = torch.Generator().manual_seed(0)
-    x = torch.rand((sample, 1) + SHAPE, generator=g)
-    for _ in range(max(args.warmup, 1)):
-        reference_step(x, lab)
+    onehot = reference_onehot_torch(synthetic_atlas(SHAPE, N_ROIS))
+    xs = torch.rand((1, 1) + SHAPE)
+    reference_step(xs, onehot)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        reference_step(x, lab)
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        reference_step(xs, onehot)
+        n += 1
     dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
-    cores = torch.get_num_threads()
-    line = {
-        "impl": "reference", "metric": "roi_pool_volumes_per_sec", "value": v, "unit": "volumes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "labels": N_ROIS, "volume": list(SHAPE)},
-        "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} volume per step of the same workload, reference torch expression "
-                                   "image_features.py:80-82,111-114 on host cores"},
-        "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    if not args.no_resnet:
-        rb = resnet_cpu_baseline()
-        line["resnet3d18_train"] = {"impl": "reference", "metric": "resnet3d18_train_volumes_per_sec", "value": rb["value"],
-                                    "unit": "volumes/s", "cpu_baseline": rb,
-                                    "config": {"workload": "resnet3d18_fp32_cpu_batch2_1x91x109x91 (BASELINE configs[0])"}}
-    print(json.dumps(line), flush=True)
+    return {"value": n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} single-volume passes (~{seconds:.0f} s) of the reference torch expression "
+                      "(image_features.py:80-82,111-114) on the host cores"}
 
 
-def run_cuda_arm(args, rank: int, local_rank: int, world: int):
-    import numpy as np
+def run_roi_pool(args, rank, world, dev, dist, steps, warmup, want_cpu):
     import torch
 
     from multimodal_ad_b200 import RoiPlan, _lib
     from multimodal_ad_b200.sharding import max_over_ranks
-    from oracle.roi_oracle import synthetic_atlas
+    from oracle.roi_oracle import synthetic_atlas                       # label-map generator only (outside every timed region)
+
+    lab = synthetic_atlas(SHAPE, N_ROIS)
+    V = lab.size
+    plan = RoiPlan(lab, N_ROIS, tile=args.tile, stages=args.stages)
+    # three input batches (3 x 231 MB > 126 MB L2) visited round-robin: every step streams from HBM
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bufs = [torch.rand((BATCH, V), device=dev, generator=g) for _ in range(3)]
+
+    def step(i):
+        return plan.pool(bufs[i % 3])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the K steps are queued behind a short spin kernel (outside the event bracket) so that the device-side time of exactly
+    # K steps is measured even when a slow host core cannot launch a 46 us step every 46 us
+    torch.cuda._sleep(int(max(0.01, steps * 1.0e-4) * 1.9e9))
+    ev0.record()
+    for i in range(steps):
+        step(i)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        ms = max_over_ranks(ms, dev)
+    value = world * BATCH * steps / (ms * 1e-3)
+
+    # --- dominant kernel alone: K back-to-back launches of the streaming kernel only (no finalize pass),
+    #     CUDA events on the launching stream (torch's current stream is the one the C-ABI call is given) ---
+    for i in range(3):
+        plan.stream_only(bufs[i % 3])
+    torch.cuda.synchronize()
+    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(max(0.01, steps * 1.0e-4) * 1.9e9))
+    ka.record()
+    for i in range(steps):
+        plan.stream_only(bufs[i % 3])
+    kb.record()
+    kb.synchronize()
+    k_avg_ms = ka.elapsed_time(kb) / steps
+    alg_bytes = plan.algorithmic_bytes(BATCH)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = roi_traffic_from_profile()
+
+    # --- end to end through the public host-buffer API: pinned host -> device, pool, results -> host ---
+    xh = torch.rand((BATCH, V)).pin_memory()
+    plan.pool_host(xh)
+    n_e2e = max(1, min(steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        plan.pool_host(xh)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        dt = max_over_ranks(dt, dev)
+    res = {
+        "metric": "roi_pool_volumes_per_sec", "value": value, "unit": "volumes/s", "steps": steps, "ms_per_step": ms / steps,
+        "dtype": "f32", "scaling": "weak",
+        "config": {"workload": ROI_WORKLOAD, "labels": N_ROIS, "volume": list(SHAPE), "batch_per_gpu": BATCH,
+                   "parallelism": f"subject-sharded x{world}, no collective", "tile": plan.tile,
+                   "l2": "3 input batches of 231 MB visited round-robin (each > 126 MB L2)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": f"roi_stream_kernel<{plan.tile},16>", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms},
+        "e2e": {"value": world * BATCH * n_e2e / dt, "unit": "volumes/s", "h2d_bytes_per_step": BATCH * V * 4,
+                "d2h_bytes_per_step": BATCH * N_ROIS * 12, "steps": n_e2e},
+        "gpu_launches": launches,
+    }
+    if want_cpu:
+        res["cpu_baseline"] = roi_cpu_reference()
+    del bufs, plan
+    torch.cuda.empty_cache()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# arms
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank: int):
+    """--impl reference: the reference's own CPU implementation of the headline path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    r = resnet_cpu_reference(args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "resnet3d18_train_volumes_per_sec", "value": r["value"], "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": RESNET_WORKLOAD, "batch_per_gpu": RESNET_BATCH, "volume": [RESNET_SIZE] * 3},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if not args.no_extras:
+        line["roi_pool"] = {"impl": "reference", "metric": "roi_pool_volumes_per_sec", "config": {"workload": ROI_WORKLOAD},
+                            **roi_cpu_reference(5.0)}
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda_arm(args, rank: int, local_rank: int, world: int):
+    import torch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -458,134 +596,54 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    solo = rank == 0 and world == 1
 
-    lab = synthetic_atlas(SHAPE, N_ROIS)
-    V = lab.size
-    plan = RoiPlan(lab, N_ROIS, tile=args.tile, stages=args.stages)
-    # three input batches (3 x 231 MB > 126 MB L2) visited round-robin: every step streams from HBM
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    bufs = [torch.rand((BATCH, V), device=dev, generator=g) for _ in range(3)]
-    lib = _lib.load()
+    head = run_resnet_train(args, rank, world, dev, dist, steps=args.steps, warmup=args.warmup, sample_clocks=True, local_rank=local_rank)
+    extras = {}
 
-    def step(i):
-        return plan.pool(bufs[i % 3])
+    def guarded(name, fn):
+        """A nested workload must never take the headline line down on one GPU (under torchrun an exception on one rank would
+        leave the others in a collective, so there it is allowed to propagate)."""
+        if world > 1:
+            extras[name] = fn()
+            return
+        try:
+            extras[name] = fn()
+        except Exception as e:                             # noqa: BLE001
+            extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the K steps are queued behind a short spin kernel (outside the event bracket) so that the device-side time of exactly
-    # K steps is measured even when a slow host core cannot launch a 46 us step every 46 us
-    torch.cuda._sleep(int(max(0.01, args.steps * 1.0e-4) * 1.9e9))
-    ev0.record()
-    for i in range(args.steps):
-        out = step(i)
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = _lib.launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    if dist is not None:
-        ms = max_over_ranks(ms, dev)
-    value = world * BATCH * args.steps / (ms * 1e-3)
-
-    # --- dominant kernel alone: K back-to-back launches of the streaming kernel only (no finalize pass),
-    #     CUDA events on the launching stream (torch's current stream is the one the C-ABI call is given) ---
-    for i in range(3):
-        plan.stream_only(bufs[i % 3])
-    torch.cuda.synchronize()
-    ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # a ~25 ms spin kernel goes first, so the host has queued all K launches before the first one starts: the events then
-    # bracket K back-to-back kernel executions whatever the host's launch rate is (a slow host core otherwise inflates this)
-    torch.cuda._sleep(int(max(0.01, args.steps * 1.0e-4) * 1.9e9))
-    ka.record()
-    for i in range(args.steps):
-        plan.stream_only(bufs[i % 3])
-    kb.record()
-    kb.synchronize()
-    k_avg_ms = ka.elapsed_time(kb) / args.steps
-    alg_bytes = plan.algorithmic_bytes(BATCH)
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-
-    # --- end to end through the public host-buffer API: pinned host -> device, pool, results -> host ---
-    e2e = None
-    if rank == 0 or world > 1:
-        xh = torch.rand((BATCH, V)).pin_memory()
-        plan.pool_host(xh)
-        n_e2e = max(1, min(args.steps, 10))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            res = plan.pool_host(xh)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            dt = max_over_ranks(dt, dev)
-        e2e = {"value": world * BATCH * n_e2e / dt, "unit": "volumes/s",
-               "h2d_bytes_per_step": BATCH * V * 4, "d2h_bytes_per_step": BATCH * N_ROIS * 12, "steps": n_e2e}
-
+    if not args.no_extras:
+        guarded("roi_pool", lambda: run_roi_pool(args, rank, world, dev, dist, max(args.steps, 20), max(args.warmup, 3),
+                                                 want_cpu=solo and not args.no_cpu_baseline))
+        guarded("resnet3d18_train_91x109x91", lambda: run_resnet_train(
+            args, rank, world, dev, dist, shape=SHAPE, steps=min(args.steps, 10), warmup=3, do_e2e=False,
+            workload="resnet3d18_bf16_train_batch16_1x91x109x91_3class (config/config_unet.json volume)",
+            metric="resnet3d18_train_91x109x91_volumes_per_sec"))
+        guarded("resnet3d50_train", lambda: run_resnet_train(
+            args, rank, world, dev, dist, depth=50, batch=8, nb_class=2, steps=min(args.steps, 8), warmup=3, do_e2e=False,
+            workload="resnet3d50_bottleneck_bf16_train_batch8_1x128^3 (cfg_denseNet.json: model_type resnet, depth 50)",
+            metric="resnet3d50_train_volumes_per_sec"))
+        if solo:
+            guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev))
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.roi_oracle import reference_onehot_torch
-
-        xs = torch.rand((1, 1) + SHAPE)
-        onehot = reference_onehot_torch(lab)
-        reference_step(xs, onehot)
-        t0 = time.perf_counter()
-        n = 0
-        while time.perf_counter() - t0 < 10.0:
-            reference_step(xs, onehot)
-            n += 1
-        dt = time.perf_counter() - t0
-        cpu_baseline = {"value": n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{n} single-volume passes (~10 s) of the reference torch expression "
-                                  "(image_features.py:80-82,111-114) on the host cores"}
-
-    resnet = resnet50 = None
-    if not args.no_resnet:
-        resnet = run_resnet_train(args, rank, local_rank, world, dev, dist)
-        if world == 1:
-            # the third workload must never take the headline line down with it on one GPU (under torchrun an exception on one
-            # rank would leave the others in a collective, so there it is allowed to propagate)
-            try:
-                resnet50 = run_resnet50_train(args, rank, local_rank, world, dev, dist)
-            except Exception as e:                             # noqa: BLE001
-                resnet50 = {"metric": "resnet3d50_train_volumes_per_sec", "error": f"{type(e).__name__}: {e}"[:300]}
-                torch.cuda.synchronize()
-                torch.cuda.empty_cache()
-        else:
-            resnet50 = run_resnet50_train(args, rank, local_rank, world, dev, dist)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            resnet["cpu_baseline"] = resnet_cpu_baseline()
+    if solo and not args.no_cpu_baseline:
+        r = resnet_cpu_reference(steps=64, warmup=1, seconds_cap=20.0)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
+        pipe = step_tensor_pipe_from_profile()
+        if pipe is not None:
+            head["roofline"]["tensor_pipe_active_pct_ncu"] = pipe
         line = {
-            "metric": "roi_pool_volumes_per_sec", "value": value, "unit": "volumes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "labels": N_ROIS, "volume": list(SHAPE), "batch_per_gpu": BATCH,
-                       "parallelism": f"subject-sharded x{world}, no collective", "tile": plan.tile,
-                       "l2": "3 input batches of 231 MB visited round-robin (each > 126 MB L2)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_NCU, "peak_source": peak_src, "kernel": "roi_stream_kernel<256,16>",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_avg_ms},
-            "cpu_baseline": cpu_baseline,
-            "e2e": e2e,
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "resnet3d18_train": resnet,
-            "resnet3d50_train": resnet50,
+            "metric": head["metric"], "value": head["value"], "unit": head["unit"], "n_gpus": world,
+            "steps": head["steps"], "warmup": head["warmup"], "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": head["config"], "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "e2e": head.get("e2e"),
+            "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"), "loss": head["loss"],
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -594,13 +652,13 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet3D-18 training measurement (second workload)")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only (no nested ROI / ResNet-50 / UNet / torch objects)")
     ap.add_argument("--no-graph", action="store_true", help="ResNet step: launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -38,6 +38,10 @@ int mmad_abi_version(void);
 /* Number of kernel launches issued through this library by the calling
  * process since load (bench.py reports it as gpu_launches). */
 int64_t mmad_launch_count(void);
+/* Tensor-core FLOPs actually ISSUED (2*M*N*16 per tcgen05.mma, counted by the issuing loops) by the convolution kernels
+ * of this library on the current device since load; synchronises with the device.  Differs from the algorithmic FLOPs
+ * of a layer by the zero-padding taps the kernels skip (fewer) and by partially filled 128-voxel tiles (more). */
+int64_t mmad_executed_mma_flops(void);
 
 /* ------------------------------------------------------------------ */
 /* Part 1: atlas ROI pooling                                           */

@@ -42,6 +42,8 @@ def load() -> ctypes.CDLL:
     lib.mmad_last_error.argtypes = []
     lib.mmad_abi_version.restype = ctypes.c_int
     lib.mmad_launch_count.restype = c_int64
+    lib.mmad_executed_mma_flops.restype = c_int64
+    lib.mmad_executed_mma_flops.argtypes = []
 
     P = c_void_p
     lib.mmad_roi_plan_create.argtypes = [P, c_int64, c_int32, POINTER(P)]
@@ -116,3 +118,8 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().mmad_launch_count())
+
+
+def executed_mma_flops() -> int:
+    """Tensor-core FLOPs the library's convolution kernels have issued on the current device since load (synchronises)."""
+    return int(load().mmad_executed_mma_flops())

@@ -23,6 +23,12 @@
 
 namespace mmad {
 
+__device__ unsigned long long g_mma_flops_igemm;           // executed tensor-core flops of this file's kernels (tc_common.cuh)
+long long mma_flops_igemm() {
+    unsigned long long v = 0;
+    return cudaMemcpyFromSymbol(&v, g_mma_flops_igemm, sizeof(v)) == cudaSuccess ? (long long)v : -1;
+}
+
 struct ConvGeom {
     int N, D, H, W, Cin;          // input
     int Do, Ho, Wo, Cout;         // output
@@ -191,7 +197,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         // ============================ MMA issuer (whole warp walks the loop, one elected lane issues) ============================
         {
-            uint32_t s = 0, ph = 0, it = 0;
+            uint32_t s = 0, ph = 0, it = 0, nmma = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // epilogue has drained this accumulator
@@ -223,6 +229,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 4; ++j)           // 4 x K16 inside the 64-wide (128-byte) swizzled row
                                 umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                            nmma += 4;
                         }
                         umma_commit(empty0 + 8 * s);              // frees the smem slot when these MMAs retire
                     }
@@ -232,6 +239,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (elect_one()) umma_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
                 __syncwarp();
             }
+            if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 128u * BN * 16u);
         }
     } else if (warp >= 4) {
         // ============================ epilogue: TMEM -> bf16 -> smem -> TMA store (+ BN statistics) ============================
@@ -434,7 +442,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else if (warp == 1) {
         // ============================ MMA issuer: leader CTA only ============================
         if (leader) {
-            uint32_t s = 0, ph = 0, it = 0;
+            uint32_t s = 0, ph = 0, it = 0, nmma = 0;
             for (int st = pair; st < total_super; st += n_pairs, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // both epilogues have drained this accumulator
@@ -452,6 +460,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     if (elect_one()) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                        nmma += 4;
                         umma_commit_2sm(empty0 + 8 * s, 3);       // frees the slot in both CTAs
                     }
                     __syncwarp();
@@ -460,6 +469,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc, 3);   // accumulator complete -> both epilogues
                 __syncwarp();
             }
+            if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 256u * 256u * 16u);
         }
     } else if (warp >= 4) {
         // ============================ epilogue (in both CTAs): own 128 accumulator rows ============================

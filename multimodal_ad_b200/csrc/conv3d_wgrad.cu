@@ -21,6 +21,12 @@
 
 namespace mmad {
 
+__device__ unsigned long long g_mma_flops_wgrad;           // executed tensor-core flops of this file's kernels (tc_common.cuh)
+long long mma_flops_wgrad() {
+    unsigned long long v = 0;
+    return cudaMemcpyFromSymbol(&v, g_mma_flops_wgrad, sizeof(v)) == cudaSuccess ? (long long)v : -1;
+}
+
 struct WgradGeom {
     int N, D, H, W, Cin;
     int Do, Ho, Wo, Cout;
@@ -154,7 +160,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // ============================ MMA issuer ============================
         {
             const uint32_t idesc = umma_idesc_bf16(128, g.nb, 1, 1);
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, nmma = 0;
             WgTapOff toff[4];
             for (int a = 0; a < nu; ++a) wg_tap_offsets(g, u0 + a, toff[a]);
             for (int c = c_begin; c < c_end; ++c) {
@@ -180,13 +186,14 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 4; ++j)               // K16 = 16 voxel rows = 2048 bytes
                             umma_bf16(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                        nmma += 4;
                     }
                     umma_commit(empty0 + 8 * s);
                 }
                 __syncwarp();
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) umma_commit(tfull);
+            if (elect_one()) { umma_commit(tfull); mma_count_flush(&g_mma_flops_wgrad, nmma, 2u * 128u * (uint32_t)g.nb * 16u); }
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -371,7 +378,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         // ============================ MMA issuer: leader CTA only ============================
         if (leader) {
             const uint32_t idesc = umma_idesc_bf16(256, g.nb, 1, 1);
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, nmma = 0;
             for (int c = c_begin; c < c_end; ++c, next_chunk()) {
                 const uint32_t skip = chunk_skip(c);
                 if (__popc(skip) == nblk) continue;
@@ -387,10 +394,12 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
                             for (int j = 0; j < 8; ++j)           // K16 = 16 voxel rows = 2048 bytes
                                 umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                            nmma += 8;
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 umma_bf16_2sm(tmem_base + a * g.nb, adesc + 128 * j, bdesc + 128 * j, idesc, (c > c_begin || j) ? 1u : 0u);
+                            nmma += 4;
                         }
                     }
                     umma_commit_2sm(empty0 + 8 * s, 3);
@@ -398,7 +407,7 @@ conv3d_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 __syncwarp();
                 if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) umma_commit_2sm(tfull, 3);
+            if (elect_one()) { umma_commit_2sm(tfull, 3); mma_count_flush(&g_mma_flops_wgrad, nmma, 2u * 256u * (uint32_t)g.nb * 16u); }
             __syncwarp();
         }
     }
@@ -513,7 +522,7 @@ conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        uint32_t s = 0, ph = 0;
+        uint32_t s = 0, ph = 0, nmma = 0;
         for (int c = c_begin; c < c_end; ++c) {
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
@@ -531,12 +540,13 @@ conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
                         umma_bf16(tmem_base + blk * 64, adesc, bdesc, IDESC, (c > c_begin || j) ? 1u : 0u);
                     }
                 }
+                nmma += 56;
                 umma_commit(empty0 + 8 * s);
             }
             __syncwarp();
             if (++s == S) { s = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(tfull);
+        if (elect_one()) { umma_commit(tfull); mma_count_flush(&g_mma_flops_wgrad, nmma, 2u * 128u * 64u * 16u); }
         __syncwarp();
     } else if (warp >= 4) {
         // ============================ epilogue: TMEM -> fp32 partials [slice][co][tap][ci] ============================

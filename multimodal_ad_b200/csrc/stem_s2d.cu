@@ -27,6 +27,12 @@ constexpr int kStemBBytes = 64 * kStemK * 2;      // packed weights: 16 atoms x 
 constexpr int kStemOutBytes = 128 * 128;          // epilogue staging: 128 voxels x 64 channels bf16
 constexpr int kStemDyBox = 128 * 128;             // wgrad: 128 voxels x 64 channels of dY
 
+__device__ unsigned long long g_mma_flops_stem;            // executed tensor-core flops of this file's kernels (tc_common.cuh)
+long long mma_flops_stem() {
+    unsigned long long v = 0;
+    return cudaMemcpyFromSymbol(&v, g_mma_flops_stem, sizeof(v)) == cudaSuccess ? (long long)v : -1;
+}
+
 struct StemGeom {
     int N, D, H, W;               // input volume (one channel)
     int Do, Ho, Wo;               // conv1 output
@@ -159,7 +165,7 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ============================ MMA issuer ============================
         {
             mbar_wait(bfull, 0);
-            uint32_t s = 0, ph = 0, it = 0;
+            uint32_t s = 0, ph = 0, it = 0, nmma = 0;
             for (int tile = blockIdx.x; tile < g.m_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);
@@ -177,12 +183,14 @@ stem_conv_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             for (int j = 0; j < 2; ++j)           // 2 x K16 inside the 32-wide (64-byte) swizzled row
                                 umma_bf16(tmem_base + acc * 64, adesc + 2 * j, bdesc + 2 * j, IDESC, (kd | kh | j) ? 1u : 0u);
                         }
+                    nmma += 32;
                     umma_commit(empty0 + 8 * s);
                     umma_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) mma_count_flush(&g_mma_flops_stem, nmma, 2u * 128u * 64u * 16u);
         }
     } else if (warp >= 4) {
         // ============================ epilogue: TMEM -> bf16 -> smem -> TMA store (+ BN statistics) ============================
@@ -322,12 +330,13 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         {
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, nmma = 0;
             for (int c = c_begin; c < c_end; ++c) {
                 mbar_wait(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t sb = base + s * STAGE;
                 if (elect_one()) {
+                nmma += 32;
 #pragma unroll
                 for (int kd = 0; kd < 4; ++kd) {
                     // A, MN-major SWIZZLE_64B: 64-byte rows are voxels (K), 8-row groups 512 B apart, the four 32-wide kh atoms one
@@ -343,7 +352,7 @@ stem_wgrad_s2d_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) umma_commit(tfull);
+            if (elect_one()) { umma_commit(tfull); mma_count_flush(&g_mma_flops_stem, nmma, 2u * 128u * 64u * 16u); }
             __syncwarp();
         }
     } else if (warp >= 4) {

@@ -168,6 +168,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
+// Executed tensor-core work: every MMA-issuing loop counts its tcgen05.mma instructions in a register (one IADD next to each
+// issue) and adds count x (2*M*N*16 flops per instruction) to a per-translation-unit device counter once per CTA.
+// mmad_executed_mma_flops() (capi.cu) sums the counters; bench.py reports it beside the algorithmic FLOPs, which also count
+// the zero-padding taps the kernels skip.
+__device__ __forceinline__ void mma_count_flush(unsigned long long* ctr, uint32_t nmma, uint32_t flops_per_mma) {
+    if (nmma) atomicAdd(ctr, (unsigned long long)nmma * flops_per_mma);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
