@@ -108,6 +108,13 @@ int mmad_roi_plan_binding(mmad_roi_plan* plan, int64_t n_vols, int32_t sms, int3
                           int32_t* grid, int32_t* item_group, int32_t* item_t0, int32_t* item_t1,
                           int32_t* item_slot_ptr, uint8_t* slot_label, int32_t* slot_dst, int32_t* fin_ptr);
 
+/* ROI means of a channels-last feature map that never left the GPU: feats_dev fp32 (n_vols, Dp, Hp, Wp, 64) NDHWC - the fp32
+ * side output of mmad_conv3d_fwd_ex_bf16 for s_block1.conv2, the tensor image_features.py:58-60 hooks - pooled over the
+ * plan's atlas (D, H, W) <= (Dp, Hp, Wp) (the crop of image_features.py:104 folded in).  mean_dev float32[n_vols][n_rois][64]
+ * = image_features.py:114's roi_feat (B, R, C).  Only the rows of labelled voxels are read. */
+int mmad_roi_pool_ndhwc_f32(mmad_roi_plan* plan, const float* feats_dev, int64_t n_vols, int Dp, int Hp, int Wp,
+                            int D, int H, int W, int C, float* mean_dev, void* stream);
+
 /* Algorithmic HBM bytes one mmad_roi_pool_f32 launch over n_vols volumes must
  * move (volume bytes + run programme + outputs); bench.py's roofline uses it. */
 int64_t mmad_roi_pool_algorithmic_bytes(const mmad_roi_plan* plan, int64_t n_vols);
@@ -184,6 +191,68 @@ int64_t mmad_stem_s2d_wgrad_workspace(int N, int D, int H, int W, int* nsplit_ou
 int mmad_stem_s2d_wgrad(const void* xs, const void* dy, float* partials,
                         int N, int D, int H, int W, void* stream);
 int mmad_stem_s2d_wgrad_reduce(const float* partials, int nsplit, float* dw, void* stream);
+
+/* ---- UNet3D pieces (/root/reference/models/unet3d.py) --------------------------------------------------------------- */
+
+/* mmad_conv3d_fwd_bf16 with (a) output rows `ldy` elements apart (0 = dense): y may be a channel slice of a wider NDHWC
+ * tensor, so the producers of a concatenation (unet3d.py:77 torch.cat((upconv, residual), 1)) write it in place; (b) a
+ * per-channel epilogue on the fp32 accumulators, stored = act(acc * ep_scale[c] + ep_shift[c]) (NULL scale = 1, NULL shift =
+ * 0, ep_relu != 0 = ReLU): a convolution bias (unet3d.py:37-40), or in eval mode the BatchNorm3d + ReLU that follows the
+ * convolution folded into the producing kernel; (c) an fp32 side output out_f32[voxel][Cout] = acc + f32_bias[c] (NULL bias
+ * = 0), dense NDHWC: the raw convolution output image_features.py:58-60 hooks (s_block1.conv2), kept at accumulator
+ * precision for the ROI pooling.  stats_partials are the statistics of the STORED bf16 values. */
+int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, float* stats_partials,
+                            const float* ep_scale, const float* ep_shift, int ep_relu, float* out_f32, const float* f32_bias,
+                            int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, void* stream);
+/* mmad_conv3d_wgrad_bf16 for an x that is the channel slice [c0, c0+Cin) of a wider NDHWC tensor (rows ldx elements apart, x
+ * points at channel c0), and the matching reduction into dw[:, ci_off : ci_off+Cin] of a (Cout, Cin_total, k,k,k) tensor:
+ * the weight gradient of a convolution over a concatenated input, computed per source. */
+int mmad_conv3d_wgrad_ex_bf16(const void* x, int64_t ldx, const void* dy, float* partials,
+                              int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, void* stream);
+int mmad_wgrad_reduce_ex(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, int Cin_total, int ci_off,
+                         void* stream);
+
+/* ConvTranspose3d(kernel 2, stride 2) (unet3d.py:68,75): y[n][2v+p][co] = bias[co] + sum_ci x[n][v][ci] * w[ci][co][p] as eight
+ * 1x1x1 implicit GEMMs writing interleaved through strided tensor maps, rows ldy elements apart (0 = dense).  x (N,D,H,W,Cin),
+ * y (N,2D,2H,2W,[ldy]) bf16; w_phases [8][Cout][Cin] bf16 from mmad_convtranspose3d_prep_weights on the torch weight
+ * (Cin, Cout, 2,2,2) fp32.  Its data gradient is mmad_conv3d_fwd_bf16 with k = 2, stride 2, pad 0 on
+ * mmad_conv3d_prep_weights(w viewed as (Cout' = Cin, Cin' = Cout, 8 taps)); its weight gradient is mmad_conv3d_wgrad_bf16 with
+ * x := dy (fine grid), dy := x (coarse grid), k = 2, stride 2, pad 0 - the result is already in the (Cin, Cout, 2,2,2) layout. */
+int mmad_convtranspose3d_prep_weights(const float* w, void* w_phases, int Cin, int Cout, void* stream);
+int mmad_convtranspose3d_k2s2_fwd_bf16(const void* x, const void* w_phases, const float* bias, void* y, int64_t ldy,
+                                       int N, int D, int H, int W, int Cin, int Cout, void* stream);
+
+/* First UNet layer (unet3d.py:37 a_block1.conv1 = Conv3d(1, 32, 3, padding 1) after the zero extension to 96x112x96 of
+ * unet3d.py:116-123): direct convolution.  x fp32 (N,1,D,H,W); w fp32 (32,1,3,3,3); y bf16 (N,Do,Ho,Wo,64), (Do,Ho,Wo) >= (D,H,W),
+ * channels 32..63 written as zeros (the next convolution reads 64-channel rows); no bias (add it through the BatchNorm
+ * shift).  stats_partials float[mmad_conv3d_c1_blocks][64][2] like mmad_conv3d_fwd_bf16.  Weight gradient: partials
+ * float[mmad_conv3d_c1_blocks][32][27], summed by mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27). */
+int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo);
+int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials,
+                       int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);
+int mmad_conv3d_c1_wgrad(const float* x, const void* dy, float* partials,
+                         int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);
+
+/* MaxPool3d(kernel 2, stride 2) (unet3d.py:31,44; floor mode), NDHWC bf16.  Forward reads x with rows ldx elements apart
+ * (0 = dense; the skip tensor is pooled in place from the concatenation buffer), writes y dense (N,D/2,H/2,W/2,C) and idx
+ * (uint8 per element: winning window position, first maximum in scan order).  Backward writes dx dense (N,D,H,W,C). */
+int mmad_maxpool3d_k2_fwd(const void* x, int64_t ldx, void* y, void* idx, int N, int D, int H, int W, int C, void* stream);
+int mmad_maxpool3d_k2_bwd(const void* dy, const void* idx, void* dx, int N, int D, int H, int W, int C, void* stream);
+
+/* Head (unet3d.py:72 conv3 = Conv3d(64, K, 1) with bias, fused with the crop back of unet3d.py:126-135): x bf16
+ * (N,Dp,Hp,Wp,64) -> out fp32 (N,K,D,H,W) for the (D,H,W) <= (Dp,Hp,Wp) corner; K <= 8.  Backward: dx bf16 (N,Dp,Hp,Wp,64)
+ * (zero in the padded margin), dw float[K][64], db float[K]; partials: float[mmad_head1x1_bwd_blocks()][K][65] scratch. */
+int mmad_head1x1_fwd(const void* x, const float* w, const float* bias, float* out,
+                     int N, int Dp, int Hp, int Wp, int D, int H, int W, int C, int K, void* stream);
+int mmad_head1x1_bwd_blocks(void);
+int mmad_head1x1_bwd(const void* x, const float* w, const float* dout, void* dx, float* partials, float* dw, float* db,
+                     int N, int Dp, int Hp, int Wp, int D, int H, int W, int C, int K, void* stream);
+
+/* mmad_bn_apply with the bf16 output's rows out_ld elements apart (0 = dense): the activation is written straight into its
+ * channel slice of a concatenation buffer. */
+int mmad_bn_apply_ex(const void* x, const float* scale, const float* shift,
+                     const void* res, const float* rscale, const float* rshift, int relu,
+                     void* out_bf16, int64_t out_ld, float* out_f32, int64_t rows, int C, void* stream);
 
 /* BatchNorm3d (resnet.py:46,49,134), training statistics from the conv
  * epilogue's partials: mean, invstd, scale = gamma*invstd, shift = beta -

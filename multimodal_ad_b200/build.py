@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmmad_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
-SOURCES = ["capi.cu", "roi_pool.cu", "conv3d_igemm.cu", "conv3d_wgrad.cu", "nn_kernels.cu", "stem_s2d.cu"]
+SOURCES = ["capi.cu", "roi_pool.cu", "conv3d_igemm.cu", "conv3d_wgrad.cu", "nn_kernels.cu", "stem_s2d.cu", "unet_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

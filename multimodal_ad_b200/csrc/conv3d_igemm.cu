@@ -34,7 +34,8 @@ struct ConvGeom {
     int Do, Ho, Wo, Cout;         // output
     int kd, kh, kw, stride, pad, dil;
     int tw, th, td, tn;           // output tile box (tn samples deep), tw*th*td*tn == 128, powers of two
-    int lw, lh;                   // log2(tw), log2(th)
+    int lw, lh, ltd;              // log2(tw), log2(th), log2(td)
+    int epi;                      // 1: the epilogue applies ConvEpi (per-channel affine / ReLU / fp32 side output)
     int tiles_w, tiles_h, tiles_d, tiles_n, m_tiles, n_tiles;   // tile index: sample tile fastest, then w, h, d
     int kc;                       // Cin / 64
     int stages;
@@ -52,6 +53,22 @@ __device__ __forceinline__ uint32_t tap_axis_mask(int o0, int tl, int extent, in
     }
     return m;
 }
+
+// Optional epilogue work on the fp32 accumulators (all pointers may be NULL):
+//   out_f32[voxel * f32_ld + c] = acc + f32_bias[c]      dense NDHWC fp32 side output (the tensor image_features.py:58-60 hooks:
+//                                                        s_block1.conv2's raw output, bias included)
+//   stored bf16 value           = act(acc * scale[c] + shift[c])   (scale NULL = 1, shift NULL = 0; relu != 0 applies ReLU):
+//                                 a convolution bias (unet3d.py:37-40 / ConvTranspose3d :68), or - in eval mode - the whole
+//                                 BatchNorm3d + ReLU that follows the convolution, folded into the producing kernel.
+// The BatchNorm statistics (stats_partials) are always those of the STORED values.
+struct ConvEpi {
+    const float* scale;
+    const float* shift;
+    const float* f32_bias;
+    float* out_f32;
+    long long f32_ld;
+    int relu;
+};
 
 constexpr int kConvThreads = 256;
 constexpr int kConvProducers = 3;          // warps 0, 2, 3
@@ -71,10 +88,33 @@ constexpr int kStageOutBytes = 128 * 128;  // epilogue staging: 128 voxels x 64 
 // 2.4x less L2->SM traffic, which is what bounds the 64-channel layers.
 constexpr int kHaloTileBytes = 160 * 128;  // 10 x 4 x 4 voxels x 64 bf16
 
+// ConvEpi on 32 accumulator columns (channels cb .. cb+31) of this thread's output voxel; coefficients come from shared memory
+// (every lane reads the same address: broadcast).
+__device__ __forceinline__ void conv_epilogue_affine(uint32_t (&v)[32], int cb, const ConvEpi& ep, const float* ep_sc, const float* ep_sh,
+                                                     const float* ep_fb, bool row_ok, long long row_vox) {
+    if (ep.out_f32 && row_ok) {
+        float* dst = ep.out_f32 + row_vox * ep.f32_ld + cb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(ep_fb + cb + j);
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                                                              __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(ep_sc + cb + j), sh = *reinterpret_cast<const float4*>(ep_sh + cb + j);
+        float f0 = fmaf(__uint_as_float(v[j]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+        float f2 = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+        if (ep.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+        v[j] = __float_as_uint(f0); v[j + 1] = __float_as_uint(f1); v[j + 2] = __float_as_uint(f2); v[j + 3] = __float_as_uint(f3);
+    }
+}
+
 template <int BN, int KS, bool WH = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+                    const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep) {
     pdl_launch_dependents();
     static_assert(!WH || KS == 3, "the W-halo variant stages the three kw taps of one (kd, kh) pair");
     constexpr int B_TILE = BN * 128;
@@ -96,6 +136,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);     // [2][Cout] (two row halves)
     float* st_sq = st_sum + 2 * g.Cout;                           // [2][Cout]
+    float* ep_sc = st_sq + 2 * g.Cout;                            // epilogue scale / shift / fp32 bias, [Cout] each (only when g.epi)
+    float* ep_sh = ep_sc + g.Cout;
+    float* ep_fb = ep_sh + g.Cout;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -247,6 +290,14 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int et = threadIdx.x - 128;                         // 0..127
         const int row = ew * 32 + lane;                           // output voxel inside the tile == TMEM lane
         uint32_t it = 0, nstore = 0;
+        if (g.epi) {
+            for (int c = et; c < g.Cout; c += 128) {
+                ep_sc[c] = ep.scale ? ep.scale[c] : 1.f;
+                ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
+                ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
+            }
+            named_bar_sync(2, 128);
+        }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
@@ -257,6 +308,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int dt = r;
             const int w0 = wt * g.tw, h0 = ht * g.th, d0 = dt * g.td;
             const int vw = min(g.tw, g.Wo - w0), vh = min(g.th, g.Ho - h0), vd = min(g.td, g.Do - d0);   // valid extent
+            const int rwi = row & (g.tw - 1), rhi = (row >> g.lw) & (g.th - 1), rdi = (row >> (g.lw + g.lh)) & (g.td - 1),
+                      rni = row >> (g.lw + g.lh + g.ltd);
+            const bool row_ok = rwi < vw && rhi < vh && rdi < vd;
+            const long long row_vox = (((long long)(n + rni) * g.Do + d0 + rdi) * g.Ho + h0 + rhi) * g.Wo + w0 + rwi;
 
             mbar_wait(tfull0 + 8 * acc, aph);
             tc_fence_after();
@@ -271,6 +326,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
+                    if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -337,7 +393,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ===============================================================================================================
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                         const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials) {
+                         const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep) {
     pdl_launch_dependents();
     constexpr int BN = 256;
     constexpr int B_HALF = (BN / 2) * 128;
@@ -358,6 +414,9 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);
     float* st_sq = st_sum + 2 * g.Cout;
+    float* ep_sc = st_sq + 2 * g.Cout;
+    float* ep_sh = ep_sc + g.Cout;
+    float* ep_fb = ep_sh + g.Cout;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -477,6 +536,14 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int et = threadIdx.x - 128;
         const int row = ew * 32 + lane;
         uint32_t it = 0, nstore = 0;
+        if (g.epi) {
+            for (int c = et; c < g.Cout; c += 128) {
+                ep_sc[c] = ep.scale ? ep.scale[c] : 1.f;
+                ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
+                ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
+            }
+            named_bar_sync(2, 128);
+        }
         for (int st = pair; st < total_super; st += n_pairs, ++it) {
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const int nt = st % g.n_tiles, mp = st / g.n_tiles;
@@ -489,6 +556,10 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int w0 = wt * g.tw, h0 = ht * g.th, d0 = dt * g.td;
             const bool real = mt < g.m_tiles;
             const int vw = real ? min(g.tw, g.Wo - w0) : 0, vh = min(g.th, g.Ho - h0), vd = min(g.td, g.Do - d0);
+            const int rwi = row & (g.tw - 1), rhi = (row >> g.lw) & (g.th - 1), rdi = (row >> (g.lw + g.lh)) & (g.td - 1),
+                      rni = row >> (g.lw + g.lh + g.ltd);
+            const bool row_ok = rwi < vw && rhi < vh && rdi < vd;
+            const long long row_vox = (((long long)(n + rni) * g.Do + d0 + rdi) * g.Ho + h0 + rhi) * g.Wo + w0 + rwi;
 
             mbar_wait(tfull0 + 8 * acc, aph);
             tc_fence_after();
@@ -503,6 +574,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
+                    if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -601,9 +673,9 @@ static void pick_tile(int N, int D, int H, int W, int Wo, int Ho, int Do, int k,
     pick_chunk(128, N, W, H, D, Wo, Ho, Do, k, stride, pad, dil, tw, th, td, tn);
 }
 
-static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false) {
+static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false, bool epi = false) {
     const int a_region = halo ? kHaloTileBytes : ks * kATileBytes;
-    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + 4 * cout * 4;
+    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + (epi ? 7 : 4) * cout * 4;
 }
 
 // W-halo variant (see the kernel): 3x3x3, unit stride, undilated, 64 -> 64 channels; on unless MMAD_CONV_HALO=0
@@ -646,9 +718,9 @@ int mmad_conv3d_stats_partials(int N, int D, int H, int W, int Cout, int k, int 
 // Shared launcher.  (kd, kh, kw) taps, output extents and the output's voxel strides (in ELEMENTS; 0 = dense NDHWC) are explicit
 // so that the phase convolutions of the stride-2 data gradient (rectangular kernels, outputs interleaved into dx) use the same
 // kernels as the public forward entry point.
-struct ConvOut { int Do, Ho, Wo; long long sw, sh, sd, sn; };
+struct ConvOut { int Do, Ho, Wo; long long sw, sh, sd, sn; int standard; };   // standard: the extents are the convolution's own (only strides differ)
 static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W, int Cin, int Cout,
-                         int kd, int kh, int kw, int stride, int pad, int dil, const ConvOut* ov, void* stream) {
+                         int kd, int kh, int kw, int stride, int pad, int dil, const ConvOut* ov, void* stream, const ConvEpi* epi = nullptr) {
     const int k = std::max(kd, std::max(kh, kw));
     MMAD_CHECK_ARG(x && w && y, "conv3d_fwd: null pointer");
     MMAD_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: empty input");
@@ -671,14 +743,18 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     MMAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     pick_tile(N, D, H, W, g.Wo, g.Ho, g.Do, k, stride, pad, dil, g.tw, g.th, g.td, g.tn);
     bool halo = false;
-    if (!ov && kd == kh && kh == kw && use_halo_kernel(Cin, Cout, k, stride, dil)) {
+    ConvEpi ep = {};
+    if (epi) ep = *epi;
+    g.epi = (ep.scale || ep.shift || ep.out_f32) ? 1 : 0;
+    MMAD_CHECK_ARG(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.f32_ld % 4 == 0), "conv3d_fwd: fp32 side output must be 16-byte aligned");
+    if ((!ov || ov->standard) && kd == kh && kh == kw && pad == 1 && use_halo_kernel(Cin, Cout, k, stride, dil)) {
         // the halo variant needs 8 x 4 x 4 tiles; mmad_conv3d_stats_partials (which does not know Cin) sizes the statistics
         // buffer from the regular tile, so only switch when both tilings fill every SM (grid == SM count either way)
         const long long reg = (long long)(N / g.tn) * ((g.Wo + g.tw - 1) / g.tw) * ((g.Ho + g.th - 1) / g.th) * ((g.Do + g.td - 1) / g.td);
         const long long hal = (long long)N * ((g.Wo + 7) / 8) * ((g.Ho + 3) / 4) * ((g.Do + 3) / 4);
         if (reg >= sms && hal >= sms) { halo = true; g.tw = 8; g.th = 4; g.td = 4; g.tn = 1; }
     }
-    g.lw = ilog2(g.tw); g.lh = ilog2(g.th);
+    g.lw = ilog2(g.tw); g.lh = ilog2(g.th); g.ltd = ilog2(g.td);
     g.tiles_w = (g.Wo + g.tw - 1) / g.tw; g.tiles_h = (g.Ho + g.th - 1) / g.th; g.tiles_d = (g.Do + g.td - 1) / g.td;
     g.tiles_n = N / g.tn;
     g.m_tiles = g.tiles_n * g.tiles_w * g.tiles_h * g.tiles_d;
@@ -692,15 +768,15 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     const int ks = halo ? 3 : (ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));     // K-steps per stage (one weight box per stage)
     g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024) --stages;
-    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
+    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024) --stages;
+    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
         g.nout = 1;                                        // trade the second epilogue buffer for pipeline depth
         stages = 8;
-        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo) > 227 * 1024) --stages;
+        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024) --stages;
     }
     if (halo) stages = 4;                                  // the halo producers assume a 4-slot ring (fits: 4 x 44 KB + 2 x 16 KB)
     g.stages = stages;
-    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo);
+    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0);
     MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_fwd: shared memory budget exceeded");
 
     CUtensorMap tmA, tmB, tmC;
@@ -742,7 +818,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
-        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);
+        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
@@ -754,7 +830,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         if (attr_done.need()) {                                                                                                   \
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
         }                                                                                                                   \
-        launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials);               \
+        launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep);           \
     } while (0)
     if (halo) MMAD_CONV_LAUNCH(64, 3, true);
     else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);
@@ -773,6 +849,46 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
     return conv_fwd_impl(x, w, y, stats_partials, N, D, H, W, Cin, Cout, k, k, k, stride, pad, dil, nullptr, stream);
 }
 
+// Extended forward: output rows `ldy` elements apart (y may be a channel slice of a wider NDHWC tensor - the concatenation
+// buffer of unet3d.py:77 is written in place, no torch.cat copy), per-channel epilogue (ConvEpi) and fp32 side output.
+int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, float* stats_partials, const float* ep_scale,
+                            const float* ep_shift, int ep_relu, float* out_f32, const float* f32_bias, int N, int D, int H, int W,
+                            int Cin, int Cout, int k, int stride, int pad, int dil, void* stream) {
+    MMAD_CHECK_ARG(ldy == 0 || (ldy >= Cout && ldy % 8 == 0), "conv3d_fwd_ex: ldy must be 0 (dense) or >= Cout and a multiple of 8");
+    ConvEpi ep = {ep_scale, ep_shift, f32_bias, out_f32, (long long)Cout, ep_relu};
+    ConvOut ov = {};
+    ov.Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    ov.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    ov.Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    const long long ld = ldy ? ldy : Cout;
+    ov.sw = ld; ov.sh = ld * ov.Wo; ov.sd = ld * ov.Wo * ov.Ho; ov.sn = ld * ov.Wo * ov.Ho * ov.Do;
+    ov.standard = 1;
+    return conv_fwd_impl(x, w, y, stats_partials, N, D, H, W, Cin, Cout, k, k, k, stride, pad, dil, &ov, stream, &ep);
+}
+
+// ConvTranspose3d(kernel 2, stride 2) forward (unet3d.py:68, :75): y[n][2v+p][co] = bias[co] + sum_ci x[n][v][ci] * w[ci][co][p]
+// - eight 1x1x1 implicit GEMMs (one per output phase p) that write their outputs interleaved through strided tensor maps,
+// rows `ldy` elements apart (so the result lands directly in the first channels of the concatenation buffer).
+// w_phases: [8][Cout][Cin] bf16 from mmad_convtranspose3d_prep_weights.
+int mmad_convtranspose3d_k2s2_fwd_bf16(const void* x, const void* w_phases, const float* bias, void* y, int64_t ldy, int N, int D, int H,
+                                       int W, int Cin, int Cout, void* stream) {
+    MMAD_CHECK_ARG(x && w_phases && y && N > 0 && D > 0 && H > 0 && W > 0, "convtranspose3d_k2s2: bad argument");
+    MMAD_CHECK_ARG(ldy == 0 || (ldy >= Cout && ldy % 8 == 0), "convtranspose3d_k2s2: ldy must be 0 (dense) or >= Cout and a multiple of 8");
+    const long long ld = ldy ? ldy : Cout;
+    ConvEpi ep = {nullptr, bias, nullptr, nullptr, 0, 0};
+    for (int p = 0; p < 8; ++p) {
+        const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
+        ConvOut ov = {};
+        ov.Do = D; ov.Ho = H; ov.Wo = W;
+        ov.sw = 2 * ld; ov.sh = 2 * ld * (2 * W); ov.sd = 2 * ld * (2 * W) * (2 * H); ov.sn = ld * (2LL * W) * (2 * H) * (2 * D);
+        char* out = static_cast<char*>(y) + (((size_t)pd * 2 * H + ph) * 2 * W + pw) * ld * 2;
+        const int rc = conv_fwd_impl(x, static_cast<const char*>(w_phases) + (size_t)p * Cout * Cin * 2, out, nullptr, N, D, H, W, Cin, Cout,
+                                     1, 1, 1, 1, 0, 1, &ov, stream, bias ? &ep : nullptr);
+        if (rc) return rc;
+    }
+    return MMAD_OK;
+}
+
 // Data gradient of a 3x3x3, stride-2, padding-1 convolution WITHOUT zero insertion: dx positions of parity (pd, ph, pw) only
 // see the taps of matching parity (1 tap on an even axis, 2 on an odd one), so dx is 8 interleaved stride-1 convolutions of
 // dy with (1+pd) x (1+ph) x (1+pw) kernels - 27 taps over 1/8 of the voxels each instead of 27 taps over all of them.
@@ -784,7 +900,7 @@ int mmad_conv3d_dgrad_s2_bf16(const void* dy, const void* w_phases, void* dx, in
     size_t woff = 0;
     for (int p = 0; p < 8; ++p) {
         const int pd = p >> 2, ph = (p >> 1) & 1, pw = p & 1;
-        ConvOut ov;
+        ConvOut ov = {};
         ov.Do = (D - pd + 1) / 2; ov.Ho = (H - ph + 1) / 2; ov.Wo = (W - pw + 1) / 2;
         ov.sw = 2ll * Cdx; ov.sh = 2ll * W * Cdx; ov.sd = 2ll * H * W * Cdx; ov.sn = (long long)D * H * W * Cdx;
         const int taps = (1 + pd) * (1 + ph) * (1 + pw);

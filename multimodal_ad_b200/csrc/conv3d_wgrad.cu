@@ -775,8 +775,26 @@ int64_t mmad_conv3d_wgrad_workspace(int N, int D, int H, int W, int Cin, int Cou
     return (int64_t)g.nsplit * Cout * g.taps * Cin;
 }
 
+static int wgrad_impl(const void* x, long long ldx, const void* dy, float* partials, int N, int D, int H, int W, int Cin, int Cout, int k,
+                      int stride, int pad, int dil, void* stream);
+
 int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N, int D, int H, int W, int Cin, int Cout, int k,
                            int stride, int pad, int dil, void* stream) {
+    return wgrad_impl(x, Cin, dy, partials, N, D, H, W, Cin, Cout, k, stride, pad, dil, stream);
+}
+
+// x is a channel slice [c0, c0 + Cin) of a wider NDHWC tensor whose rows are ldx elements apart (x points at channel c0): the
+// weight gradient of a convolution over a concatenated input (unet3d.py:77-78) is computed per source, no copies.
+int mmad_conv3d_wgrad_ex_bf16(const void* x, int64_t ldx, const void* dy, float* partials, int N, int D, int H, int W, int Cin, int Cout,
+                              int k, int stride, int pad, int dil, void* stream) {
+    MMAD_CHECK_ARG(ldx >= Cin && ldx % 8 == 0, "conv3d_wgrad_ex: ldx must be >= Cin and a multiple of 8");
+    return wgrad_impl(x, ldx, dy, partials, N, D, H, W, Cin, Cout, k, stride, pad, dil, stream);
+}
+
+}  // extern "C"
+
+static int wgrad_impl(const void* x, long long ldx, const void* dy, float* partials, int N, int D, int H, int W, int Cin, int Cout, int k,
+                      int stride, int pad, int dil, void* stream) {
     MMAD_CHECK_ARG(x && dy && partials, "conv3d_wgrad: null pointer");
     MMAD_CHECK_ARG(Cin % 64 == 0 && (Cin == 64 || Cin % 128 == 0), "conv3d_wgrad: Cin must be 64 or a multiple of 128");
     MMAD_CHECK_ARG(Cout % 64 == 0 && (Cout == 64 || Cout == 128 || Cout % 256 == 0), "conv3d_wgrad: Cout must be 64, 128 or a multiple of 256");
@@ -790,7 +808,7 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     if (g.halo) {
         {
             const uint64_t dims[5] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
-            const uint64_t str[4] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128, (uint64_t)D * H * W * 128};
+            const uint64_t str[4] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2, (uint64_t)D * H * W * ldx * 2};
             const uint32_t box[5] = {64, 10, 6, 6, 1};
             const uint32_t es[5] = {1, 1, 1, 1, 1};
             int rc = make_tmap_bf16(&tmX, x, 5, dims, str, box, es);
@@ -816,7 +834,7 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     }
     {
         const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
-        const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};
+        const uint64_t str[4] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2, (uint64_t)D * H * W * ldx * 2};
         const uint32_t box[5] = {64, (uint32_t)(g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), (uint32_t)g.tn};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_tmap_bf16(&tmX, x, 5, dims, str, box, es);
@@ -846,5 +864,3 @@ int mmad_conv3d_wgrad_bf16(const void* x, const void* dy, float* partials, int N
     count_launch();
     return MMAD_OK;
 }
-
-}  // extern "C"

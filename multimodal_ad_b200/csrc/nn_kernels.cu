@@ -148,7 +148,7 @@ template <bool RELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const uint4* __restrict__ res, const float* __restrict__ rscale,
                                                        const float* __restrict__ rshift, uint4* __restrict__ out_bf16,
-                                                       float4* __restrict__ out_f32, long long nvec, int C) {
+                                                       float4* __restrict__ out_f32, long long nvec, int C, int out_ld8) {
     pdl_launch_dependents();
     pdl_wait();                                        // see launch_pdl (common.cuh)
     // the grid stride is a multiple of C/8 (see the launcher): a thread keeps one channel vector, coefficients in registers
@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (out_bf16) out_bf16[i] = pack8(f);
+        // out_ld8: distance between output rows in 16-byte vectors (== cv when dense); the bf16 output may be a channel slice of a
+        // wider NDHWC tensor (the skip half of a concatenation buffer, unet3d.py:77)
+        if (out_bf16) out_bf16[out_ld8 == cv ? i : (i / cv) * out_ld8 + (i % cv)] = pack8(f);
         if (out_f32) { out_f32[2 * i] = make_float4(f[0], f[1], f[2], f[3]); out_f32[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]); }
     }
 }
@@ -811,7 +813,7 @@ __global__ void __launch_bounds__(256) ncs_f32_to_nsc_bf16_kernel(const float* _
 //      Block = (co, 64-ci chunk), 256 threads: coalesced reads of the [tap][ci] rows of every split (4 independent partial
 //      sums per thread), shared-memory transpose, coalesced [ci][tap] writes.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout, int Cin,
-                                                           int taps) {
+                                                           int taps, int Cin_total, int ci_off) {
     pdl_launch_dependents();
     pdl_wait();                                        // see launch_pdl (common.cuh)
     extern __shared__ float tile[];                  // [taps][65]
@@ -832,13 +834,13 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         tile[t * 65 + c] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
-    float* dst = dw + ((size_t)co * Cin + c0) * taps;                    // nci * taps contiguous floats
+    float* dst = dw + ((size_t)co * Cin_total + ci_off + c0) * taps;     // nci * taps contiguous floats
     for (int i = threadIdx.x; i < nci * taps; i += 256) dst[i] = tile[(i % taps) * 65 + (i / taps)];
 }
 
 // small weight tensors (few (co, ci-chunk) blocks): one thread per element, strided write into the torch layout
 __global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __restrict__ part, int nsplit, float* __restrict__ dw, int Cout,
-                                                                 int Cin, int taps) {
+                                                                 int Cin, int taps, int Cin_total, int ci_off) {
     pdl_launch_dependents();
     pdl_wait();                                        // see launch_pdl (common.cuh)
     const long long plane = (long long)Cout * taps * Cin;
@@ -855,7 +857,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_small_kernel(const float* __
         s2 += src[(size_t)(p + 2) * plane]; s3 += src[(size_t)(p + 3) * plane];
     }
     for (; p < nsplit; ++p) s0 += src[(size_t)p * plane];
-    dw[((long long)co * Cin + ci) * taps + tap] = (s0 + s1) + (s2 + s3);
+    dw[((long long)co * Cin_total + ci_off + ci) * taps + tap] = (s0 + s1) + (s2 + s3);
 }
 
 }  // namespace mmad
@@ -899,14 +901,20 @@ int mmad_bn_eval_params(int C, const float* gamma, const float* beta, const floa
     launch_pdl(bn_eval_kernel, dim3((C + 127) / 128), dim3(128), 0, ST, C, gamma, beta, running_mean, running_var, eps, mean, invstd, scale, shift);
     LAUNCH_OK();
 }
+int mmad_bn_apply_ex(const void* x, const float* scale, const float* shift, const void* res, const float* rscale, const float* rshift,
+                     int relu, void* out_bf16, int64_t out_ld, float* out_f32, int64_t rows, int C, void* stream) {
+    MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
+    MMAD_CHECK_ARG(out_ld == 0 || (out_ld >= C && out_ld % 8 == 0), "bn_apply: out_ld must be 0 (dense) or >= C and a multiple of 8");
+    const long long nvec = rows * (C / 8);
+    const int ld8 = (int)((out_ld ? out_ld : C) / 8);
+    const int grid = grid_for_channels(nvec, C / 8, sm_count() * 8);
+    if (relu) launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C, ld8);
+    else launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C, ld8);
+    LAUNCH_OK();
+}
 int mmad_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale, const float* rshift,
                   int relu, void* out_bf16, float* out_f32, int64_t rows, int C, void* stream) {
-    MMAD_CHECK_ARG(x && scale && shift && (out_bf16 || out_f32) && C % 8 == 0 && rows > 0, "bn_apply: bad argument");
-    const long long nvec = rows * (C / 8);
-    const int grid = grid_for_channels(nvec, C / 8, sm_count() * 8);
-    if (relu) launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
-    else launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(256), 0, ST, (const uint4*)x, scale, shift, (const uint4*)res, rscale, rshift, (uint4*)out_bf16, (float4*)out_f32, nvec, C);
-    LAUNCH_OK();
+    return mmad_bn_apply_ex(x, scale, shift, res, rscale, rshift, relu, out_bf16, 0, out_f32, rows, C, stream);
 }
 // number of block partials mmad_bn_bwd_reduce writes: float[n][C][2]
 int mmad_bn_bwd_partials(int64_t rows) { return (int)std::max<long long>(1, std::min<long long>(rows / 64, sm_count())); }
@@ -1021,15 +1029,19 @@ int mmad_ncs_f32_to_nsc_bf16(const float* x, void* y, int N, int C, int64_t S, v
     launch_pdl(ncs_f32_to_nsc_bf16_kernel, dim3(grid), dim3(256), 0, ST, x, (__nv_bfloat16*)y, C, S);
     LAUNCH_OK();
 }
-int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
-    MMAD_CHECK_ARG(partials && dw && nsplit > 0, "wgrad_reduce: bad argument");
+// partials [nsplit][Cout][taps][Cin] -> dw[:, ci_off : ci_off + Cin] of a torch-layout (Cout, Cin_total, taps) fp32 tensor
+int mmad_wgrad_reduce_ex(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, int Cin_total, int ci_off, void* stream) {
+    MMAD_CHECK_ARG(partials && dw && nsplit > 0 && ci_off >= 0 && ci_off + Cin <= Cin_total, "wgrad_reduce: bad argument");
     if ((long long)((Cin + 63) / 64) * Cout < 1024) {
         const long long plane = (long long)Cout * taps * Cin;
-        launch_pdl(wgrad_reduce_small_kernel, dim3((unsigned)((plane + 255) / 256)), dim3(256), 0, ST, partials, nsplit, dw, Cout, Cin, taps);
+        launch_pdl(wgrad_reduce_small_kernel, dim3((unsigned)((plane + 255) / 256)), dim3(256), 0, ST, partials, nsplit, dw, Cout, Cin, taps, Cin_total, ci_off);
     } else {
-        launch_pdl(wgrad_reduce_kernel, dim3((Cin + 63) / 64, Cout), dim3(256), taps * 65 * sizeof(float), ST, partials, nsplit, dw, Cout, Cin, taps);
+        launch_pdl(wgrad_reduce_kernel, dim3((Cin + 63) / 64, Cout), dim3(256), taps * 65 * sizeof(float), ST, partials, nsplit, dw, Cout, Cin, taps, Cin_total, ci_off);
     }
     LAUNCH_OK();
+}
+int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw, int Cout, int Cin, int taps, void* stream) {
+    return mmad_wgrad_reduce_ex(partials, nsplit, dw, Cout, Cin, taps, Cin, 0, stream);
 }
 
 }  // extern "C"

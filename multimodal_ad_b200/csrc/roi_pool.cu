@@ -383,6 +383,73 @@ __global__ void __launch_bounds__(256) roi_mean_bwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------
+// Channels-last variant: pools a (N, Dp, Hp, Wp, 64) fp32 NDHWC feature map - the layout the convolution epilogue writes
+// the tensor image_features.py:58-60 hooks - over the atlas (D, H, W) <= (Dp, Hp, Wp) (the crop of :104 folded in), mean only
+// (what image_features.py:111-114 computes).  A warp walks one (d, h) line: lane = channel pair, the line's labels sit in
+// registers (one ballot per 32 voxels), and ONLY the rows of labelled voxels are read (256 contiguous bytes per voxel);
+// consecutive voxels of the same ROI are summed in registers and folded into the block's shared double accumulators
+// [R][64] when the label changes.  Blocks add their accumulators to acc[n][R][64] (double atomics), roi_cl_finalize_kernel
+// divides by the clamped count in fp32 exactly as image_features.py:113-114 does.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) roi_cl_pool_kernel(const float2* __restrict__ feats, const uint8_t* __restrict__ labels,
+                                                          double* __restrict__ acc, int Dp, int Hp, int Wp, int D, int H, int W, int R) {
+    extern __shared__ double sacc[];                     // [R][64]
+    const int n = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < R * 64; i += 256) sacc[i] = 0.0;
+    __syncthreads();
+    int cur = 0;
+    float2 a = make_float2(0.f, 0.f);
+    auto flush = [&]() {
+        if (cur) {
+            atomicAdd(&sacc[(cur - 1) * 64 + 2 * lane], (double)a.x);
+            atomicAdd(&sacc[(cur - 1) * 64 + 2 * lane + 1], (double)a.y);
+        }
+        a = make_float2(0.f, 0.f);
+    };
+    for (int row = blockIdx.x * 8 + warp; row < D * H; row += gridDim.x * 8) {
+        const int d = row / H, h = row - d * H;
+        const uint8_t* lrow = labels + (long long)row * W;
+        const float2* frow = feats + ((((long long)n * Dp + d) * Hp + h) * Wp) * 32;
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const int lab = (w0 + lane < W) ? (int)lrow[w0 + lane] : 0;
+            unsigned m = __ballot_sync(0xffffffffu, lab != 0);
+            while (m) {
+                int ix[4], cnt = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ix[q] = 0;
+                    if (m) { ix[q] = __ffs(m) - 1; m &= m - 1; ++cnt; }
+                }
+                float2 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    v[q] = q < cnt ? __ldg(frow + (long long)(w0 + ix[q]) * 32 + lane) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int l = __shfl_sync(0xffffffffu, lab, ix[q]);
+                    if (q < cnt) {
+                        if (l != cur) { flush(); cur = l; }
+                        a.x += v[q].x; a.y += v[q].y;
+                    }
+                }
+            }
+        }
+    }
+    flush();
+    __syncthreads();
+    double* dst = acc + (long long)n * R * 64;
+    for (int i = threadIdx.x; i < R * 64; i += 256)
+        if (sacc[i] != 0.0) atomicAdd(&dst[i], sacc[i]);
+}
+__global__ void __launch_bounds__(256) roi_cl_finalize_kernel(const double* __restrict__ acc, const int32_t* __restrict__ counts,
+                                                              float* __restrict__ mean, long long total, int R) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = (int)((i >> 6) % R);
+    mean[i] = (float)acc[i] / fmaxf((float)__ldg(&counts[r]), 1e-6f);
+}
+
+// ------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------
 struct Binding {
@@ -424,6 +491,9 @@ struct mmad_roi_plan {
     long long out_cap = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // channels-last pooling (mmad_roi_pool_ndhwc_f32): double accumulators [n_vols][R][64]
+    double* d_cl_acc = nullptr;
+    long long cl_cap = 0;
 };
 
 namespace mmad {
@@ -542,6 +612,12 @@ static int get_binding(mmad_roi_plan* pl, long long n_vols, Binding** out) {
         b->release();
         delete b;
         return fail(MMAD_ECUDA, std::string("roi binding upload: ") + cudaGetErrorString(e));
+    }
+    if (pl->bindings.size() >= 16) {                       // bounded cache: drop the oldest batch size (cudaFree waits for its kernels)
+        auto old = pl->bindings.begin();
+        old->second->release();
+        delete old->second;
+        pl->bindings.erase(old);
     }
     pl->bindings[n_vols] = b;
     *out = b;
@@ -672,7 +748,7 @@ int mmad_roi_plan_destroy(mmad_roi_plan* pl) {
     for (auto& kv : pl->bindings) { kv.second->release(); delete kv.second; }
     cudaFree(pl->d_prog); cudaFree(pl->d_prog_off); cudaFree(pl->d_labels); cudaFree(pl->d_counts);
     cudaFree(pl->d_stage[0]); cudaFree(pl->d_stage[1]);
-    cudaFree(pl->d_omean); cudaFree(pl->d_omax); cudaFree(pl->d_oarg);
+    cudaFree(pl->d_omean); cudaFree(pl->d_omax); cudaFree(pl->d_oarg); cudaFree(pl->d_cl_acc);
     for (int i = 0; i < 2; ++i) {
         if (pl->ev_copied[i]) cudaEventDestroy(pl->ev_copied[i]);
         if (pl->ev_done[i]) cudaEventDestroy(pl->ev_done[i]);
@@ -716,6 +792,43 @@ int mmad_roi_pool_mean_backward_f32(mmad_roi_plan* pl, const float* grad_mean_de
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)pl->sms * 16);
     roi_mean_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grad_mean_dev, pl->d_labels, pl->d_counts, pl->V, pl->R,
                                                                 n_vols, grad_vols_dev);
+    MMAD_CUDA(cudaGetLastError());
+    count_launch();
+    return MMAD_OK;
+}
+
+// Channels-last pooling of a convolution output that never left the GPU (see roi_cl_pool_kernel).
+int mmad_roi_pool_ndhwc_f32(mmad_roi_plan* pl, const float* feats_dev, int64_t n_vols, int Dp, int Hp, int Wp, int D, int H, int W,
+                            int C, float* mean_dev, void* stream) {
+    MMAD_CHECK_ARG(pl && pl->d_labels, "roi_pool_ndhwc: null or host-only plan");
+    MMAD_CHECK_ARG(n_vols >= 0, "roi_pool_ndhwc: n_vols < 0");
+    if (n_vols == 0) return MMAD_OK;
+    MMAD_CHECK_ARG(feats_dev && mean_dev, "roi_pool_ndhwc: null pointer");
+    MMAD_CHECK_ARG(C == 64, "roi_pool_ndhwc: the channels-last kernel pools 64-channel feature maps (s_block1.conv2)");
+    MMAD_CHECK_ARG((long long)D * H * W == pl->V && D <= Dp && H <= Hp && W <= Wp && D > 0 && H > 0 && W > 0,
+                   "roi_pool_ndhwc: the atlas grid must match the plan and lie inside the feature grid");
+    MMAD_CHECK_ARG((reinterpret_cast<uintptr_t>(feats_dev) & 7) == 0, "roi_pool_ndhwc: features must be 8-byte aligned");
+    const size_t smem = (size_t)pl->R * 64 * sizeof(double);
+    MMAD_CHECK_ARG(smem <= (size_t)kMaxSmem, "roi_pool_ndhwc: too many ROIs for the shared accumulators");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long need = (long long)n_vols * pl->R * 64;
+    if (need > pl->cl_cap) {
+        cudaFree(pl->d_cl_acc);
+        pl->d_cl_acc = nullptr; pl->cl_cap = 0;
+        MMAD_CUDA(cudaMalloc((void**)&pl->d_cl_acc, (size_t)need * sizeof(double)));
+        pl->cl_cap = need;
+    }
+    MMAD_CUDA(cudaMemsetAsync(pl->d_cl_acc, 0, (size_t)need * sizeof(double), st));
+    static DevOnce attr_done;
+    if (attr_done.need()) MMAD_CUDA(cudaFuncSetAttribute(roi_cl_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    const int per_sm = std::max(1, std::min(2, (int)((size_t)kMaxSmem / (smem + 1024))));
+    const long long lines = ((long long)D * H + 7) / 8;
+    const int gx = (int)std::max<long long>(1, std::min<long long>(lines, ((long long)pl->sms * per_sm + n_vols - 1) / n_vols));
+    roi_cl_pool_kernel<<<dim3(gx, (unsigned)n_vols), 256, smem, st>>>(reinterpret_cast<const float2*>(feats_dev), pl->d_labels, pl->d_cl_acc,
+                                                                   Dp, Hp, Wp, D, H, W, pl->R);
+    MMAD_CUDA(cudaGetLastError());
+    count_launch();
+    roi_cl_finalize_kernel<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(pl->d_cl_acc, pl->d_counts, mean_dev, need, pl->R);
     MMAD_CUDA(cudaGetLastError());
     count_launch();
     return MMAD_OK;

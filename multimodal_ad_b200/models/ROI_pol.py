@@ -135,6 +135,27 @@ class RoiPlan:
         v = vols.reshape(-1, self.n_voxels) if vols.numel() else vols.reshape(0, self.n_voxels)
         return v.contiguous()
 
+    def pool_channels_last(self, feats: torch.Tensor, atlas_shape) -> torch.Tensor:
+        """ROI means of a channels-last feature map that never left the GPU.
+
+        feats: (N, Dp, Hp, Wp, 64) float32 CUDA, NDHWC contiguous - the fp32 side output the convolution epilogue writes for
+        the layer image_features.py:58-60 hooks; atlas_shape (D, H, W) <= (Dp, Hp, Wp) is the plan's label grid (the crop of
+        image_features.py:104 is folded into the kernel).  Returns roi_feat (N, R, 64) = image_features.py:114."""
+        if self.host_only:
+            raise _lib.MmadError("host-only plan cannot run kernels")
+        if not isinstance(feats, torch.Tensor) or not feats.is_cuda:
+            raise _lib.MmadError("ROI pooling runs on CUDA tensors only (no CPU fallback)")
+        if feats.dtype != torch.float32 or feats.dim() != 5 or not feats.is_contiguous():
+            raise TypeError("pool_channels_last expects a contiguous float32 (N, Dp, Hp, Wp, C) tensor")
+        n, dp, hp, wp, c = feats.shape
+        d, h, w = (int(t) for t in atlas_shape)
+        out = torch.empty((n, self.n_rois, c), dtype=torch.float32, device=feats.device)
+        with torch.cuda.device(feats.device):
+            st = c_void_p(torch.cuda.current_stream(feats.device).cuda_stream)
+            _lib.check(_lib.load().mmad_roi_pool_ndhwc_f32(self._h, c_void_p(feats.data_ptr()), n, dp, hp, wp, d, h, w, c,
+                                                           c_void_p(out.data_ptr()), st), "mmad_roi_pool_ndhwc_f32")
+        return out
+
     def pool(self, vols: torch.Tensor, want_max: bool = True):
         """vols (N, V) float32 CUDA -> mean (N, R), max (N, R), argmax (N, R) int32 (max/argmax None if not wanted)."""
         v = self._check_vols(vols)
