@@ -221,11 +221,13 @@ def run_resnet_train(args, rank, world, dev, dist, *, depth=18, batch=RESNET_BAT
         step(i)
     torch.cuda.synchronize()
 
-    # Single GPU: the whole step (our launches + the torch loss / clip / Adam kernels) is captured once into a CUDA graph
-    # and replayed, so the step time does not depend on the host's launch rate (eager enqueue costs 8-11 ms per step).
-    # The eager step is kept when capture is unavailable and under data parallel (NCCL collectives stay eager).
+    # The whole step (our launches, the torch loss / clip / Adam kernels and - under data parallel - the NCCL all-reduces the
+    # GradReducer issues on its side stream) is captured once into a CUDA graph and replayed, so the step time does not depend
+    # on the host's launch rate (eager enqueue costs 8-11 ms per step) and every N runs in the same launch mode.  Falls back to
+    # the eager step when capture is unavailable (MMAD_BENCH_DP_GRAPH=0 keeps data parallel eager).
     graph, graph_note, graph_launches = None, "eager", 0
-    if world == 1 and not getattr(args, "no_graph", False):
+    want_graph = not getattr(args, "no_graph", False) and (world == 1 or os.environ.get("MMAD_BENCH_DP_GRAPH", "1") != "0")
+    if want_graph:
         try:
             sx, sy = xs[0].clone(), ys[0].clone()
             opt.zero_grad(set_to_none=True)
@@ -234,14 +236,15 @@ def run_resnet_train(args, rank, world, dev, dist, *, depth=18, batch=RESNET_BAT
             with torch.cuda.graph(graph):
                 gloss = crit(model(sx), sy)
                 gloss.backward()
+                reducer.finish(model.parameters())
                 torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
                 opt.step()
             graph_launches = _lib.launch_count() - c0
             graph.replay()
             torch.cuda.synchronize()
-            graph_note = "cuda graph replay"
+            graph_note = "cuda graph replay" + (" (NCCL all-reduces captured)" if world > 1 else "")
         except Exception as e:                             # noqa: BLE001 - any capture problem falls back to the eager step
-            graph, graph_note = None, f"eager (graph capture failed: {type(e).__name__})"
+            graph, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:80]})"
             torch.cuda.synchronize()
             opt.zero_grad(set_to_none=True)
 
@@ -563,6 +566,129 @@ def run_roi_pool(args, rank, world, dev, dist, steps, warmup, want_cpu):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# UNet3D forward + on-device ROI features (configs[4]'s image branch; image_features.py:97-114)
+# ---------------------------------------------------------------------------------------------------------------------
+def unet3d_forward_flops(grid=(96, 112, 96)):
+    """Algorithmic FLOPs of one UNet3D(1, 1) forward on one volume (unet3d.py:100-113 channel plan on the padded grid)."""
+    v0 = grid[0] * grid[1] * grid[2]
+    v = [v0, v0 // 8, v0 // 64, v0 // 512]
+    f = 0.0
+    enc = [(1, 32, 64), (64, 64, 128), (128, 128, 256), (256, 256, 512)]
+    for lvl, (cin, mid, cout) in enumerate(enc):
+        f += 2.0 * v[lvl] * 27 * (cin * mid + mid * cout)
+    for lvl, (cup, cres) in ((2, (512, 256)), (1, (256, 128)), (0, (128, 64))):
+        f += 2.0 * v[lvl] * cup * cup                      # transposed convolution: one tap per output voxel
+        mid = cup // 2
+        f += 2.0 * v[lvl] * 27 * ((cup + cres) * mid + mid * mid)
+    f += 2.0 * v0 * 64
+    return f
+
+
+def unet_cpu_reference(seconds_cap=40.0):
+    """CPU leg for the extraction path: oracle UNet3D forward (pinned bit-exact to models/unet3d.py) in eval mode + the ROI means of
+    the hooked tensor, one 1x91x109x91 volume per pass, fp32 on the host cores.  The reference's own pooling expression
+    (image_features.py:111-114) would materialise a (1,170,64,91,109,91) product = 39 GB per volume for this 64-channel map;
+    the per-ROI restatement (oracle/unet_oracle.py, pinned to that expression on small cases) is timed instead."""
+    import torch
+
+    from multimodal_ad_b200.models import unet3d
+    from oracle.roi_oracle import synthetic_atlas
+    from oracle.unet_oracle import roi_features_oracle, unet3d_oracle
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in unet3d.UNet3D(1, 1).state_dict().items()}
+    lab = synthetic_atlas(SHAPE, N_ROIS)
+    x = torch.rand((1, 1) + SHAPE)
+    t0 = time.perf_counter()
+    n = 0
+    with torch.no_grad():
+        while n < 1 or time.perf_counter() - t0 < seconds_cap / 2:
+            hooked = {}
+            unet3d_oracle(sd, x, False, hooked=hooked)
+            roi_features_oracle(hooked["s_block1.conv2"], lab, N_ROIS)
+            n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} single-volume pass(es) of the UNet3D forward (eval, fp32) + ROI means of the 64-channel map on the host cores"}
+
+
+def run_unet_roi_extract(args, rank, world, dev, dist, batch=8, steps=10, want_cpu=False):
+    """image_features.py:97-114 on the accelerated path: UNet3D(1, 1).eval() forward on batch `batch` of 1x91x109x91 volumes, the
+    64-channel s_block1.conv2 map pooled over a 170-label atlas without leaving the GPU; subject-sharded across ranks."""
+    import torch
+
+    from multimodal_ad_b200 import RoiPlan, _lib
+    from multimodal_ad_b200.models import unet3d
+    from multimodal_ad_b200.sharding import max_over_ranks
+    from oracle.roi_oracle import synthetic_atlas                       # label-map generator only
+
+    torch.manual_seed(0)
+    model = unet3d.UNet3D(in_channels=1, num_classes=1).to(dev).eval()
+    plan = RoiPlan(synthetic_atlas(SHAPE, N_ROIS), N_ROIS)
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    xs = [torch.rand((batch, 1) + SHAPE, device=dev, generator=g) for _ in range(2)]
+
+    def step(x):
+        with torch.no_grad():
+            return model.roi_features(x, plan)
+
+    for i in range(3):
+        step(xs[i % 2])
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    f0, l0 = _lib.executed_mma_flops(), _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(xs[i % 2])
+    b.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b), dev) / steps
+    executed = (_lib.executed_mma_flops() - f0) / steps
+    launches = _lib.launch_count() - l0
+    # end to end: pinned host volumes in, network output + ROI features back on the host every step
+    xh = torch.rand((batch, 1) + SHAPE).pin_memory()
+    oh = torch.empty((batch, 1) + SHAPE).pin_memory()
+    rh = torch.empty((batch, N_ROIS, 64)).pin_memory()
+    xd = torch.empty((batch, 1) + SHAPE, device=dev)
+    torch.cuda.synchronize()
+    n_e2e = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        xd.copy_(xh, non_blocking=True)
+        out, roi = step(xd)
+        oh.copy_(out, non_blocking=True)
+        rh.copy_(roi, non_blocking=True)
+        torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, dev)
+    flops = unet3d_forward_flops() * batch
+    peak, peak_src = tensor_peak()
+    ach = flops / (ms * 1e-3) / 1e12
+    res = {
+        "metric": "unet3d_roi_extract_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms,
+        "steps": steps, "dtype": "bf16", "scaling": "weak",
+        "config": {"workload": "unet3d_eval_forward_plus_roi_mean_170labels_batch8_1x91x109x91 (image_features.py:97-114)",
+                   "batch_per_gpu": batch, "volume": list(SHAPE), "padded_grid": [96, 112, 96],
+                   "parallelism": f"subject-sharded x{world}, no collective", "launch": "eager"},
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_flops_per_step": flops, "executed_flops_per_step": executed,
+                     "executed_frac": executed / (ms * 1e-3) / 1e12 / peak},
+        "e2e": {"value": world * batch * n_e2e / dt, "unit": "volumes/s", "h2d_bytes_per_step": batch * SHAPE[0] * SHAPE[1] * SHAPE[2] * 4,
+                "d2h_bytes_per_step": batch * (SHAPE[0] * SHAPE[1] * SHAPE[2] + N_ROIS * 64) * 4, "steps": n_e2e},
+        "gpu_launches": launches,
+    }
+    if want_cpu:
+        res["cpu_baseline"] = unet_cpu_reference()
+    del model, xs, plan
+    torch.cuda.empty_cache()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # arms
 # ---------------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank: int):
@@ -625,6 +751,8 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
             args, rank, world, dev, dist, depth=50, batch=8, nb_class=2, steps=min(args.steps, 8), warmup=3, do_e2e=False,
             workload="resnet3d50_bottleneck_bf16_train_batch8_1x128^3 (cfg_denseNet.json: model_type resnet, depth 50)",
             metric="resnet3d50_train_volumes_per_sec"))
+        guarded("unet3d_roi_extract", lambda: run_unet_roi_extract(args, rank, world, dev, dist, steps=min(args.steps, 10),
+                                                                   want_cpu=solo and not args.no_cpu_baseline))
         if solo:
             guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev))
     cpu_baseline = None
