@@ -36,7 +36,8 @@ def load() -> ctypes.CDLL:
             raise
     if not os.path.exists(_LIB_PATH):
         raise MmadError(f"CUDA library not found at {_LIB_PATH}; run python -m multimodal_ad_b200.build")
-    lib = ctypes.CDLL(_LIB_PATH)
+    # MMAD_LIB: load another build of the same ABI instead (A/B measurements of kernel changes; tools/ only)
+    lib = ctypes.CDLL(os.environ.get("MMAD_LIB") or _LIB_PATH)
 
     lib.mmad_last_error.restype = c_char_p
     lib.mmad_last_error.argtypes = []

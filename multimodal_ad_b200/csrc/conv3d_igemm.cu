@@ -36,6 +36,7 @@ struct ConvGeom {
     int tw, th, td, tn;           // output tile box (tn samples deep), tw*th*td*tn == 128, powers of two
     int lw, lh, ltd;              // log2(tw), log2(th), log2(td)
     int epi;                      // 1: the epilogue applies ConvEpi (per-channel affine / ReLU / fp32 side output)
+    int dyn;                      // 1: tiles are drawn from the global counter (dynamic scheduler), 0: static stride
     int tiles_w, tiles_h, tiles_d, tiles_n, m_tiles, n_tiles;   // tile index: sample tile fastest, then w, h, d
     int kc;                       // Cin / 64
     int stages;
@@ -70,8 +71,17 @@ struct ConvEpi {
     int relu;
 };
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 288;          // 9 warps: 0, 2, 3 TMA producers, 1 MMA issuer, 4-7 epilogue, 8 tile scheduler
 constexpr int kConvProducers = 3;          // warps 0, 2, 3
+// Dynamic tile scheduler.  The kernels are persistent (one CTA or CTA pair per SM), but WHICH tiles a CTA computes is decided
+// at run time: warp 8 draws tile indices from a global counter (atomicAdd) and hands them to the other roles through a small
+// shared-memory ring (sched_tile[] + full / empty mbarriers), a few tiles ahead of the consumers.  A CTA that starts late -
+// because another kernel (a weight-gradient GEMM on the side stream, an NCCL all-reduce) still holds its SM - simply finds fewer
+// tiles left, and tiles that skip padding taps no longer unbalance a static stride.  g.dyn == 0 keeps the static assignment
+// (tile = blockIdx.x + k * gridDim.x) through the same ring.  The counter pair {next, done} resets itself: the last CTA to
+// leave zeroes it, so a launch (or a CUDA-graph replay of it) always finds it at zero.
+constexpr int kSchedSlots = 2;
+constexpr int kSchedConsumers = 8;         // 3 producer warps + MMA warp + 4 epilogue warps arrive on a slot's empty barrier
 // A producer re-enters the ring every nprod stages and waits on a PARITY, so it must never be two phases ahead of a
 // slot: that needs stages >= active producers (nprod = min(kConvProducers, stages)).
 constexpr int kATileBytes = 128 * 128;     // 128 voxels x 64 bf16
@@ -114,7 +124,8 @@ __device__ __forceinline__ void conv_epilogue_affine(uint32_t (&v)[32], int cb, 
 template <int BN, int KS, bool WH = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep) {
+                    const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
+                    unsigned int* __restrict__ sched_counter) {
     pdl_launch_dependents();
     static_assert(!WH || KS == 3, "the W-halo variant stages the three kw taps of one (kd, kh) pair");
     constexpr int B_TILE = BN * 128;
@@ -131,10 +142,12 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t stage0 = base;
     const uint32_t out0 = base + (uint32_t)S * STAGE;      // nout x 16 KB epilogue staging
     unsigned char* tail = sm + (size_t)S * STAGE + (size_t)g.nout * kStageOutBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);    // full[S], empty[S], tfull[2], tempty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);    // full[S], empty[S], tfull[2], tempty[2], sfull[4], sempty[4]
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);     // [2][Cout] (two row halves)
+    const uint32_t sfull0 = tempty0 + 16, sempty0 = sfull0 + 8 * kSchedSlots;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * kSchedSlots);
+    volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_ptr_s + 4);   // [kSchedSlots]
+    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 8);     // [2][Cout] (two row halves)
     float* st_sq = st_sum + 2 * g.Cout;                           // [2][Cout]
     float* ep_sc = st_sq + 2 * g.Cout;                            // epilogue scale / shift / fp32 bias, [Cout] each (only when g.epi)
     float* ep_sh = ep_sc + g.Cout;
@@ -145,6 +158,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < kSchedSlots; ++a) { mbar_init(sfull0 + 8 * a, 1); mbar_init(sempty0 + 8 * a, kSchedConsumers); }
         mbar_fence_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
     }
@@ -159,40 +173,71 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int total_tiles = g.m_tiles * g.n_tiles;
     const int taps = g.kd * g.kh * g.kw;
     const int ksteps = taps * g.kc;
+    // consumer side of the tile ring: every role warp walks the same sequence of tile indices (>= total_tiles: no more work)
+    uint32_t sc_slot = 0, sc_ph = 0;
+    auto next_tile = [&]() -> int {
+        mbar_wait(sfull0 + 8 * sc_slot, sc_ph);
+        const int t = sched_tile[sc_slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty0 + 8 * sc_slot);
+        if (++sc_slot == kSchedSlots) { sc_slot = 0; sc_ph ^= 1; }
+        return t;
+    };
 
-    if (warp == 0 || warp == 2 || warp == 3) {
+    if (warp == 8) {
+        // ============================ tile scheduler ============================
+        uint32_t slot = 0, ph = 0;
+        for (int k = 0;; ++k) {
+            mbar_wait(sempty0 + 8 * slot, ph ^ 1);
+            int t = 0;
+            if (lane == 0) {
+                t = g.dyn ? (int)atomicAdd(sched_counter, 1u) : (int)blockIdx.x + k * (int)gridDim.x;
+                sched_tile[slot] = t;
+                mbar_arrive(sfull0 + 8 * slot);             // release: the tile index is visible to the waiters
+            }
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total_tiles) break;
+            if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
+        }
+    } else if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: stage i is issued by producer i % 3 ============================
         if (WH) {
-            // W-halo variant: 9 stages per tile, one per (kd, kh); 3 producers, 4 ring slots (host guarantees it).  Producer
+            // W-halo variant: 9 x (Cin / 64) stages per tile, one per (kd, kh, channel slab); 3 producers, 4 ring slots (host guarantees it).  Producer
             // `me` owns kh == me of every kd, i.e. every third stage of the global stage sequence: no per-tap loop overhead in
             // these single-thread loops, which otherwise cost more than the 384 MMA cycles of a stage.
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t G = me;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (;;) {
+                const int tile = next_tile();
+                if (tile >= total_tiles) break;
                 int r = tile;                               // n_tiles == 1 (Cout == 64), tn == 1
                 const int n = r % g.tiles_n; r /= g.tiles_n;
                 const int wt = r % g.tiles_w; r /= g.tiles_w;
                 const int ht = r % g.tiles_h; r /= g.tiles_h;
                 const int dt = r;
                 const int w0 = wt * 8 - 1, h0 = ht * 4 - 1 + (int)me, d0 = dt * 4 - 1;
-#pragma unroll
-                for (int a = 0; a < 3; ++a, G += 3) {
-                    const uint32_t s = G & 3u, ph = (G >> 2) & 1u;
-                    const uint32_t sa = stage0 + s * STAGE;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)STAGE);
-                        tma_load_3d(sa + A_REGION, &tmB, full0 + 8 * s, 0, 0, (a * 3 + (int)me) * 3);
-                        tma_load_5d(sa, &tmA, full0 + 8 * s, 0, w0, h0, d0 + a, n);
+                // stage order (kd, 64-channel slab, kh): kh stays the fastest index, so producer `me` keeps kh == me; the weight
+                // box {64 ci, 64 co, 1 slab, 3 kw taps} of the 4-D weight view lands as three consecutive K-major B tiles
+                for (int a = 0; a < 3; ++a)
+                    for (int cc = 0; cc < g.kc; ++cc, G += 3) {
+                        const uint32_t s = G & 3u, ph = (G >> 2) & 1u;
+                        const uint32_t sa = stage0 + s * STAGE;
+                        mbar_wait(empty0 + 8 * s, ph ^ 1);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)STAGE);
+                            tma_load_4d(sa + A_REGION, &tmB, full0 + 8 * s, 0, 0, cc, (a * 3 + (int)me) * 3);
+                            tma_load_5d(sa, &tmA, full0 + 8 * s, cc * 64, w0, h0, d0 + a, n);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
-                }
             }
         } else {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (;;) {
+                const int tile = next_tile();
+                if (tile >= total_tiles) break;
                 const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
                 int r = mt;
                 const int n = (r % g.tiles_n) * g.tn; r /= g.tiles_n;
@@ -241,7 +286,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ============================ MMA issuer (whole warp walks the loop, one elected lane issues) ============================
         {
             uint32_t s = 0, ph = 0, it = 0, nmma = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (;; ++it) {
+                const int tile = next_tile();
+                if (tile >= total_tiles) break;
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // epilogue has drained this accumulator
                 tc_fence_after();
@@ -284,7 +331,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 128u * BN * 16u);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ============================ epilogue: TMEM -> bf16 -> smem -> TMA store (+ BN statistics) ============================
         const int ew = warp - 4;                                  // == warp % 4: the TMEM lane quarter this warp may read
         const int et = threadIdx.x - 128;                         // 0..127
@@ -298,7 +345,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             named_bar_sync(2, 128);
         }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (;; ++it) {
+            const int tile = next_tile();
+            if (tile >= total_tiles) break;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const int nt = tile % g.n_tiles, mt = tile / g.n_tiles;
             int r = mt;
@@ -381,6 +430,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (g.dyn && threadIdx.x == 0) {
+        // every CTA has drawn its last (out-of-range) index by now; the last one to leave re-arms the counter pair
+        if (atomicAdd(sched_counter + 1, 1u) == gridDim.x - 1) { sched_counter[0] = 0u; sched_counter[1] = 0u; __threadfence(); }
+    }
 }
 
 // ===============================================================================================================
@@ -393,7 +446,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ===============================================================================================================
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                         const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep) {
+                         const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
+                         unsigned int* __restrict__ sched_counter) {
     pdl_launch_dependents();
     constexpr int BN = 256;
     constexpr int B_HALF = (BN / 2) * 128;
@@ -411,8 +465,10 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     unsigned char* tail = sm + (size_t)S * STAGE + (size_t)g.nout * kStageOutBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 4);
+    const uint32_t sfull0 = tempty0 + 16, sempty0 = sfull0 + 8 * kSchedSlots;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * kSchedSlots);
+    volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_ptr_s + 4);   // [kSchedSlots]
+    float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 8);
     float* st_sq = st_sum + 2 * g.Cout;
     float* ep_sc = st_sq + 2 * g.Cout;
     float* ep_sh = ep_sc + g.Cout;
@@ -425,6 +481,8 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
+        // tile ring: the leader's scheduler fills the slot in BOTH CTAs; the consumers of both CTAs release the LEADER's slot
+        for (int a = 0; a < kSchedSlots; ++a) { mbar_init(sfull0 + 8 * a, 1); mbar_init(sempty0 + 8 * a, 2 * kSchedConsumers); }
         mbar_fence_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmC);
     }
@@ -441,6 +499,17 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int total_super = m_super * g.n_tiles;
     const int taps = g.kd * g.kh * g.kw;
     const int ksteps = taps * g.kc;
+
+    // consumer side of the tile ring (see the single-CTA kernel): super-tile indices, the same sequence in both CTAs
+    uint32_t sc_slot = 0, sc_ph = 0;
+    auto next_tile = [&]() -> int {
+        mbar_wait_cluster(sfull0 + 8 * sc_slot, sc_ph);
+        const int t = sched_tile[sc_slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(sempty0 + 8 * sc_slot, 0);
+        if (++sc_slot == kSchedSlots) { sc_slot = 0; sc_ph ^= 1; }
+        return t;
+    };
 
     // tap validity of a super tile = union over its two voxel tiles (both CTAs and the MMA issuer must agree)
     auto super_masks = [&](int mp, uint32_t& mw, uint32_t& mh, uint32_t& md) {
@@ -460,13 +529,34 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     };
 
-    if (warp == 0 || warp == 2 || warp == 3) {
+    if (warp == 8) {
+        // ============================ tile scheduler: leader CTA only, publishes to both CTAs ============================
+        if (leader) {
+            uint32_t slot = 0, ph = 0;
+            for (int k = 0;; ++k) {
+                mbar_wait_cluster(sempty0 + 8 * slot, ph ^ 1);
+                int t = 0;
+                if (lane == 0) {
+                    t = g.dyn ? (int)atomicAdd(sched_counter, 1u) : pair + k * n_pairs;
+                    sched_tile[slot] = t;
+                    st_shared_remote_u32(smem_u32(const_cast<int*>(sched_tile + slot)), 1, (uint32_t)t);
+                    mbar_arrive(sfull0 + 8 * slot);
+                    mbar_arrive_remote(sfull0 + 8 * slot, 1);      // release.cluster: the peer sees the index written above
+                }
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= total_super) break;
+                if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers (in both CTAs) ============================
         {
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
-            for (int st = pair; st < total_super; st += n_pairs) {
+            for (;;) {
+                const int st = next_tile();
+                if (st >= total_super) break;
                 const int nt = st % g.n_tiles, mp = st / g.n_tiles;
                 int r = 2 * mp + (int)rank;                 // this CTA's voxel tile (may be the phantom tile past the end:
                 const int n = (r % g.tiles_n) * g.tn; r /= g.tiles_n;   // its d index is >= tiles_d, every box is out of bounds -> zeros)
@@ -499,10 +589,14 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ============================ MMA issuer: leader CTA only ============================
-        if (leader) {
+        // ============================ MMA issuer: leader CTA only (the peer's warp 1 still walks the tile ring) ============================
+        if (!leader) {
+            while (next_tile() < total_super) {}
+        } else {
             uint32_t s = 0, ph = 0, it = 0, nmma = 0;
-            for (int st = pair; st < total_super; st += n_pairs, ++it) {
+            for (;; ++it) {
+                const int st = next_tile();
+                if (st >= total_super) break;
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // both epilogues have drained this accumulator
                 tc_fence_after();
@@ -530,7 +624,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 256u * 256u * 16u);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ============================ epilogue (in both CTAs): own 128 accumulator rows ============================
         const int ew = warp - 4;
         const int et = threadIdx.x - 128;
@@ -544,7 +638,9 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             named_bar_sync(2, 128);
         }
-        for (int st = pair; st < total_super; st += n_pairs, ++it) {
+        for (;; ++it) {
+            const int st = next_tile();
+            if (st >= total_super) break;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const int nt = st % g.n_tiles, mp = st / g.n_tiles;
             const int mt = 2 * mp + (int)rank;
@@ -628,6 +724,9 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc_fence_before();
     cluster_sync_all();                                     // nobody frees TMEM / exits while the peer may still signal it
     if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    if (g.dyn && threadIdx.x == 0) {
+        if (atomicAdd(sched_counter + 1, 1u) == gridDim.x - 1) { sched_counter[0] = 0u; sched_counter[1] = 0u; __threadfence(); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -675,14 +774,43 @@ static void pick_tile(int N, int D, int H, int W, int Wo, int Ho, int Do, int k,
 
 static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false, bool epi = false) {
     const int a_region = halo ? kHaloTileBytes : ks * kATileBytes;
-    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4) * 8 + 16 + (epi ? 7 : 4) * cout * 4;
+    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4 + 2 * kSchedSlots) * 8 + 32 +
+           (epi ? 7 : 4) * cout * 4;
+}
+
+// {next, done} counter pairs of the dynamic tile scheduler: a pool per device, one pair per launch (round robin - two kernels
+// that may be in flight together, e.g. on the main and the weight-gradient stream, never share a pair); zeroed once, then
+// every kernel leaves its pair at zero.  Allocated on first use (before any CUDA-graph capture: capture follows warm-up).
+constexpr int kSchedPool = 4096;
+static unsigned int* sched_counter_slot() {
+    static unsigned int* pool[64] = {};
+    static std::atomic<unsigned> next{0};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    dev &= 63;
+    if (!pool[dev]) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool[dev]) {
+            unsigned int* p = nullptr;
+            if (cudaMalloc((void**)&p, kSchedPool * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+            if (cudaMemset(p, 0, kSchedPool * 2 * sizeof(unsigned int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+            pool[dev] = p;
+        }
+    }
+    return pool[dev] + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSchedPool);
+}
+static bool use_dynamic_scheduler() {                    // on unless MMAD_CONV_DYN=0
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("MMAD_CONV_DYN"); mode = e ? atoi(e) : 1; }
+    return mode != 0;
 }
 
 // W-halo variant (see the kernel): 3x3x3, unit stride, undilated, 64 -> 64 channels; on unless MMAD_CONV_HALO=0
 static bool use_halo_kernel(int Cin, int Cout, int k, int stride, int dil) {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("MMAD_CONV_HALO"); mode = e ? atoi(e) : 1; }
-    return mode != 0 && Cin == 64 && Cout == 64 && k == 3 && stride == 1 && dil == 1;
+    return mode != 0 && Cin % 64 == 0 && Cout == 64 && k == 3 && stride == 1 && dil == 1;
 }
 
 
@@ -788,7 +916,17 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         int rc = make_tmap_bf16(&tmA, x, 5, dims, str, box, es);
         if (rc) return rc;
     }
-    {
+    if (halo) {
+        // weights [Cout][taps][Cin] viewed as [64 ci][co][ci slab][tap]: a box of one slab x three consecutive taps (the kw taps of a
+        // (kd, kh) pair) lands as three consecutive canonical K-major B tiles
+        const int taps = kd * kh * kw;
+        const uint64_t dims[4] = {64, (uint64_t)Cout, (uint64_t)(Cin / 64), (uint64_t)taps};
+        const uint64_t str[3] = {(uint64_t)taps * Cin * 2, 128, (uint64_t)Cin * 2};
+        const uint32_t box[4] = {64, (uint32_t)bn_stage, 1, 3};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        int rc = make_tmap_bf16(&tmB, w, 4, dims, str, box, es);
+        if (rc) return rc;
+    } else {
         // weights [Cout][taps][Cin] viewed as [64 ci][co][K-slice]: K-slice = tap * (Cin/64) + ci block, 128 bytes apart, so a
         // box of KS consecutive K-slices lands as KS consecutive canonical K-major B tiles
         const int taps = kd * kh * kw;
@@ -812,13 +950,19 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* sched = nullptr;
+    g.dyn = use_dynamic_scheduler() ? 1 : 0;
+    if (g.dyn) {
+        sched = sched_counter_slot();
+        if (!sched) return fail(MMAD_ECUDA, "conv3d_fwd: cannot allocate the tile-scheduler counters");
+    }
     if (pairk) {
         static DevOnce attr_done;
         if (attr_done.need()) {
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
-        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep);
+        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
@@ -830,7 +974,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         if (attr_done.need()) {                                                                                                   \
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
         }                                                                                                                   \
-        launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep);           \
+        launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);    \
     } while (0)
     if (halo) MMAD_CONV_LAUNCH(64, 3, true);
     else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);

@@ -32,6 +32,8 @@ CONV_CASES = [
     # CTA-pair kernel (dilation 4), the single-CTA BN=256 kernel (one voxel tile) and BN=128; multi-tile BN=64 K-step groups
     (3, 23, 28, 23, 64, 64, 3, 1, 1, 1), (2, 16, 16, 16, 64, 256, 3, 1, 4, 4), (4, 8, 8, 8, 128, 512, 3, 1, 2, 2),
     (2, 4, 4, 4, 64, 256, 3, 1, 4, 4), (2, 16, 16, 16, 64, 128, 3, 1, 4, 4), (1, 1, 1, 40000, 128, 64, 1, 1, 0, 1),
+    # multi-slab W-halo kernel (Cin = 128 / 192 -> 64: the concatenated input of unet3d.py's s_block1.conv1), ragged grid
+    (2, 24, 28, 31, 128, 64, 3, 1, 1, 1), (1, 32, 32, 45, 192, 64, 3, 1, 1, 1),
 ]
 
 
