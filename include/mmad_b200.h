@@ -204,6 +204,14 @@ int mmad_stem_s2d_wgrad_reduce(const float* partials, int nsplit, float* dw, voi
 int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, float* stats_partials,
                             const float* ep_scale, const float* ep_shift, int ep_relu, float* out_f32, const float* f32_bias,
                             int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, void* stream);
+/* The tail of unet3d.py's eval-mode forward as one kernel: 3x3x3 convolution (padding 1) to 64 channels, the BatchNorm3d + ReLU
+ * that follow it (ep_scale / ep_shift), the 1x1x1 head (unet3d.py:72 conv3: head_w float[K][64], head_b float[K], K <= 8) and the
+ * crop back to (Dc,Hc,Wc) (unet3d.py:126-135) - the 64-channel activation is never written.  head_out fp32 (N,K,Dc,Hc,Wc);
+ * out_f32 (optional) receives the raw convolution output + f32_bias as fp32 NDHWC (N,D,H,W,64), the tensor
+ * image_features.py:58-60 hooks. */
+int mmad_conv3d_fwd_head_bf16(const void* x, const void* w, const float* ep_scale, const float* ep_shift,
+                              float* out_f32, const float* f32_bias, const float* head_w, const float* head_b, float* head_out,
+                              int K, int N, int D, int H, int W, int Dc, int Hc, int Wc, int Cin, void* stream);
 /* mmad_conv3d_wgrad_bf16 for an x that is the channel slice [c0, c0+Cin) of a wider NDHWC tensor (rows ldx elements apart, x
  * points at channel c0), and the matching reduction into dw[:, ci_off : ci_off+Cin] of a (Cout, Cin_total, k,k,k) tensor:
  * the weight gradient of a convolution over a concatenated input, computed per source. */
@@ -225,10 +233,13 @@ int mmad_convtranspose3d_k2s2_fwd_bf16(const void* x, const void* w_phases, cons
 /* First UNet layer (unet3d.py:37 a_block1.conv1 = Conv3d(1, 32, 3, padding 1) after the zero extension to 96x112x96 of
  * unet3d.py:116-123): direct convolution.  x fp32 (N,1,D,H,W); w fp32 (32,1,3,3,3); y bf16 (N,Do,Ho,Wo,64), (Do,Ho,Wo) >= (D,H,W),
  * channels 32..63 written as zeros (the next convolution reads 64-channel rows); no bias (add it through the BatchNorm
- * shift).  stats_partials float[mmad_conv3d_c1_blocks][64][2] like mmad_conv3d_fwd_bf16.  Weight gradient: partials
- * float[mmad_conv3d_c1_blocks][32][27], summed by mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27). */
+ * shift).  Training: stats_partials float[mmad_conv3d_c1_blocks][64][2] like mmad_conv3d_fwd_bf16 (ep_* NULL).  Eval:
+ * ep_scale / ep_shift float[32] fold BatchNorm3d + ReLU (and the bias) in, stored = relu(acc * scale[c] + shift[c])
+ * (stats_partials NULL).  Weight gradient: partials float[mmad_conv3d_c1_wgrad_blocks][32][27], summed by
+ * mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27). */
 int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo);
-int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials,
+int mmad_conv3d_c1_wgrad_blocks(int N, int Do, int Ho, int Wo);
+int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials, const float* ep_scale, const float* ep_shift,
                        int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);
 int mmad_conv3d_c1_wgrad(const float* x, const void* dy, float* partials,
                          int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);

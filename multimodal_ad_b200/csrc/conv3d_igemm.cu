@@ -62,6 +62,10 @@ __device__ __forceinline__ uint32_t tap_axis_mask(int o0, int tl, int extent, in
 //                                 a convolution bias (unet3d.py:37-40 / ConvTranspose3d :68), or - in eval mode - the whole
 //                                 BatchNorm3d + ReLU that follows the convolution, folded into the producing kernel.
 // The BatchNorm statistics (stats_partials) are always those of the STORED values.
+//   head_out[n][k][d][h][w]     = head_b[k] + sum_c bf16(stored value)[c] * head_w[k][c]  for voxels inside the crop (hD,hH,hW):
+//                                 a 1x1x1 convolution of the 64 output channels (unet3d.py:72 conv3) and the crop back of
+//                                 unet3d.py:126-135 folded into the epilogue (Cout == 64, single-CTA kernel); with y == NULL the
+//                                 activation itself is never written.
 struct ConvEpi {
     const float* scale;
     const float* shift;
@@ -69,7 +73,13 @@ struct ConvEpi {
     float* out_f32;
     long long f32_ld;
     int relu;
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+    int head_k, hD, hH, hW;
+    int nostore;
 };
+constexpr int kHeadMaxK = 8;
 
 constexpr int kConvThreads = 288;          // 9 warps: 0, 2, 3 TMA producers, 1 MMA issuer, 4-7 epilogue, 8 tile scheduler
 constexpr int kConvProducers = 3;          // warps 0, 2, 3
@@ -152,6 +162,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* ep_sc = st_sq + 2 * g.Cout;                            // epilogue scale / shift / fp32 bias, [Cout] each (only when g.epi)
     float* ep_sh = ep_sc + g.Cout;
     float* ep_fb = ep_sh + g.Cout;
+    float* ep_hw = ep_fb + g.Cout;                                // fused head weights [head_k][64] (only with ep.head_out)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -343,6 +354,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
                 ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
             }
+            if (ep.head_out)
+                for (int c = et; c < ep.head_k * 64; c += 128) ep_hw[c] = ep.head_w[c];
             named_bar_sync(2, 128);
         }
         for (;; ++it) {
@@ -364,18 +377,41 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
             mbar_wait(tfull0 + 8 * acc, aph);
             tc_fence_after();
+            float hacc[kHeadMaxK];
+#pragma unroll
+            for (int k = 0; k < kHeadMaxK; ++k) hacc[k] = 0.f;
             for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
                 const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
-                if (et == 0) {                                    // the store that last used this buffer has finished reading it
-                    if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                if (!ep.nostore) {
+                    if (et == 0) {                                // the store that last used this buffer has finished reading it
+                        if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                    }
+                    named_bar_sync(2, 128);
                 }
-                named_bar_sync(2, 128);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
                     if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
+                    if (BN == 64 && ep.head_out) {
+                        // 1x1x1 head on the values as they would be stored (rounded to bf16), fp32 accumulation
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))));
+#pragma unroll
+                        for (int k = 0; k < kHeadMaxK; ++k) {
+                            if (k < ep.head_k) {
+                                const float4* hw4 = reinterpret_cast<const float4*>(ep_hw + k * 64 + half * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 w4 = hw4[j];
+                                    hacc[k] = fmaf(__uint_as_float(v[4 * j]), w4.x, hacc[k]); hacc[k] = fmaf(__uint_as_float(v[4 * j + 1]), w4.y, hacc[k]);
+                                    hacc[k] = fmaf(__uint_as_float(v[4 * j + 2]), w4.z, hacc[k]); hacc[k] = fmaf(__uint_as_float(v[4 * j + 3]), w4.w, hacc[k]);
+                                }
+                            }
+                        }
+                    }
+                    if (ep.nostore) continue;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -388,6 +424,17 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      : "memory");
                     }
                 }
+                if (BN == 64 && ep.head_out && row_ok) {
+                    const int od = d0 + rdi, oh = h0 + rhi, ow = w0 + rwi;
+                    if (od < ep.hD && oh < ep.hH && ow < ep.hW) {
+#pragma unroll
+                        for (int k = 0; k < kHeadMaxK; ++k)
+                            if (k < ep.head_k)
+                                ep.head_out[(((long long)(n + rni) * ep.head_k + k) * ep.hD + od) * ((long long)ep.hH * ep.hW) + (long long)oh * ep.hW + ow] =
+                                    hacc[k] + __ldg(ep.head_b + k);
+                    }
+                }
+                if (ep.nostore) continue;
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
                 if (et == 0) {
@@ -775,7 +822,7 @@ static void pick_tile(int N, int D, int H, int W, int Wo, int Ho, int Do, int k,
 static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false, bool epi = false) {
     const int a_region = halo ? kHaloTileBytes : ks * kATileBytes;
     return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4 + 2 * kSchedSlots) * 8 + 32 +
-           (epi ? 7 : 4) * cout * 4;
+           (epi ? 7 : 4) * cout * 4 + (epi ? kHeadMaxK * 64 * 4 : 0);
 }
 
 // {next, done} counter pairs of the dynamic tile scheduler: a pool per device, one pair per launch (round robin - two kernels
@@ -850,7 +897,7 @@ struct ConvOut { int Do, Ho, Wo; long long sw, sh, sd, sn; int standard; };   //
 static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_partials, int N, int D, int H, int W, int Cin, int Cout,
                          int kd, int kh, int kw, int stride, int pad, int dil, const ConvOut* ov, void* stream, const ConvEpi* epi = nullptr) {
     const int k = std::max(kd, std::max(kh, kw));
-    MMAD_CHECK_ARG(x && w && y, "conv3d_fwd: null pointer");
+    MMAD_CHECK_ARG(x && w && (y || (epi && epi->head_out)), "conv3d_fwd: null pointer");
     MMAD_CHECK_ARG(N > 0 && D > 0 && H > 0 && W > 0, "conv3d_fwd: empty input");
     MMAD_CHECK_ARG(Cin % 64 == 0 && Cin >= 64, "conv3d_fwd: Cin must be a multiple of 64");
     MMAD_CHECK_ARG(Cout % 64 == 0 && Cout >= 64 && (Cout <= 256 || Cout % 256 == 0) && (Cout == 64 || Cout % 128 == 0) &&
@@ -873,7 +920,11 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     bool halo = false;
     ConvEpi ep = {};
     if (epi) ep = *epi;
-    g.epi = (ep.scale || ep.shift || ep.out_f32) ? 1 : 0;
+    g.epi = (ep.scale || ep.shift || ep.out_f32 || ep.head_out) ? 1 : 0;
+    ep.nostore = y ? 0 : 1;
+    MMAD_CHECK_ARG(!ep.head_out || (Cout == 64 && ep.head_w && ep.head_b && ep.head_k >= 1 && ep.head_k <= kHeadMaxK),
+                   "conv3d_fwd: the fused 1x1x1 head needs Cout == 64 and 1..8 classes");
+    MMAD_CHECK_ARG(!ep.nostore || !stats_partials, "conv3d_fwd: statistics need the stored output");
     MMAD_CHECK_ARG(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.f32_ld % 4 == 0), "conv3d_fwd: fp32 side output must be 16-byte aligned");
     if ((!ov || ov->standard) && kd == kh && kh == kw && pad == 1 && use_halo_kernel(Cin, Cout, k, stride, dil)) {
         // the halo variant needs 8 x 4 x 4 tiles; mmad_conv3d_stats_partials (which does not know Cin) sizes the statistics
@@ -946,7 +997,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         const uint64_t* str = (ov && ov->sw) ? strided : dense;
         const uint32_t box[5] = {64, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.td, (uint32_t)g.tn};
         const uint32_t es[5] = {1, 1, 1, 1, 1};
-        int rc = make_tmap_bf16(&tmC, y, 5, dims, str, box, es);
+        int rc = make_tmap_bf16(&tmC, y ? y : const_cast<void*>(x), 5, dims, str, box, es);   // y == NULL: never stored (fused head)
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -1008,6 +1059,17 @@ int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, 
     ov.sw = ld; ov.sh = ld * ov.Wo; ov.sd = ld * ov.Wo * ov.Ho; ov.sn = ld * ov.Wo * ov.Ho * ov.Do;
     ov.standard = 1;
     return conv_fwd_impl(x, w, y, stats_partials, N, D, H, W, Cin, Cout, k, k, k, stride, pad, dil, &ov, stream, &ep);
+}
+
+// 3x3x3 convolution (padding 1) to 64 channels + BatchNorm/ReLU epilogue + 1x1x1 head + crop, the activation never written:
+// the tail of unet3d.py's forward in eval mode (s_block1.conv2 -> bn -> relu -> conv3 -> _crop_back) as ONE kernel.
+// head_out fp32 (N, K, Dc, Hc, Wc); out_f32 (optional) = the raw convolution output + f32_bias, fp32 NDHWC (N, D, H, W, 64).
+int mmad_conv3d_fwd_head_bf16(const void* x, const void* w, const float* ep_scale, const float* ep_shift, float* out_f32,
+                              const float* f32_bias, const float* head_w, const float* head_b, float* head_out, int K, int N, int D, int H,
+                              int W, int Dc, int Hc, int Wc, int Cin, void* stream) {
+    MMAD_CHECK_ARG(head_w && head_b && head_out && Dc <= D && Hc <= H && Wc <= W && Dc > 0 && Hc > 0 && Wc > 0, "conv3d_fwd_head: bad argument");
+    ConvEpi ep = {ep_scale, ep_shift, f32_bias, out_f32, 64, 1, head_w, head_b, head_out, K, Dc, Hc, Wc, 1};
+    return conv_fwd_impl(x, w, nullptr, nullptr, N, D, H, W, Cin, 64, 3, 3, 3, 1, 1, 1, nullptr, stream, &ep);
 }
 
 // ConvTranspose3d(kernel 2, stride 2) forward (unet3d.py:68, :75): y[n][2v+p][co] = bias[co] + sum_ci x[n][v][ci] * w[ci][co][p]

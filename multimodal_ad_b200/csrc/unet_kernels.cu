@@ -34,22 +34,32 @@ __device__ __forceinline__ uint4 u_pack8(const float (&f)[8]) {
 // 27 x 32 weights are staged in shared memory; per-channel sum / sum of squares of the STORED bf16 values go to
 // stats_partials[block][64][2] (BatchNorm statistics, the same contract as mmad_conv3d_fwd_bf16).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kC1Tw = 8, kC1Th = 8, kC1Td = 4;
+constexpr int kC1Tw = 8, kC1Th = 8, kC1Td = 4;            // weight-gradient tile (one voxel per thread)
+constexpr int kF1Tw = 16, kF1Th = 8, kF1Td = 4;           // forward tile: 512 voxels, two W-neighbours per thread
+constexpr int kF1Sx = (kF1Td + 2) * (kF1Th + 2) * (kF1Tw + 2);
 
+// STATS: per-channel sum / sum of squares of the stored values (training).  EPI: stored = relu(acc * scale[c] + shift[c]) - in
+// eval mode the BatchNorm3d + ReLU that follow the convolution (and its bias) are folded in, the pre-activation is never written.
+// A thread computes two W-adjacent voxels x 32 channels: every weight vector fetched from shared memory (a broadcast LDS.128)
+// feeds 8 FMAs, so the kernel is bound by the FP32 pipe (864 FMAs per voxel), not by shared-memory traffic.
+template <bool STATS, bool EPI>
 __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt, uint4* __restrict__ y,
-                                                            float* __restrict__ stats_partials, int N, int D, int H, int W, int Do, int Ho,
+                                                            float* __restrict__ stats_partials, const float* __restrict__ ep_scale,
+                                                            const float* __restrict__ ep_shift, int N, int D, int H, int W, int Do, int Ho,
                                                             int Wo, int tiles_w, int tiles_h, int tiles_d) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float sw[27 * 32];
-    __shared__ float sx[6 * 10 * 10];
+    __shared__ __align__(16) float sw[27 * 32];
+    __shared__ float sx[kF1Sx];
     __shared__ float sred[64 * 2];
+    __shared__ __align__(16) float sep[64];                 // scale[32], shift[32]
     for (int i = threadIdx.x; i < 27 * 32; i += 256) sw[i] = wgt[(i & 31) * 27 + (i >> 5)];      // [tap][co]
     if (threadIdx.x < 128) sred[threadIdx.x] = 0.f;
-    const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
-    float ssum[32], ssq[32];
+    if (EPI && threadIdx.x < 64) sep[threadIdx.x] = threadIdx.x < 32 ? ep_scale[threadIdx.x] : ep_shift[threadIdx.x - 32];
+    const int pw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
+    float ssum[STATS ? 32 : 1], ssq[STATS ? 32 : 1];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+    for (int c = 0; c < (STATS ? 32 : 1); ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
     const long long total = (long long)N * tiles_d * tiles_h * tiles_w;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         long long r = t;
@@ -57,51 +67,64 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
         const int ht = (int)(r % tiles_h); r /= tiles_h;
         const int dt = (int)(r % tiles_d); r /= tiles_d;
         const int n = (int)r;
-        const int w0 = wt * kC1Tw, h0 = ht * kC1Th, d0 = dt * kC1Td;
-        __syncthreads();                                    // previous tile's readers are done with sx (and sw is complete)
-        for (int i = threadIdx.x; i < 600; i += 256) {
-            const int iw = w0 - 1 + i % 10, ih = h0 - 1 + (i / 10) % 10, id = d0 - 1 + i / 100;
+        const int w0 = wt * kF1Tw, h0 = ht * kF1Th, d0 = dt * kF1Td;
+        __syncthreads();                                    // previous tile's readers are done with sx (and sw / sep are complete)
+        for (int i = threadIdx.x; i < kF1Sx; i += 256) {
+            const int iw = w0 - 1 + i % (kF1Tw + 2), ih = h0 - 1 + (i / (kF1Tw + 2)) % (kF1Th + 2), id = d0 - 1 + i / ((kF1Tw + 2) * (kF1Th + 2));
             sx[i] = ((unsigned)iw < (unsigned)W && (unsigned)ih < (unsigned)H && (unsigned)id < (unsigned)D)
                         ? __ldg(x + (((long long)n * D + id) * H + ih) * W + iw) : 0.f;
         }
         __syncthreads();
-        float acc[32];
+        float acc0[32], acc1[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 32; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b = 0; b < 3; ++b)
+            for (int b = 0; b < 3; ++b) {
+                const float* row = sx + ((td + a) * (kF1Th + 2) + th + b) * (kF1Tw + 2) + 2 * pw;
+                const float xr[4] = {row[0], row[1], row[2], row[3]};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float xv = sx[((td + a) * 10 + th + b) * 10 + tw + c];
                     const float4* wp = reinterpret_cast<const float4*>(sw + ((a * 3 + b) * 3 + c) * 32);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 w4 = wp[q];
-                        acc[4 * q] = fmaf(xv, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, w4.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(xv, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, w4.w, acc[4 * q + 3]);
+                        acc0[4 * q] = fmaf(xr[c], w4.x, acc0[4 * q]); acc0[4 * q + 1] = fmaf(xr[c], w4.y, acc0[4 * q + 1]);
+                        acc0[4 * q + 2] = fmaf(xr[c], w4.z, acc0[4 * q + 2]); acc0[4 * q + 3] = fmaf(xr[c], w4.w, acc0[4 * q + 3]);
+                        acc1[4 * q] = fmaf(xr[c + 1], w4.x, acc1[4 * q]); acc1[4 * q + 1] = fmaf(xr[c + 1], w4.y, acc1[4 * q + 1]);
+                        acc1[4 * q + 2] = fmaf(xr[c + 1], w4.z, acc1[4 * q + 2]); acc1[4 * q + 3] = fmaf(xr[c + 1], w4.w, acc1[4 * q + 3]);
                     }
                 }
-        const int ow = w0 + tw, oh = h0 + th, od = d0 + td;
-        if (ow < Wo && oh < Ho && od < Do) {
-            uint4* dst = y + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 8;      // 64 channels = 8 vectors
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = acc[8 * q + j];
-                const uint4 pk = u_pack8(f);
-                dst[q] = pk;
-                u_unpack8(pk, f);                           // statistics of the rounded values, as the tensor-core epilogue does
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { ssum[8 * q + j] += f[j]; ssq[8 * q + j] += f[j] * f[j]; }
             }
+        const int oh = h0 + th, od = d0 + td;
 #pragma unroll
-            for (int q = 4; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (int v = 0; v < 2; ++v) {
+            const int ow = w0 + 2 * pw + v;
+            if (ow < Wo && oh < Ho && od < Do) {
+                uint4* dst = y + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 8;      // 64 channels = 8 vectors
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f[j] = v ? acc1[8 * q + j] : acc0[8 * q + j];
+                        if (EPI) f[j] = fmaxf(fmaf(f[j], sep[8 * q + j], sep[32 + 8 * q + j]), 0.f);
+                    }
+                    const uint4 pk = u_pack8(f);
+                    dst[q] = pk;
+                    if (STATS) {
+                        u_unpack8(pk, f);                   // statistics of the rounded values, as the tensor-core epilogue does
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { ssum[8 * q + j] += f[j]; ssq[8 * q + j] += f[j] * f[j]; }
+                    }
+                }
+#pragma unroll
+                for (int q = 4; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
     }
-    if (stats_partials) {
+    if (STATS && stats_partials) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             float a = ssum[c], b = ssq[c];
@@ -380,24 +403,32 @@ using namespace mmad;
 
 extern "C" {
 
-int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo) {
-    const long long tiles = (long long)N * ((Do + kC1Td - 1) / kC1Td) * ((Ho + kC1Th - 1) / kC1Th) * ((Wo + kC1Tw - 1) / kC1Tw);
+static int c1_blocks(int N, int Do, int Ho, int Wo, int tw, int th, int td) {
+    const long long tiles = (long long)N * ((Do + td - 1) / td) * ((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
     return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sm_count() * 4));
 }
+// blocks (== statistic partials) of the forward kernel / of the weight-gradient kernel
+int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo) { return c1_blocks(N, Do, Ho, Wo, kF1Tw, kF1Th, kF1Td); }
+int mmad_conv3d_c1_wgrad_blocks(int N, int Do, int Ho, int Wo) { return c1_blocks(N, Do, Ho, Wo, kC1Tw, kC1Th, kC1Td); }
 
-int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials, int N, int D, int H, int W, int Do, int Ho, int Wo,
-                       void* stream) {
+int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials, const float* ep_scale, const float* ep_shift, int N,
+                       int D, int H, int W, int Do, int Ho, int Wo, void* stream) {
     MMAD_CHECK_ARG(x && w && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_c1_fwd: bad argument");
     MMAD_CHECK_ARG(Do >= D && Ho >= H && Wo >= W, "conv3d_c1_fwd: the output grid is the input grid zero-extended on the right");
-    launch_pdl(conv3d_c1_fwd_kernel, dim3(mmad_conv3d_c1_blocks(N, Do, Ho, Wo)), dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, N, D, H, W,
-               Do, Ho, Wo, (Wo + kC1Tw - 1) / kC1Tw, (Ho + kC1Th - 1) / kC1Th, (Do + kC1Td - 1) / kC1Td);
+    MMAD_CHECK_ARG((ep_scale == nullptr) == (ep_shift == nullptr), "conv3d_c1_fwd: epilogue scale and shift come together");
+    MMAD_CHECK_ARG(!(ep_scale && stats_partials), "conv3d_c1_fwd: statistics are those of the raw output (no epilogue in training mode)");
+    const dim3 grid(mmad_conv3d_c1_blocks(N, Do, Ho, Wo));
+    const int tws = (Wo + kF1Tw - 1) / kF1Tw, ths = (Ho + kF1Th - 1) / kF1Th, tds = (Do + kF1Td - 1) / kF1Td;
+    if (ep_scale) launch_pdl(conv3d_c1_fwd_kernel<false, true>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
+    else if (stats_partials) launch_pdl(conv3d_c1_fwd_kernel<true, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
+    else launch_pdl(conv3d_c1_fwd_kernel<false, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
     LAUNCH_OK();
 }
 
-// partials: float[mmad_conv3d_c1_blocks][32][27]; sum with mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27)
+// partials: float[mmad_conv3d_c1_wgrad_blocks][32][27]; sum with mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27)
 int mmad_conv3d_c1_wgrad(const float* x, const void* dy, float* partials, int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream) {
     MMAD_CHECK_ARG(x && dy && partials && N > 0 && Do >= D && Ho >= H && Wo >= W, "conv3d_c1_wgrad: bad argument");
-    launch_pdl(conv3d_c1_wgrad_kernel, dim3(mmad_conv3d_c1_blocks(N, Do, Ho, Wo)), dim3(256), 0, ST, x, (const uint4*)dy, partials, N, D, H, W,
+    launch_pdl(conv3d_c1_wgrad_kernel, dim3(mmad_conv3d_c1_wgrad_blocks(N, Do, Ho, Wo)), dim3(256), 0, ST, x, (const uint4*)dy, partials, N, D, H, W,
                Do, Ho, Wo, (Wo + kC1Tw - 1) / kC1Tw, (Ho + kC1Th - 1) / kC1Th, (Do + kC1Td - 1) / kC1Td);
     LAUNCH_OK();
 }

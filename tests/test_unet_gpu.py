@@ -106,7 +106,7 @@ def test_first_layer_direct_convolution_forward_and_weight_gradient(run):
     y = run.empty((n, do, ho, wo, 64))
     nb = run.lib.mmad_conv3d_c1_blocks(n, do, ho, wo)
     part = run.empty((nb, 64, 2), torch.float32)
-    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(y), _p(part), n, d, h, w, do, ho, wo, run.stream), "c1 fwd")
+    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(y), _p(part), None, None, n, d, h, w, do, ho, wo, run.stream), "c1 fwd")
     xe = F.pad(x, (0, wo - w, 0, ho - h, 0, do - d)).requires_grad_(True)
     wr = wt.clone().requires_grad_(True)
     ref = F.conv3d(xe, wr, padding=1)
@@ -115,11 +115,18 @@ def test_first_layer_direct_convolution_forward_and_weight_gradient(run):
     assert torch.allclose(part[:, :32, 0].sum(0), y[..., :32].float().sum(dim=(0, 1, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(part[:, :32, 1].sum(0), (y[..., :32].float() ** 2).sum(dim=(0, 1, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.all(part[:, 32:] == 0)
+    # eval-mode epilogue: relu(acc * scale + shift) in the same pass, no statistics
+    scale, shift = torch.rand(32, device="cuda", generator=g) + 0.5, torch.randn(32, device="cuda", generator=g) * 0.3
+    ye = run.empty((n, do, ho, wo, 64))
+    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(ye), None, _p(scale), _p(shift), n, d, h, w, do, ho, wo, run.stream), "c1 fwd epi")
+    want = F.relu(ref.detach() * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    assert torch.all((_nc(ye[..., :32]) - want).abs() <= 2 ** -8 * want.abs() + 1e-6) and torch.all(ye[..., 32:] == 0)
     dy = torch.randn_like(ref).to(torch.bfloat16).float()
     ref.backward(dy)
     dyb = torch.zeros((n, do, ho, wo, 64), device="cuda", dtype=torch.bfloat16)
     dyb[..., :32] = _nd(dy)
     dyb[..., 32:] = 3.0                                                   # the padding channels are ignored
+    nb = run.lib.mmad_conv3d_c1_wgrad_blocks(n, do, ho, wo)
     ws = run.empty((nb, 32, 27), torch.float32)
     gw = torch.empty_like(wt)
     run.chk(run.lib.mmad_conv3d_c1_wgrad(_p(x), _p(dyb), _p(ws), n, d, h, w, do, ho, wo, run.stream), "c1 wgrad")
