@@ -199,7 +199,7 @@ def run_resnet_train(args, rank, world, dev, dist, *, depth=18, batch=RESNET_BAT
     model = generate_model(model_depth=depth, input_W=shape[2], input_H=shape[1], input_D=shape[0], nb_class=nb_class,
                            pretrain_path=None, dropout_rate=0.5, device=dev)
     model.train()
-    reducer = GradReducer()
+    reducer = GradReducer(bucket_numel=int(os.environ.get("MMAD_BUCKET_NUMEL", str(1 << 23))))
     model.grad_reducer = reducer
     opt = torch.optim.Adam(model.parameters(), lr=1e-5, weight_decay=1e-4, fused=True, capturable=True)
     crit = nn.CrossEntropyLoss()

@@ -160,6 +160,12 @@ int mmad_wgrad_reduce(const float* partials, int nsplit, float* dw,
 int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad,
                              int Cout, int Cin, int taps, void* stream);
 
+/* The same for n layers at once (two launches per 64 layers instead of two per layer: a training step re-lays every
+ * convolution's weights).  w / w_fwd / w_dgrad: HOST arrays of n DEVICE pointers (w_dgrad[i] NULL = no dgrad layout for layer
+ * i); cout / cin / taps: host arrays of n ints. */
+int mmad_conv3d_prep_weights_batched(int n, const void* const* w, void* const* w_fwd, void* const* w_dgrad,
+                                     const int* cout, const int* cin, const int* taps, void* stream);
+
 /* Data gradient of a 3x3x3, stride-2, padding-1 convolution (resnet.py:18-23 with
  * stride 2: layer2.0.conv1) without zero insertion: dx (N,D,H,W,Cdx) bf16 from
  * dy (N,(D-1)/2+1,..,Cdy) bf16 as 8 interleaved stride-1 phase convolutions.

@@ -89,6 +89,7 @@ def load() -> ctypes.CDLL:
         "mmad_roi_pool_ndhwc_f32": [P, P, L, I, I, I, I, I, I, I, P, P],
         "mmad_conv3d_prep_weights": [P, P, P, I, I, I, P],
         "mmad_conv3d_prep_weights_s2": [P, P, I, I, P],
+        "mmad_conv3d_prep_weights_batched": [I, P, P, P, P, P, P, P],
         "mmad_conv3d_dgrad_s2_bf16": [P, P, P, I, I, I, I, I, I, P],
         "mmad_stem_s2d_elems": [I, I, I, I],
         "mmad_stem_s2d_pack": [P, P, I, I, I, I, P],
@@ -113,6 +114,8 @@ def load() -> ctypes.CDLL:
         "mmad_ncs_f32_to_nsc_bf16": [P, P, I, I, L, P],
     }
     for name, args in sigs.items():
+        if os.environ.get("MMAD_LIB") and not hasattr(lib, name):
+            continue                                       # an older build loaded for an A/B measurement
         getattr(lib, name).argtypes = args
         getattr(lib, name).restype = I
     lib.mmad_conv3d_wgrad_workspace.argtypes = [I] * 10 + [POINTER(ctypes.c_int)]

@@ -37,6 +37,7 @@ struct ConvGeom {
     int lw, lh, ltd;              // log2(tw), log2(th), log2(td)
     int epi;                      // 1: the epilogue applies ConvEpi (per-channel affine / ReLU / fp32 side output)
     int dyn;                      // 1: tiles are drawn from the global counter (dynamic scheduler), 0: static stride
+    int sched_depth;              // tile-ring slots in use: 2 when dynamic (a CTA holds at most one tile it has not started), 4 when static
     int tiles_w, tiles_h, tiles_d, tiles_n, m_tiles, n_tiles;   // tile index: sample tile fastest, then w, h, d
     int kc;                       // Cin / 64
     int stages;
@@ -87,10 +88,11 @@ constexpr int kConvProducers = 3;          // warps 0, 2, 3
 // at run time: warp 8 draws tile indices from a global counter (atomicAdd) and hands them to the other roles through a small
 // shared-memory ring (sched_tile[] + full / empty mbarriers), a few tiles ahead of the consumers.  A CTA that starts late -
 // because another kernel (a weight-gradient GEMM on the side stream, an NCCL all-reduce) still holds its SM - simply finds fewer
-// tiles left, and tiles that skip padding taps no longer unbalance a static stride.  g.dyn == 0 keeps the static assignment
-// (tile = blockIdx.x + k * gridDim.x) through the same ring.  The counter pair {next, done} resets itself: the last CTA to
-// leave zeroes it, so a launch (or a CUDA-graph replay of it) always finds it at zero.
-constexpr int kSchedSlots = 2;
+// tiles left, and tiles that skip padding taps no longer unbalance a static stride.  g.dyn == 0 (short uniform tiles: 1x1x1
+// convolutions) keeps the static assignment tile = blockIdx.x + k * gridDim.x, computed locally by every role without touching
+// the ring.  The counter pair {next, done} resets itself: the last CTA to leave zeroes it, so a launch (or a CUDA-graph replay
+// of it) always finds it at zero.
+constexpr int kSchedSlots = 4;           // ring capacity; g.sched_depth (<= kSchedSlots) slots are used
 constexpr int kSchedConsumers = 8;         // 3 producer warps + MMA warp + 4 epilogue warps arrive on a slot's empty barrier
 // A producer re-enters the ring every nprod stages and waits on a PARITY, so it must never be two phases ahead of a
 // slot: that needs stages >= active producers (nprod = min(kConvProducers, stages)).
@@ -186,29 +188,31 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ksteps = taps * g.kc;
     // consumer side of the tile ring: every role warp walks the same sequence of tile indices (>= total_tiles: no more work)
     uint32_t sc_slot = 0, sc_ph = 0;
+    int sc_static = (int)blockIdx.x;                        // static mode: no ring traffic at all (the MMA issuer's loop is a critical path)
     auto next_tile = [&]() -> int {
+        if (!g.dyn) { const int t = sc_static; sc_static += (int)gridDim.x; return t; }
         mbar_wait(sfull0 + 8 * sc_slot, sc_ph);
         const int t = sched_tile[sc_slot];
         __syncwarp();
         if (lane == 0) mbar_arrive(sempty0 + 8 * sc_slot);
-        if (++sc_slot == kSchedSlots) { sc_slot = 0; sc_ph ^= 1; }
+        if (++sc_slot == (uint32_t)g.sched_depth) { sc_slot = 0; sc_ph ^= 1; }
         return t;
     };
 
     if (warp == 8) {
-        // ============================ tile scheduler ============================
+        // ============================ tile scheduler (dynamic mode only) ============================
         uint32_t slot = 0, ph = 0;
-        for (int k = 0;; ++k) {
+        for (; g.dyn;) {
             mbar_wait(sempty0 + 8 * slot, ph ^ 1);
             int t = 0;
             if (lane == 0) {
-                t = g.dyn ? (int)atomicAdd(sched_counter, 1u) : (int)blockIdx.x + k * (int)gridDim.x;
+                t = (int)atomicAdd(sched_counter, 1u);
                 sched_tile[slot] = t;
                 mbar_arrive(sfull0 + 8 * slot);             // release: the tile index is visible to the waiters
             }
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= total_tiles) break;
-            if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
+            if (++slot == (uint32_t)g.sched_depth) { slot = 0; ph ^= 1; }
         }
     } else if (warp == 0 || warp == 2 || warp == 3) {
         // ============================ TMA producers: stage i is issued by producer i % 3 ============================
@@ -549,12 +553,14 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
     // consumer side of the tile ring (see the single-CTA kernel): super-tile indices, the same sequence in both CTAs
     uint32_t sc_slot = 0, sc_ph = 0;
+    int sc_static = pair;
     auto next_tile = [&]() -> int {
+        if (!g.dyn) { const int t = sc_static; sc_static += n_pairs; return t; }
         mbar_wait_cluster(sfull0 + 8 * sc_slot, sc_ph);
         const int t = sched_tile[sc_slot];
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(sempty0 + 8 * sc_slot, 0);
-        if (++sc_slot == kSchedSlots) { sc_slot = 0; sc_ph ^= 1; }
+        if (++sc_slot == (uint32_t)g.sched_depth) { sc_slot = 0; sc_ph ^= 1; }
         return t;
     };
 
@@ -580,11 +586,11 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ============================ tile scheduler: leader CTA only, publishes to both CTAs ============================
         if (leader) {
             uint32_t slot = 0, ph = 0;
-            for (int k = 0;; ++k) {
+            for (; g.dyn;) {
                 mbar_wait_cluster(sempty0 + 8 * slot, ph ^ 1);
                 int t = 0;
                 if (lane == 0) {
-                    t = g.dyn ? (int)atomicAdd(sched_counter, 1u) : pair + k * n_pairs;
+                    t = (int)atomicAdd(sched_counter, 1u);
                     sched_tile[slot] = t;
                     st_shared_remote_u32(smem_u32(const_cast<int*>(sched_tile + slot)), 1, (uint32_t)t);
                     mbar_arrive(sfull0 + 8 * slot);
@@ -592,7 +598,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
                 t = __shfl_sync(0xffffffffu, t, 0);
                 if (t >= total_super) break;
-                if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
+                if (++slot == (uint32_t)g.sched_depth) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp == 0 || warp == 2 || warp == 3) {
@@ -1002,7 +1008,10 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* sched = nullptr;
-    g.dyn = use_dynamic_scheduler() ? 1 : 0;
+    // dynamic draws pay off where tiles are long and uneven (3x3x3 taps, padding skips, co-running kernels); the short uniform
+    // tiles of a 1x1x1 convolution keep the static stride (measured on ResNet3D-50: the per-tile atomic costs 1 % there)
+    g.dyn = (use_dynamic_scheduler() && kd * kh * kw * g.kc >= 16) ? 1 : 0;
+    g.sched_depth = g.dyn ? 2 : kSchedSlots;
     if (g.dyn) {
         sched = sched_counter_slot();
         if (!sched) return fail(MMAD_ECUDA, "conv3d_fwd: cannot allocate the tile-scheduler counters");

@@ -67,6 +67,55 @@ __global__ void __launch_bounds__(256) prep_weights_dgrad_kernel(const __nv_bflo
         if (co < Cout && ci < Cin) wt[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = tile[tx][j];
     }
 }
+// ---- the same two passes for MANY layers in one launch each: a training step re-lays every convolution's weights (they change
+//      every step), and ~40 launches of 5-10 us kernels cost more in launch gaps than in bytes.  The layer table travels in the
+//      kernel parameter space (no upload); a block finds its layer by scanning the block-offset prefix.
+constexpr int kPrepBatch = 64;
+struct PrepDesc { const float* w; __nv_bfloat16* wf; __nv_bfloat16* wt; int Cout, Cin, taps; };
+struct PrepBatch { int n; int start[kPrepBatch + 1]; PrepDesc d[kPrepBatch]; };
+__device__ __forceinline__ int prep_find_layer(const PrepBatch& b, int blk) {
+    int l = 0;
+    while (l + 1 < b.n && blk >= b.start[l + 1]) ++l;
+    return l;
+}
+__global__ void __launch_bounds__(64) prep_weights_fwd_batched_kernel(const __grid_constant__ PrepBatch b) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float tile[];                  // [64][taps + 1]
+    const int l = prep_find_layer(b, blockIdx.x);
+    const PrepDesc& d = b.d[l];
+    const int local = blockIdx.x - b.start[l], chunks = (d.Cin + 63) / 64;
+    const int co = local / chunks, c0 = (local % chunks) * 64, taps = d.taps;
+    const int nci = min(64, d.Cin - c0);
+    const float* src = d.w + ((long long)co * d.Cin + c0) * taps;
+    for (int i = threadIdx.x; i < nci * taps; i += 64) tile[(i / taps) * (taps + 1) + (i % taps)] = src[i];
+    __syncthreads();
+    if (threadIdx.x < nci)
+        for (int t = 0; t < taps; ++t)
+            d.wf[((long long)co * taps + t) * d.Cin + c0 + threadIdx.x] = __float2bfloat16_rn(tile[threadIdx.x * (taps + 1) + t]);
+}
+__global__ void __launch_bounds__(256) prep_weights_dgrad_batched_kernel(const __grid_constant__ PrepBatch b) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ __nv_bfloat16 tile[32][34];
+    const int l = prep_find_layer(b, blockIdx.x);
+    const PrepDesc& d = b.d[l];
+    int local = blockIdx.x - b.start[l];
+    const int nx = (d.Cin + 31) / 32, ny = (d.Cout + 31) / 32;
+    const int ci0 = (local % nx) * 32; local /= nx;
+    const int co0 = (local % ny) * 32;
+    const int tap = local / ny, taps = d.taps;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int co = co0 + j, ci = ci0 + tx;
+        if (co < d.Cout && ci < d.Cin) tile[j][tx] = d.wf[((long long)co * taps + tap) * d.Cin + ci];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int ci = ci0 + j, co = co0 + tx;
+        if (co < d.Cout && ci < d.Cin) d.wt[((long long)ci * taps + (taps - 1 - tap)) * d.Cout + co] = tile[tx][j];
+    }
+}
 // ---- weights of the phase convolutions of mmad_conv3d_dgrad_s2_bf16: torch (Cdy, Cdx, 3,3,3) fp32 -> for phase p = pd*4+ph*2+pw
 //      a block [Cdx][taps_p][Cdy] bf16, tap (a, b, c) of the phase = original tap t with t = 1 on an even axis, t = 2 - 2*a on an
 //      odd one (dx[2j+1] = dy[j] w[2] + dy[j+1] w[0]).  Blocks are concatenated in phase order.
@@ -879,6 +928,45 @@ int mmad_conv3d_prep_weights(const float* w, void* w_fwd, void* w_dgrad, int Cou
                                                                                               (__nv_bfloat16*)w_dgrad, Cout, Cin, taps);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
+    }
+    return MMAD_OK;
+}
+// Batched mmad_conv3d_prep_weights: n layers, two launches per 64 layers.  w / w_fwd / w_dgrad: host arrays of n device pointers
+// (w_dgrad[i] NULL = no dgrad layout for layer i); cout / cin / taps: host arrays of n ints.
+int mmad_conv3d_prep_weights_batched(int n, const void* const* w, void* const* w_fwd, void* const* w_dgrad, const int* cout,
+                                     const int* cin, const int* taps, void* stream) {
+    MMAD_CHECK_ARG(n > 0 && w && w_fwd && w_dgrad && cout && cin && taps, "prep_weights_batched: bad argument");
+    for (int base = 0; base < n; base += kPrepBatch) {
+        const int m = std::min(kPrepBatch, n - base);
+        PrepBatch fb = {}, db = {};
+        int max_taps = 1, nd = 0;
+        fb.n = m;
+        for (int i = 0; i < m; ++i) {
+            const int k = base + i;
+            MMAD_CHECK_ARG(w[k] && w_fwd[k] && cout[k] > 0 && cin[k] > 0 && taps[k] > 0 && taps[k] <= 343, "prep_weights_batched: bad layer");
+            fb.d[i] = PrepDesc{(const float*)w[k], (__nv_bfloat16*)w_fwd[k], (__nv_bfloat16*)w_dgrad[k], cout[k], cin[k], taps[k]};
+            fb.start[i + 1] = fb.start[i] + ((cin[k] + 63) / 64) * cout[k];
+            max_taps = std::max(max_taps, taps[k]);
+            if (w_dgrad[k]) {
+                db.d[nd] = fb.d[i];
+                db.start[nd + 1] = db.start[nd] + ((cin[k] + 31) / 32) * ((cout[k] + 31) / 32) * taps[k];
+                ++nd;
+            }
+        }
+        db.n = nd;
+        const size_t smem = 64 * (size_t)(max_taps + 1) * sizeof(float);
+        if (smem > 48 * 1024) {
+            static DevOnce attr_done;
+            if (attr_done.need()) MMAD_CUDA(cudaFuncSetAttribute(prep_weights_fwd_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        }
+        launch_pdl(prep_weights_fwd_batched_kernel, dim3(fb.start[m]), dim3(64), smem, ST, fb);
+        MMAD_CUDA(cudaGetLastError());
+        count_launch();
+        if (nd) {
+            launch_pdl(prep_weights_dgrad_batched_kernel, dim3(db.start[nd]), dim3(256), 0, ST, db);
+            MMAD_CUDA(cudaGetLastError());
+            count_launch();
+        }
     }
     return MMAD_OK;
 }

@@ -101,6 +101,15 @@ class _Run:
         # BatchNorm / ReLU kernels of the main chain run underneath the tensor-bound wgrad work
         self.side = _side_stream(device) if use_side_stream else None
         self._keep = []                                    # tensors in use on the side stream, released by join_side()
+        self.tracked = []                                  # num_batches_tracked buffers of the BatchNorms this pass has updated
+
+    def bump_tracked(self):
+        if self.tracked:
+            uniq = {}
+            for t in self.tracked:                         # a BatchNorm shared by two convolutions (unet3d.py:69) counts twice
+                uniq[id(t)] = (t, uniq.get(id(t), (t, 0))[1] + 1)
+            torch._foreach_add_([t for t, _ in uniq.values()], [c for _, c in uniq.values()])
+            self.tracked = []
 
     def empty(self, shape, dtype=torch.bfloat16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -177,6 +186,36 @@ class _Run:
                  "mmad_conv3d_prep_weights")
         return wf, wt
 
+    def prep_all(self, items):
+        """items: [(key, fp32 weight (Cout, Cin, k,k,k), want_dgrad)] -> {key: (w_fwd [Cout][taps][Cin] bf16, w_dgrad [Cin][taps
+        reversed][Cout] bf16 or None)} with TWO launches for all layers (mmad_conv3d_prep_weights_batched) instead of two per layer."""
+        n = len(items)
+        if n == 0:
+            return {}
+        ws = [w.detach().contiguous() for _, w, _ in items]
+        sizes = [w.numel() for w in ws]
+        fwd = self.empty((sum(sizes),))
+        dgr = self.empty((sum(sz for sz, (_, _, wd) in zip(sizes, items) if wd),)) if any(wd for _, _, wd in items) else None
+        P = ctypes.c_void_p * n
+        I = ctypes.c_int * n
+        pw, pf, pd, co, ci, tp = P(), P(), P(), I(), I(), I()
+        out, of, od = {}, 0, 0
+        for i, ((key, _, wd), w, sz) in enumerate(zip(items, ws, sizes)):
+            cout, cin = w.shape[0], w.shape[1]
+            taps = sz // (cout * cin)
+            wf = fwd[of:of + sz].view(cout, taps, cin)
+            of += sz
+            wt = None
+            if wd:
+                wt = dgr[od:od + sz].view(cin, taps, cout)
+                od += sz
+            pw[i], pf[i], pd[i] = w.data_ptr(), wf.data_ptr(), (wt.data_ptr() if wt is not None else None)
+            co[i], ci[i], tp[i] = cout, cin, taps
+            out[key] = (wf, wt)
+        self.chk(self.lib.mmad_conv3d_prep_weights_batched(n, pw, pf, pd, co, ci, tp, self.stream), "mmad_conv3d_prep_weights_batched")
+        self._prep_keep = ws                               # the fp32 sources stay alive until the launches are enqueued (they are)
+        return out
+
     def bn_params(self, bn: nn.BatchNorm3d, part, count, training):
         c = bn.num_features
         vec = self.empty((4, c), torch.float32)          # mean, invstd, scale, shift
@@ -188,7 +227,7 @@ class _Run:
                                                _p(bn.running_mean) if track else None, _p(bn.running_var) if track else None,
                                                _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]), self.stream), "mmad_bn_finalize")
             if track and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                self.tracked.append(bn.num_batches_tracked)   # bumped together at the end of the pass (one launch, not one per layer)
         else:
             self.chk(self.lib.mmad_bn_eval_params(c, _p(g), _p(b), _p(bn.running_mean), _p(bn.running_var), bn.eps,
                                                   _p(vec[0]), _p(vec[1]), _p(vec[2]), _p(vec[3]), self.stream), "mmad_bn_eval_params")
@@ -261,15 +300,23 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     # ---- residual stages (resnet.py:209-212) ----
     cur = p0
     blocks = [b for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer]
+    items = []
+    for blk in blocks:                                     # every convolution's weights re-laid in two launches
+        if isinstance(blk, Bottleneck):
+            items += [(blk.conv1, blk.conv1.weight, need_grad), (blk.conv2, blk.conv2.weight, need_grad and blk.conv2.stride[0] == 1),
+                      (blk.conv3, blk.conv3.weight, need_grad)]
+        else:
+            items += [(blk.conv1, blk.conv1.weight, need_grad), (blk.conv2, blk.conv2.weight, need_grad)]
+        if isinstance(blk.downsample, nn.Module):
+            items.append((blk.downsample[0], blk.downsample[0].weight, need_grad))
+    prepped = r.prep_all(items)
     for bi, blk in enumerate(blocks):
         last = bi == len(blocks) - 1
         if isinstance(blk, Bottleneck):
             # resnet.py:89-109: 1x1x1 reduce, 3x3x3 (stride / dilation), 1x1x1 expand (x4), residual
             st, dil = blk.conv2.stride[0], blk.conv2.dilation[0]
             planes, outc = blk.conv1.out_channels, blk.conv3.out_channels
-            w1f, w1t = r.prep_weights(blk.conv1, need_grad)
-            w2f, w2t = r.prep_weights(blk.conv2, need_grad and st == 1)
-            w3f, w3t = r.prep_weights(blk.conv3, need_grad)
+            (w1f, w1t), (w2f, w2t), (w3f, w3t) = prepped[blk.conv1], prepped[blk.conv2], prepped[blk.conv3]
             c1, part1 = r.conv(cur, w1f, planes, 1, 1, 0, 1, training)
             v1 = r.bn_params(blk.bn1, part1, c1.numel() // planes, training)
             a1 = r.bn_apply(c1, v1, relu=True)
@@ -285,8 +332,7 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
         else:
             st, dil = blk.conv1.stride[0], blk.conv1.dilation[0]
             planes = blk.conv1.out_channels
-            w1f, w1t = r.prep_weights(blk.conv1, need_grad)
-            w2f, w2t = r.prep_weights(blk.conv2, need_grad)
+            (w1f, w1t), (w2f, w2t) = prepped[blk.conv1], prepped[blk.conv2]
             c1, part1 = r.conv(cur, w1f, planes, 3, st, dil, dil, training)
             cnt = c1.numel() // planes
             v1 = r.bn_params(blk.bn1, part1, cnt, training)
@@ -304,7 +350,7 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
             rec.update(short_a=True)
         elif blk.downsample is not None:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
-            wdf, wdt = r.prep_weights(dconv, need_grad)
+            wdf, wdt = prepped[dconv]
             cd, partd = r.conv(cur, wdf, width, 1, dconv.stride[0], 0, 1, training)
             vd = r.bn_params(dbn, partd, cnt, training)
             out = r.bn_apply(pre, vpre, relu=True, res=cd, res_vec=vd, also_f32=last)
@@ -317,6 +363,7 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
         rec["out"] = out                                   # bf16: next block's input and the ReLU mask of the backward
         tape["blocks"].append(rec)
         cur = out
+    r.bump_tracked()
     return out32, tape
 
 
@@ -450,6 +497,8 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             dx2 = g2                                                                # identity shortcut
         dy, dy2 = dx1, dx2
 
+    if grads.reducer is not None:
+        grads.reducer.flush()                              # the last large bucket is all-reduced under the stem's backward kernels
     # ---- stem backward: maxpool, relu+bn1 (mask recomputed from c0), wgrad of the space-to-depth GEMM.  No input gradient: the MRI
     #      volume is data ----
     stem = tape["stem"]

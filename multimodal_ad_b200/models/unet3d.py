@@ -158,7 +158,7 @@ def _bn_vec(r: _UNetRun, bn: nn.BatchNorm3d, part, count, bias, training, width=
             if bias is not None:
                 bn.running_mean.add_(bias.detach(), alpha=momentum)    # the batch mean of (conv + bias) is the stored mean + bias
             if bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                r.tracked.append(bn.num_batches_tracked)    # bumped together at the end of the pass (a shared BatchNorm appears twice)
     else:
         # eval: xhat = (c + bias - running_mean) * invstd with c stored without the bias -> use mean' = running_mean - bias
         mean = bn.running_mean if bias is None else bn.running_mean - bias.detach()
@@ -184,12 +184,20 @@ def _unet_forward(model: "UNet3D", x: torch.Tensor, training: bool, need_grad: b
     blocks_s = [model.s_block3, model.s_block2, model.s_block1]
     tape = {"training": training, "in_shape": (n, d, h, w), "x": x if need_grad else None, "enc": [], "dec": []}
 
+    # every 3x3x3 convolution's weights (but the fp32 first layer's) re-laid in two launches
+    items = []
+    for bi, blk in enumerate(blocks_a):
+        if bi:
+            items.append((blk.conv1, blk.conv1.weight, need_grad))
+        w2 = blk.conv2.weight.detach()
+        items.append((blk.conv2, F.pad(w2, (0, 0, 0, 0, 0, 0, 0, 64 - w2.shape[1])) if bi == 0 else w2, need_grad))
+    for blk in blocks_s:
+        items += [(blk.conv1, blk.conv1.weight, need_grad), (blk.conv2, blk.conv2.weight, need_grad)]
+    prepped = r.prep_all(items)
+
     def conv_bn_relu(xin, conv, bn, out_t, out_off, out_ld, w_pad_cin=None, hook=False):
         """relu(bn(conv(xin) + bias)) written to channels [out_off, out_off + Cout) of out_t (rows out_ld apart; 0 = dense)."""
-        wt_src = conv.weight.detach()
-        if w_pad_cin:
-            wt_src = F.pad(wt_src, (0, 0, 0, 0, 0, 0, 0, w_pad_cin - wt_src.shape[1]))
-        wf, wt = r.prep_w(wt_src, need_grad)
+        wf, wt = prepped[conv]
         cout = conv.out_channels
         rows = xin.numel() // xin.shape[-1]
         hook32 = r.empty(tuple(xin.shape[:4]) + (cout,), torch.float32) if hook else None
@@ -286,7 +294,7 @@ def _unet_forward(model: "UNet3D", x: torch.Tensor, training: bool, need_grad: b
             # eval without autograd: conv2 + bn + relu + conv3 + crop back as ONE kernel, the last activation is never written
             head = blk.conv3
             k = head.out_channels
-            wf, _ = r.prep_w(blk.conv2.weight.detach(), False)
+            wf, _ = prepped[blk.conv2]
             vec, _ = _bn_vec(r, blk.bn, None, 0, blk.conv2.bias, False)
             hook32 = r.empty((n,) + g + (mid,), torch.float32) if want_hook else None
             out = r.empty((n, k, d, h, w), torch.float32)
@@ -309,6 +317,7 @@ def _unet_forward(model: "UNet3D", x: torch.Tensor, training: bool, need_grad: b
     out = r.empty((n, k, d, h, w), torch.float32)
     r.chk(lib.mmad_head1x1_fwd(_p(cur), _p(head.weight.detach().reshape(k, -1).contiguous()), _p(head.bias.detach()), _p(out), n, dp, hp, wp,
                                d, h, w, cur.shape[-1], k, r.stream), "mmad_head1x1_fwd")
+    r.bump_tracked()
     if not need_grad and not getattr(model, "keep_tape", False):
         tape = None
     return out, hook32, tape

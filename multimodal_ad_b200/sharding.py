@@ -94,6 +94,13 @@ class GradReducer:
         self._view_bucket[id(view)] = (b, view)          # keeps the view (and so its id) alive
         return view
 
+    def flush(self) -> None:
+        """Close the bucket that is being filled: it is all-reduced as soon as its members have been handed over, instead of
+        waiting for `finish`.  The backward pass calls this before its last (stem) stage, so that the final bucket's collective runs
+        under that stage's kernels and only the small-tensor all-reduce is left for the end of the step."""
+        if self.active and self._buckets and not self._buckets[-1]["closed"]:
+            self._close(self._buckets[-1])
+
     def _close(self, b) -> None:
         b["closed"] = True
         if not b["pending"]:

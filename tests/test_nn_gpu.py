@@ -138,6 +138,7 @@ def test_batchnorm_forward_backward(c, rows, run):
     assert torch.allclose(vec[0], xf.mean(0), rtol=1e-5, atol=1e-5)
     assert torch.allclose(vec[1], 1.0 / torch.sqrt(xf.var(0, unbiased=False) + bn.eps), rtol=1e-4)
     assert torch.allclose(bn.running_mean, rm, rtol=1e-5, atol=1e-6) and torch.allclose(bn.running_var, rv, rtol=1e-4, atol=1e-6)
+    run.bump_tracked()                                                     # the per-layer counters are bumped together at the end of a pass
     assert int(bn.num_batches_tracked) == 1
     o = out.float().reshape(rows, c)
     assert torch.all((o - ot).abs() <= 2 ** -8 * ot.abs() + 1e-5)

@@ -28,7 +28,11 @@ def main():
         d[r[mi]] = float(r[vi].replace(",", ""))
     seq = list(launches.values())
     starts = [i for i, d in enumerate(seq) if "stem_s2d_pack" in d["name"]]
-    step = seq[starts[-2]:starts[-1]] if len(starts) >= 2 else seq[starts[-1]:]
+    # the last step of the capture when it is complete (the first step also carries the optimizer's one-off state initialisation),
+    # else the one before it
+    step = seq[starts[-1]:]
+    if len(starts) >= 2 and len(step) < 0.55 * (starts[-1] - starts[-2]):
+        step = seq[starts[-2]:starts[-1]]
     tkey = "gpu__time_duration.sum"
     pkey = [k for k in step[0] if k.startswith("sm__pipe_tensor_cycles_active")][0]
     tot = sum(d[tkey] for d in step)
