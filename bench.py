@@ -613,6 +613,79 @@ def unet_cpu_reference(seconds_cap=40.0):
             "sample": f"{n} single-volume pass(es) of the UNet3D forward (eval, fp32) + ROI means of the 64-channel map on the host cores"}
 
 
+def unet_stock_torch_forward(m, x):
+    """unet3d.py:137-157 through the nn modules' OWN forward (stock PyTorch / cuDNN): same module tree, nothing of this repo's
+    CUDA library runs here.  Returns (out, the raw s_block1.conv2 output)."""
+    import torch
+    import torch.nn.functional as F
+
+    d, h, w = x.shape[2:]
+    td, th, tw = m.target
+    cur = F.pad(x, (0, tw - w, 0, th - h, 0, td - d))
+    skips = []
+    for blk in (m.a_block1, m.a_block2, m.a_block3, m.bottleNeck):
+        cur = blk.relu(blk.bn1(blk.conv1(cur)))
+        cur = blk.relu(blk.bn2(blk.conv2(cur)))
+        if not blk.bottleneck:
+            skips.append(cur)
+            cur = blk.pooling(cur)
+    hook = None
+    for blk in (m.s_block3, m.s_block2, m.s_block1):
+        cur = torch.cat((blk.upconv1(cur), skips.pop()), 1)
+        cur = blk.relu(blk.bn(blk.conv1(cur)))
+        hook = blk.conv2(cur)
+        cur = blk.relu(blk.bn(hook))
+    return m.s_block1.conv3(cur)[:, :, :d, :h, :w], hook
+
+
+def unet_torch_gpu_baseline(dev, batch=8, steps=3):
+    """Same-box context for the extraction path: the same UNet3D module tree run by stock PyTorch + cuDNN in eval mode (bf16 autocast,
+    channels_last_3d) + the ROI means of the 64-channel map as a torch index_add over labelled voxels (the reference's one-hot
+    product would need 39 GB per volume).  Not the target and not the --impl reference arm."""
+    import numpy as np
+    import torch
+
+    from multimodal_ad_b200.models import unet3d
+    from oracle.roi_oracle import synthetic_atlas                       # label-map generator only
+
+    out = {"batch": batch, "steps": steps, "what": "stock torch.nn modules (cuDNN), eval, bf16 autocast + channels_last_3d, + torch index_add ROI means"}
+    try:
+        torch.manual_seed(0)
+        model = unet3d.UNet3D(1, 1).to(dev).eval().to(memory_format=torch.channels_last_3d)
+        lab = torch.from_numpy(synthetic_atlas(SHAPE, N_ROIS).astype(np.int64)).to(dev).reshape(-1)
+        idx = torch.nonzero(lab).squeeze(1)
+        cnt = torch.bincount(lab, minlength=N_ROIS + 1)[1:].clamp_min(1).float()
+        x = torch.rand((batch, 1) + SHAPE, device=dev)
+        old = torch.backends.cudnn.benchmark
+        torch.backends.cudnn.benchmark = True
+
+        def step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                o, hook = unet_stock_torch_forward(model, x)
+                f = hook[..., :SHAPE[0], :SHAPE[1], :SHAPE[2]].float().reshape(batch, 64, -1)[:, :, idx]      # (B, 64, labelled voxels)
+                acc = torch.zeros((batch, 64, N_ROIS + 1), device=dev).index_add_(2, lab[idx], f)
+                return o, (acc[:, :, 1:] / cnt).permute(0, 2, 1)
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out.update({"ms_per_step": ms, "volumes_per_sec": batch / (ms * 1e-3)})
+        torch.backends.cudnn.benchmark = old
+        del model
+    except Exception as e:                                 # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {e}"[:200]
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_unet_roi_extract(args, rank, world, dev, dist, batch=8, steps=10, want_cpu=False):
     """image_features.py:97-114 on the accelerated path: UNet3D(1, 1).eval() forward on batch `batch` of 1x91x109x91 volumes, the
     64-channel s_block1.conv2 map pooled over a 170-label atlas without leaving the GPU; subject-sharded across ranks."""
@@ -684,6 +757,9 @@ def run_unet_roi_extract(args, rank, world, dev, dist, batch=8, steps=10, want_c
     if want_cpu:
         res["cpu_baseline"] = unet_cpu_reference()
     del model, xs, plan
+    torch.cuda.empty_cache()
+    if want_cpu:                                           # one GPU, rank 0: the stock PyTorch / cuDNN context number as well
+        res["torch_gpu_baseline"] = unet_torch_gpu_baseline(dev, batch)
     torch.cuda.empty_cache()
     return res
 
