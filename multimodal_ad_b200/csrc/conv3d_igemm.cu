@@ -495,14 +495,22 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // multicast tcgen05.commit; the leader's `full` barrier collects the TMA bytes of both CTAs; accumulator-full is multicast
 // to both epilogues, accumulator-empty is collected on the leader from both.
 // ===============================================================================================================
+//
+// WH = true: the W-halo formulation of the single-CTA kernel (3x3x3, unit stride, Cout = 64, Cin = 64 k) on a CTA pair: a 256-voxel x
+// 64-channel super tile, every CTA stages its own 10 x 4 x 4 halo box per (kd, kh, channel slab) and only 32 of the 64 weight rows
+// of the three kw taps.  The single-CTA N = 64 kernel is bound by shared-memory bandwidth (44 KB of TMA writes + 72 KB of operand
+// reads per 384 MMA cycles); here a CTA moves 32 + 60 KB per stage.
+template <bool WH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                          const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
                          unsigned int* __restrict__ sched_counter) {
     pdl_launch_dependents();
-    constexpr int BN = 256;
-    constexpr int B_HALF = (BN / 2) * 128;
-    constexpr int STAGE = kATileBytes + B_HALF;             // 32 KB per CTA per K-step
+    constexpr int BN = WH ? 64 : 256;
+    constexpr int B_TAP = (BN / 2) * 128;                   // this CTA's half of one tap's weight rows
+    constexpr int B_HALF = (WH ? 3 : 1) * B_TAP;
+    constexpr int A_REGION = WH ? kHaloTileBytes : kATileBytes;
+    constexpr int STAGE = A_REGION + B_HALF;                // 32 KB per CTA per stage (either variant)
     constexpr uint32_t IDESC = umma_idesc_bf16(256, BN, 0, 0);
     constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -607,7 +615,34 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
-            for (;;) {
+            for (; WH;) {
+                // W-halo stages (kd, channel slab, kh): one halo box + this CTA's 32 weight rows of the three kw taps
+                const int st = next_tile();
+                if (st >= total_super) break;
+                int r = 2 * st + (int)rank;                 // n_tiles == 1, tn == 1; the phantom tile past the end loads zeros
+                const int n = r % g.tiles_n; r /= g.tiles_n;
+                const int wt = r % g.tiles_w; r /= g.tiles_w;
+                const int ht = r % g.tiles_h; r /= g.tiles_h;
+                const int dt = r;
+                const int w0 = wt * 8 - 1, h0 = ht * 4 - 1, d0 = dt * 4 - 1;
+                for (int a = 0; a < 3; ++a)
+                    for (int cc = 0; cc < g.kc; ++cc)
+                        for (int b = 0; b < 3; ++b) {
+                            if (turn == me) {
+                                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                if (elect_one()) {
+                                    if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);
+                                    const uint32_t sa = stage0 + s * STAGE;
+                                    tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0, h0 + b, d0 + a, n);
+                                    tma_load_4d_2sm(sa + A_REGION, &tmBh, full0 + 8 * s, 0, (int)rank * (BN / 2), cc, (a * 3 + b) * 3);
+                                }
+                                __syncwarp();
+                            }
+                            if (++turn == nprod) turn = 0;
+                            if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                        }
+            }
+            for (; !WH;) {
                 const int st = next_tile();
                 if (st >= total_super) break;
                 const int nt = st % g.n_tiles, mp = st / g.n_tiles;
@@ -631,7 +666,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                         if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);   // bytes of BOTH CTAs
                                         const uint32_t sa = stage0 + s * STAGE;
                                         tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0 + c * g.dil, h0 + b * g.dil, d0 + a * g.dil, n);
-                                        tma_load_3d_2sm(sa + kATileBytes, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
+                                        tma_load_3d_2sm(sa + A_REGION, &tmBh, full0 + 8 * s, 0, nt * BN + (int)rank * (BN / 2), tap * g.kc + cc);
                                     }
                                     __syncwarp();
                                 }
@@ -654,19 +689,30 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);            // both epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                uint32_t mw, mh, md;
-                super_masks(st / g.n_tiles, mw, mh, md);
-                const int ksteps_t = (mw == 0xffffffffu) ? ksteps : __popc(mw) * __popc(mh) * __popc(md) * g.kc;
+                uint32_t mw = 0xffffffffu, mh = 0xffffffffu, md = 0xffffffffu;
+                if (!WH) super_masks(st / g.n_tiles, mw, mh, md);
+                const int ksteps_t = WH ? 9 * g.kc : ((mw == 0xffffffffu) ? ksteps : __popc(mw) * __popc(mh) * __popc(md) * g.kc);
                 for (int k = 0; k < ksteps_t; ++k) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t sa = stage0 + s * STAGE;
-                    const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-                    const uint64_t bdesc = umma_desc_sw128(sa + kATileBytes, 16, 1024);
                     if (elect_one()) {
+                        if (WH) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
-                        nmma += 4;
+                            for (int q = 0; q < 3; ++q) {         // kw taps: operand = the halo box shifted by q rows, W lines 10 rows apart
+                                const uint64_t adesc = umma_desc_sw128(sa + q * 128, 16, 1280);
+                                const uint64_t bdesc = umma_desc_sw128(sa + A_REGION + q * B_TAP, 16, 1024);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                            }
+                            nmma += 12;
+                        } else {
+                            const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+                            const uint64_t bdesc = umma_desc_sw128(sa + A_REGION, 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                            nmma += 4;
+                        }
                         umma_commit_2sm(empty0 + 8 * s, 3);       // frees the slot in both CTAs
                     }
                     __syncwarp();
@@ -675,7 +721,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc, 3);   // accumulator complete -> both epilogues
                 __syncwarp();
             }
-            if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 256u * 256u * 16u);
+            if (elect_one()) mma_count_flush(&g_mma_flops_igemm, nmma, 2u * 256u * (uint32_t)BN * 16u);
         }
     } else if (warp >= 4 && warp < 8) {
         // ============================ epilogue (in both CTAs): own 128 accumulator rows ============================
@@ -946,7 +992,10 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     const int bn = std::min(256, Cout);
     g.n_tiles = Cout / bn;
     g.kc = Cin / 64;
-    const bool pairk = use_pair_kernel(bn, g.m_tiles);
+    static int halo_pair_mode = -1;                        // CTA-pair W-halo kernel: on unless MMAD_CONV_HALO_PAIR=0
+    if (halo_pair_mode < 0) { const char* e = getenv("MMAD_CONV_HALO_PAIR"); halo_pair_mode = e ? atoi(e) : 1; }
+    const bool halo_pair = halo && halo_pair_mode != 0 && g.m_tiles >= 2 && !ep.head_out;
+    const bool pairk = halo_pair || use_pair_kernel(bn, g.m_tiles);
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
     static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
     if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
@@ -959,7 +1008,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
         stages = 8;
         while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024) --stages;
     }
-    if (halo) stages = 4;                                  // the halo producers assume a 4-slot ring (fits: 4 x 44 KB + 2 x 16 KB)
+    if (halo && !pairk) stages = 4;                        // the single-CTA halo producers assume a 4-slot ring (fits: 4 x 44 KB + 2 x 16 KB)
     g.stages = stages;
     const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0);
     MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_fwd: shared memory budget exceeded");
@@ -1019,10 +1068,12 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     if (pairk) {
         static DevOnce attr_done;
         if (attr_done.need()) {
-            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
-        launch_pdl(conv3d_igemm_pair_kernel, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        if (halo_pair) launch_pdl(conv3d_igemm_pair_kernel<true>, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else launch_pdl(conv3d_igemm_pair_kernel<false>, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
