@@ -37,6 +37,7 @@ struct ConvGeom {
     int lw, lh, ltd;              // log2(tw), log2(th), log2(td)
     int epi;                      // 1: the epilogue applies ConvEpi (per-channel affine / ReLU / fp32 side output)
     int dyn;                      // 1: tiles are drawn from the global counter (dynamic scheduler), 0: static stride
+    int wres;                     // pair W-halo kernel, Cin == 64: this CTA's 27 x 32 weight rows stay resident in shared memory
     int sched_depth;              // tile-ring slots in use: 2 when dynamic (a CTA holds at most one tile it has not started), 4 when static
     int tiles_w, tiles_h, tiles_d, tiles_n, m_tiles, n_tiles;   // tile index: sample tile fastest, then w, h, d
     int kc;                       // Cin / 64
@@ -519,19 +520,29 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     const int S = g.stages;
+    // Resident weights (WH, Cin == 64): the kernel is bound by the L2 -> SM fabric (~39 B per cycle per SM: 288 KB per tile at
+    // 7.5 k cycles against 3.5 k MMA cycles), and 108 of those 288 KB are the SAME weight rows fetched again for every tile.  With a
+    // single channel slab the CTA's half of all 27 taps (27 x 32 rows x 128 B = 108 KB) fits beside four 20 KB input stages: it is
+    // loaded once per CTA and a stage carries only the halo box.
+    const bool wres = WH && g.wres;
+    const uint32_t stage_sz = wres ? (uint32_t)A_REGION : (uint32_t)STAGE;
+    const uint32_t wres_bytes = wres ? 27u * B_TAP : 0u;
     const uint32_t stage0 = base;
-    const uint32_t out0 = base + (uint32_t)S * STAGE;
-    unsigned char* tail = sm + (size_t)S * STAGE + (size_t)g.nout * kStageOutBytes;
+    const uint32_t wres0 = base + (uint32_t)S * stage_sz;
+    const uint32_t out0 = wres0 + wres_bytes;
+    unsigned char* tail = sm + (size_t)S * stage_sz + wres_bytes + (size_t)g.nout * kStageOutBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tfull0 = empty0 + 8 * S, tempty0 = tfull0 + 16;
     const uint32_t sfull0 = tempty0 + 16, sempty0 = sfull0 + 8 * kSchedSlots;
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * kSchedSlots);
     volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_ptr_s + 4);   // [kSchedSlots]
+    const uint32_t wfull = smem_u32(tmem_ptr_s + 2);             // mbarrier (8 bytes): the resident weights of BOTH CTAs have landed
     float* st_sum = reinterpret_cast<float*>(tmem_ptr_s + 8);
     float* st_sq = st_sum + 2 * g.Cout;
     float* ep_sc = st_sq + 2 * g.Cout;
     float* ep_sh = ep_sc + g.Cout;
     float* ep_fb = ep_sh + g.Cout;
+    float* ep_hw = ep_fb + g.Cout;                                // fused head weights (WH variant, ep.head_out)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -542,6 +553,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }   // 4 epilogue warps x 2 CTAs
         // tile ring: the leader's scheduler fills the slot in BOTH CTAs; the consumers of both CTAs release the LEADER's slot
         for (int a = 0; a < kSchedSlots; ++a) { mbar_init(sfull0 + 8 * a, 1); mbar_init(sempty0 + 8 * a, 2 * kSchedConsumers); }
+        mbar_init(wfull, 1);
         mbar_fence_init();
         tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmC);
     }
@@ -615,6 +627,15 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - 1);
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t nprod = (uint32_t)min(kConvProducers, S);     // see the ring invariant above: stages >= active producers
+            if (wres && me == 0) {
+                // once per CTA: this CTA's 32 rows of all 27 taps (nine boxes of three kw taps); the leader's barrier counts both CTAs
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(wfull, 2u * 27u * B_TAP);
+                    for (int t = 0; t < 9; ++t)
+                        tma_load_4d_2sm(wres0 + (uint32_t)t * 3u * B_TAP, &tmBh, wfull, 0, (int)rank * (BN / 2), 0, t * 3);
+                }
+                __syncwarp();
+            }
             for (; WH;) {
                 // W-halo stages (kd, channel slab, kh): one halo box + this CTA's 32 weight rows of the three kw taps
                 const int st = next_tile();
@@ -631,10 +652,10 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             if (turn == me) {
                                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                                 if (elect_one()) {
-                                    if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * STAGE);
-                                    const uint32_t sa = stage0 + s * STAGE;
+                                    if (leader) mbar_arrive_expect_tx(full0 + 8 * s, 2 * stage_sz);
+                                    const uint32_t sa = stage0 + s * stage_sz;
                                     tma_load_5d_2sm(sa, &tmA, full0 + 8 * s, cc * 64, w0, h0 + b, d0 + a, n);
-                                    tma_load_4d_2sm(sa + A_REGION, &tmBh, full0 + 8 * s, 0, (int)rank * (BN / 2), cc, (a * 3 + b) * 3);
+                                    if (!wres) tma_load_4d_2sm(sa + A_REGION, &tmBh, full0 + 8 * s, 0, (int)rank * (BN / 2), cc, (a * 3 + b) * 3);
                                 }
                                 __syncwarp();
                             }
@@ -682,6 +703,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             while (next_tile() < total_super) {}
         } else {
             uint32_t s = 0, ph = 0, it = 0, nmma = 0;
+            if (wres) { mbar_wait(wfull, 0); tc_fence_after(); }
             for (;; ++it) {
                 const int st = next_tile();
                 if (st >= total_super) break;
@@ -695,13 +717,15 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int k = 0; k < ksteps_t; ++k) {
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t sa = stage0 + s * STAGE;
+                    const uint32_t sa = stage0 + s * (WH ? stage_sz : (uint32_t)STAGE);
                     if (elect_one()) {
                         if (WH) {
+                            // stage k of a tile = (kd, kh) = (k / 3, k % 3) when the weights are resident (one channel slab)
+                            const uint32_t sb = wres ? wres0 + (uint32_t)k * 3u * B_TAP : sa + A_REGION;
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {         // kw taps: operand = the halo box shifted by q rows, W lines 10 rows apart
                                 const uint64_t adesc = umma_desc_sw128(sa + q * 128, 16, 1280);
-                                const uint64_t bdesc = umma_desc_sw128(sa + A_REGION + q * B_TAP, 16, 1024);
+                                const uint64_t bdesc = umma_desc_sw128(sb + q * B_TAP, 16, 1024);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
                             }
@@ -735,6 +759,8 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
                 ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
             }
+            if (BN == 64 && ep.head_out)
+                for (int c = et; c < ep.head_k * 64; c += 128) ep_hw[c] = ep.head_w[c];
             named_bar_sync(2, 128);
         }
         for (;; ++it) {
@@ -758,18 +784,41 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
             mbar_wait(tfull0 + 8 * acc, aph);
             tc_fence_after();
+            float hacc[kHeadMaxK];
+#pragma unroll
+            for (int k = 0; k < kHeadMaxK; ++k) hacc[k] = 0.f;
             for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
                 const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
-                if (et == 0) {
-                    if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                if (!ep.nostore) {
+                    if (et == 0) {
+                        if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+                    }
+                    named_bar_sync(2, 128);
                 }
-                named_bar_sync(2, 128);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
                     if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
+                    if (BN == 64 && ep.head_out) {
+                        // 1x1x1 head on the values as they would be stored (rounded to bf16), fp32 accumulation (see the single-CTA kernel)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))));
+#pragma unroll
+                        for (int k = 0; k < kHeadMaxK; ++k) {
+                            if (k < ep.head_k) {
+                                const float4* hw4 = reinterpret_cast<const float4*>(ep_hw + k * 64 + half * 32);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 w4 = hw4[j];
+                                    hacc[k] = fmaf(__uint_as_float(v[4 * j]), w4.x, hacc[k]); hacc[k] = fmaf(__uint_as_float(v[4 * j + 1]), w4.y, hacc[k]);
+                                    hacc[k] = fmaf(__uint_as_float(v[4 * j + 2]), w4.z, hacc[k]); hacc[k] = fmaf(__uint_as_float(v[4 * j + 3]), w4.w, hacc[k]);
+                                }
+                            }
+                        }
+                    }
+                    if (ep.nostore) continue;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -782,6 +831,17 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                      : "memory");
                     }
                 }
+                if (BN == 64 && ep.head_out && row_ok) {
+                    const int od = d0 + rdi, oh = h0 + rhi, ow = w0 + rwi;
+                    if (od < ep.hD && oh < ep.hH && ow < ep.hW) {
+#pragma unroll
+                        for (int k = 0; k < kHeadMaxK; ++k)
+                            if (k < ep.head_k)
+                                ep.head_out[(((long long)(n + rni) * ep.head_k + k) * ep.hD + od) * ((long long)ep.hH * ep.hW) + (long long)oh * ep.hW + ow] =
+                                    hacc[k] + __ldg(ep.head_b + k);
+                    }
+                }
+                if (ep.nostore) continue;
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
                 if (et == 0 && real) {
@@ -871,9 +931,11 @@ static void pick_tile(int N, int D, int H, int W, int Wo, int Ho, int Do, int k,
     pick_chunk(128, N, W, H, D, Wo, Ho, Do, k, stride, pad, dil, tw, th, td, tn);
 }
 
-static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false, bool epi = false) {
+// wres: resident weights of the pair W-halo kernel (27 taps x bn rows x 128 B kept once, stages carry only the halo box)
+static int conv_smem_bytes(int bn, int ks, int stages, int nout, int cout, bool halo = false, bool epi = false, bool wres = false) {
     const int a_region = halo ? kHaloTileBytes : ks * kATileBytes;
-    return 1024 + stages * (a_region + ks * bn * 128) + nout * kStageOutBytes + (2 * stages + 4 + 2 * kSchedSlots) * 8 + 32 +
+    const int stage = wres ? a_region : a_region + ks * bn * 128;
+    return 1024 + stages * stage + (wres ? 27 * bn * 128 : 0) + nout * kStageOutBytes + (2 * stages + 4 + 2 * kSchedSlots) * 8 + 32 +
            (epi ? 7 : 4) * cout * 4 + (epi ? kHeadMaxK * 64 * 4 : 0);
 }
 
@@ -994,23 +1056,28 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     g.kc = Cin / 64;
     static int halo_pair_mode = -1;                        // CTA-pair W-halo kernel: on unless MMAD_CONV_HALO_PAIR=0
     if (halo_pair_mode < 0) { const char* e = getenv("MMAD_CONV_HALO_PAIR"); halo_pair_mode = e ? atoi(e) : 1; }
-    const bool halo_pair = halo && halo_pair_mode != 0 && g.m_tiles >= 2 && !ep.head_out;
+    const bool halo_pair = halo && halo_pair_mode != 0 && g.m_tiles >= 2;
     const bool pairk = halo_pair || use_pair_kernel(bn, g.m_tiles);
+    // resident weights (pair W-halo kernel, Cin == 64): measured neutral (UNet eval 17.0 / 17.2 ms with, 17.5 / 16.9 without; the
+    // resident copy costs one of five pipeline stages), so OFF unless MMAD_CONV_WRES=1
+    static int wres_mode = -1;
+    if (wres_mode < 0) { const char* e = getenv("MMAD_CONV_WRES"); wres_mode = e ? atoi(e) : 0; }
+    g.wres = (halo_pair && Cin == 64 && wres_mode != 0) ? 1 : 0;
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
     static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
     if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
     const int ks = halo ? 3 : (ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));     // K-steps per stage (one weight box per stage)
     g.nout = (bn == 256 && !pairk) ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024) --stages;
-    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
+    while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024) --stages;
+    if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {
         g.nout = 1;                                        // trade the second epilogue buffer for pipeline depth
         stages = 8;
-        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0) > 227 * 1024) --stages;
+        while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024) --stages;
     }
     if (halo && !pairk) stages = 4;                        // the single-CTA halo producers assume a 4-slot ring (fits: 4 x 44 KB + 2 x 16 KB)
     g.stages = stages;
-    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0);
+    const int smem = conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0);
     MMAD_CHECK_ARG(smem <= 227 * 1024, "conv3d_fwd: shared memory budget exceeded");
 
     CUtensorMap tmA, tmB, tmC;
