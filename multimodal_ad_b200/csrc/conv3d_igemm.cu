@@ -134,7 +134,10 @@ __device__ __forceinline__ void conv_epilogue_affine(uint32_t (&v)[32], int cb, 
     }
 }
 
-template <int BN, int KS, bool WH = false>
+// EPI: compile the ConvEpi epilogue in (affine / ReLU / fp32 side output / fused head).  The plain instantiation keeps the
+// epilogue of the training path free of it: on ResNet3D-50 (57 convolutions, most of them short 1x1x1 tiles whose time IS the
+// epilogue) the run-time-switched version cost 2.7 % of the step.
+template <int BN, int KS, bool WH = false, bool EPI = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
@@ -353,13 +356,13 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int et = threadIdx.x - 128;                         // 0..127
         const int row = ew * 32 + lane;                           // output voxel inside the tile == TMEM lane
         uint32_t it = 0, nstore = 0;
-        if (g.epi) {
+        if (EPI) {
             for (int c = et; c < g.Cout; c += 128) {
                 ep_sc[c] = ep.scale ? ep.scale[c] : 1.f;
                 ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
                 ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
             }
-            if (ep.head_out)
+            if (EPI && ep.head_out)
                 for (int c = et; c < ep.head_k * 64; c += 128) ep_hw[c] = ep.head_w[c];
             named_bar_sync(2, 128);
         }
@@ -387,7 +390,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < kHeadMaxK; ++k) hacc[k] = 0.f;
             for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
                 const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
-                if (!ep.nostore) {
+                if (!(EPI && ep.nostore)) {
                     if (et == 0) {                                // the store that last used this buffer has finished reading it
                         if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
                     }
@@ -398,8 +401,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
-                    if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
-                    if (BN == 64 && ep.head_out) {
+                    if (EPI) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
+                    if (EPI && BN == 64 && ep.head_out) {
                         // 1x1x1 head on the values as they would be stored (rounded to bf16), fp32 accumulation
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))));
@@ -416,7 +419,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         }
                     }
-                    if (ep.nostore) continue;
+                    if (EPI && ep.nostore) continue;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -429,7 +432,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      : "memory");
                     }
                 }
-                if (BN == 64 && ep.head_out && row_ok) {
+                if (EPI && BN == 64 && ep.head_out && row_ok) {
                     const int od = d0 + rdi, oh = h0 + rhi, ow = w0 + rwi;
                     if (od < ep.hD && oh < ep.hH && ow < ep.hW) {
 #pragma unroll
@@ -439,7 +442,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     hacc[k] + __ldg(ep.head_b + k);
                     }
                 }
-                if (ep.nostore) continue;
+                if (EPI && ep.nostore) continue;
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
                 if (et == 0) {
@@ -501,7 +504,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // 64-channel super tile, every CTA stages its own 10 x 4 x 4 halo box per (kd, kh, channel slab) and only 32 of the 64 weight rows
 // of the three kw taps.  The single-CTA N = 64 kernel is bound by shared-memory bandwidth (44 KB of TMA writes + 72 KB of operand
 // reads per 384 MMA cycles); here a CTA moves 32 + 60 KB per stage.
-template <bool WH>
+template <bool WH, bool EPI = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                          const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
@@ -753,13 +756,13 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int et = threadIdx.x - 128;
         const int row = ew * 32 + lane;
         uint32_t it = 0, nstore = 0;
-        if (g.epi) {
+        if (EPI) {
             for (int c = et; c < g.Cout; c += 128) {
                 ep_sc[c] = ep.scale ? ep.scale[c] : 1.f;
                 ep_sh[c] = ep.shift ? ep.shift[c] : 0.f;
                 ep_fb[c] = ep.f32_bias ? ep.f32_bias[c] : 0.f;
             }
-            if (BN == 64 && ep.head_out)
+            if (EPI && BN == 64 && ep.head_out)
                 for (int c = et; c < ep.head_k * 64; c += 128) ep_hw[c] = ep.head_w[c];
             named_bar_sync(2, 128);
         }
@@ -789,7 +792,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             for (int k = 0; k < kHeadMaxK; ++k) hacc[k] = 0.f;
             for (int sub = 0; sub < BN / 64; ++sub, ++nstore) {
                 const uint32_t ob = out0 + (g.nout == 2 ? (nstore & 1) : 0u) * kStageOutBytes;
-                if (!ep.nostore) {
+                if (!(EPI && ep.nostore)) {
                     if (et == 0) {
                         if (g.nout == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
                     }
@@ -800,8 +803,8 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + sub * 64 + half * 32, v);
                     tmem_ld_wait();
-                    if (g.epi) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
-                    if (BN == 64 && ep.head_out) {
+                    if (EPI) conv_epilogue_affine(v, nt * BN + sub * 64 + half * 32, ep, ep_sc, ep_sh, ep_fb, row_ok, row_vox);
+                    if (EPI && BN == 64 && ep.head_out) {
                         // 1x1x1 head on the values as they would be stored (rounded to bf16), fp32 accumulation (see the single-CTA kernel)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))));
@@ -818,7 +821,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                             }
                         }
                     }
-                    if (ep.nostore) continue;
+                    if (EPI && ep.nostore) continue;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t p0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
@@ -831,7 +834,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                      : "memory");
                     }
                 }
-                if (BN == 64 && ep.head_out && row_ok) {
+                if (EPI && BN == 64 && ep.head_out && row_ok) {
                     const int od = d0 + rdi, oh = h0 + rhi, ow = w0 + rwi;
                     if (od < ep.hD && oh < ep.hH && ow < ep.hW) {
 #pragma unroll
@@ -841,7 +844,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                     hacc[k] + __ldg(ep.head_b + k);
                     }
                 }
-                if (ep.nostore) continue;
+                if (EPI && ep.nostore) continue;
                 fence_proxy_async_smem();
                 named_bar_sync(2, 128);
                 if (et == 0 && real) {
@@ -1126,7 +1129,11 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     unsigned int* sched = nullptr;
     // dynamic draws pay off where tiles are long and uneven (3x3x3 taps, padding skips, co-running kernels); the short uniform
     // tiles of a 1x1x1 convolution keep the static stride (measured on ResNet3D-50: the per-tile atomic costs 1 % there)
-    g.dyn = (use_dynamic_scheduler() && kd * kh * kw * g.kc >= 16) ? 1 : 0;
+    // ... and layers with only a few tiles per CTA (ResNet3D-50's 3x3x3 convolutions at batch 8: 1.7 - 3.5) lose more to the draw's
+    // start / end latency than they can gain: +0.6 ms on that network's 16.7 ms step.  Dynamic from 4 tiles per CTA (pair) on.
+    const long long work_items = pairk ? (long long)((g.m_tiles + 1) / 2) * g.n_tiles : (long long)g.m_tiles * g.n_tiles;
+    const long long ctas = pairk ? sms / 2 : sms;
+    g.dyn = (use_dynamic_scheduler() && kd * kh * kw * g.kc >= 16 && work_items >= 4 * ctas) ? 1 : 0;
     g.sched_depth = g.dyn ? 2 : kSchedSlots;
     if (g.dyn) {
         sched = sched_counter_slot();
@@ -1135,31 +1142,41 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     if (pairk) {
         static DevOnce attr_done;
         if (attr_done.need()) {
-            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
-        if (halo_pair) launch_pdl(conv3d_igemm_pair_kernel<true>, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
-        else launch_pdl(conv3d_igemm_pair_kernel<false>, dim3(2 * pairs), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        const dim3 pgrid(2 * pairs);
+        if (halo_pair && g.epi) launch_pdl(conv3d_igemm_pair_kernel<true, true>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else if (halo_pair) launch_pdl(conv3d_igemm_pair_kernel<true, false>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else if (g.epi) launch_pdl(conv3d_igemm_pair_kernel<false, true>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else launch_pdl(conv3d_igemm_pair_kernel<false, false>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         MMAD_CUDA(cudaGetLastError());
         count_launch();
         return MMAD_OK;
     }
     const int grid = (int)std::min<long long>((long long)g.m_tiles * g.n_tiles, sms);
-#define MMAD_CONV_LAUNCH(...)                                                                                               \
+#define MMAD_CONV_LAUNCH1(...)                                                                                              \
     do {                                                                                                                    \
-        static DevOnce attr_done;                                                                                      \
-        if (attr_done.need()) {                                                                                                   \
+        static DevOnce attr_done;                                                                                           \
+        if (attr_done.need()) {                                                                                             \
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
         }                                                                                                                   \
         launch_pdl(conv3d_igemm_kernel<__VA_ARGS__>, dim3(grid), dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);    \
     } while (0)
+#define MMAD_CONV_LAUNCH(BN_, KS_, WH_)                                                                                     \
+    do {                                                                                                                    \
+        if (g.epi) MMAD_CONV_LAUNCH1(BN_, KS_, WH_, true); else MMAD_CONV_LAUNCH1(BN_, KS_, WH_, false);                    \
+    } while (0)
     if (halo) MMAD_CONV_LAUNCH(64, 3, true);
-    else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4);
-    else if (bn == 64) MMAD_CONV_LAUNCH(64, 1);
-    else if (bn == 128 && ks == 2) MMAD_CONV_LAUNCH(128, 2);
-    else if (bn == 128) MMAD_CONV_LAUNCH(128, 1);
-    else MMAD_CONV_LAUNCH(256, 1);
+    else if (bn == 64 && ks == 4) MMAD_CONV_LAUNCH(64, 4, false);
+    else if (bn == 64) MMAD_CONV_LAUNCH(64, 1, false);
+    else if (bn == 128 && ks == 2) MMAD_CONV_LAUNCH(128, 2, false);
+    else if (bn == 128) MMAD_CONV_LAUNCH(128, 1, false);
+    else MMAD_CONV_LAUNCH(256, 1, false);
+#undef MMAD_CONV_LAUNCH1
 #undef MMAD_CONV_LAUNCH
     MMAD_CUDA(cudaGetLastError());
     count_launch();
