@@ -261,3 +261,31 @@ def test_stem_space_to_depth_forward_statistics_wgrad(shape, run):
     run.stem_wgrad(xs, dy, n, d, h, w, gw)
     ref.backward(dy.float().permute(0, 4, 1, 2, 3))
     assert _rel(gw, wr.grad) < 1e-4
+
+
+def test_conv_kernel_variants_behind_environment_knobs():
+    """The tuning knobs select other code paths of the same convolution (read once per process, hence a subprocess each): the
+    single-CTA W-halo kernel, the static tile stride, resident weights in the CTA-pair W-halo kernel.  All must agree with torch."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import torch, torch.nn.functional as F
+from multimodal_ad_b200.models.resnet import _Run
+r = _Run(torch.device("cuda", 0))
+g = torch.Generator(device="cuda").manual_seed(7)
+for (n, d, h, w, cin) in ((2, 24, 28, 31, 64), (1, 32, 32, 45, 192)):
+    x = torch.randn((n, d, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn((64, 27, cin), device="cuda", generator=g) / (27 * cin) ** 0.5).to(torch.bfloat16)
+    y, part = r.conv(x, wt, 64, 3, 1, 1, 1, True)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), wt.float().reshape(64, 3, 3, 3, cin).permute(0, 4, 1, 2, 3), padding=1).permute(0, 2, 3, 4, 1)
+    assert torch.all((y.float() - ref).abs() <= 2 ** -8 * ref.abs() + 1e-4)
+    assert torch.allclose(part.sum(0)[:, 0], y.float().reshape(-1, 64).sum(0), rtol=1e-4, atol=1e-2)
+print("ok")
+'''
+    for knobs in ({"MMAD_CONV_HALO_PAIR": "0"}, {"MMAD_CONV_DYN": "0"}, {"MMAD_CONV_WRES": "1"}, {"MMAD_CONV_HALO": "0"}):
+        env = dict(os.environ, PYTHONPATH=root, **knobs)
+        res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0 and "ok" in res.stdout, (knobs, res.stdout[-500:], res.stderr[-1500:])

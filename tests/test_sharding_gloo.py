@@ -81,7 +81,17 @@ def _reducer_worker(rank, world, port, out):
         assert g1.shape == (4, 6) and g2.shape == (30,) and g1.untyped_storage().data_ptr() != g2.untyped_storage().data_ptr()
         red.push(g2)
         red.push(g3)
+        # flush(): the open bucket (g2's) is closed and reduced NOW (the backward pass does this before its last stage); a
+        # gradient allocated afterwards starts a new bucket
+        assert not red._buckets[-1]["launched"]
+        red.flush()
+        assert red._buckets[-1]["closed"] and red._buckets[-1]["launched"]
+        w4 = torch.nn.Parameter(torch.zeros(12))
+        g4 = red.alloc_like(w4); g4.fill_(float(2 * rank))
+        assert g4.untyped_storage().data_ptr() != g2.untyped_storage().data_ptr()
+        red.push(g4)
         red.finish(lin.parameters())
+        assert torch.allclose(g4, torch.full((12,), 1.0))
         assert torch.allclose(g1, torch.full((4, 6), 1.5)) and torch.allclose(g2, torch.full((30,), 1.5)) and torch.allclose(g3, torch.full((2,), 7.0))
         assert torch.allclose(big, torch.full((16,), 1.5))
         assert torch.allclose(small[0], torch.full((3,), 15.0)) and torch.allclose(small[1], torch.full((2, 2), 0.5))

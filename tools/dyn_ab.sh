@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the dynamic tile scheduler at N GPUs (usage: tools/dyn_ab.sh N)
 N=${1:-2}
-for d in 1 0 1 0; do
+for d in 1 0; do
   if [ "$N" = "1" ]; then
     MMAD_CONV_DYN=$d timeout 300 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/ab.log 2> gpurun_out/ab.err
   else
