@@ -1061,16 +1061,17 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     if (halo_pair_mode < 0) { const char* e = getenv("MMAD_CONV_HALO_PAIR"); halo_pair_mode = e ? atoi(e) : 1; }
     const bool halo_pair = halo && halo_pair_mode != 0 && g.m_tiles >= 2;
     const bool pairk = halo_pair || use_pair_kernel(bn, g.m_tiles);
-    // resident weights (pair W-halo kernel, Cin == 64): measured neutral (UNet eval 17.0 / 17.2 ms with, 17.5 / 16.9 without; the
-    // resident copy costs one of five pipeline stages), so OFF unless MMAD_CONV_WRES=1
+    // resident weights (pair W-halo kernel, Cin == 64), with ONE epilogue staging buffer so that five (training) / four (ConvEpi)
+    // input stages still fit: UNet3D eval forward 16.7 - 16.8 ms with, 17.3 - 17.8 ms without; ResNet3D-18 step neutral.
+    // On unless MMAD_CONV_WRES=0.
     static int wres_mode = -1;
-    if (wres_mode < 0) { const char* e = getenv("MMAD_CONV_WRES"); wres_mode = e ? atoi(e) : 0; }
+    if (wres_mode < 0) { const char* e = getenv("MMAD_CONV_WRES"); wres_mode = e ? atoi(e) : 1; }
     g.wres = (halo_pair && Cin == 64 && wres_mode != 0) ? 1 : 0;
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
     static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
     if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
     const int ks = halo ? 3 : (ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));     // K-steps per stage (one weight box per stage)
-    g.nout = (bn == 256 && !pairk) ? 1 : 2;
+    g.nout = ((bn == 256 && !pairk) || g.wres) ? 1 : 2;   // resident weights: one staging buffer buys the fifth input stage
     int stages = 8;
     while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024) --stages;
     if (conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024 || (stages < 3 && g.nout == 2 && ks > 1)) {

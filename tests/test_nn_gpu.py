@@ -265,7 +265,7 @@ def test_stem_space_to_depth_forward_statistics_wgrad(shape, run):
 
 def test_conv_kernel_variants_behind_environment_knobs():
     """The tuning knobs select other code paths of the same convolution (read once per process, hence a subprocess each): the
-    single-CTA W-halo kernel, the static tile stride, resident weights in the CTA-pair W-halo kernel.  All must agree with torch."""
+    single-CTA W-halo kernel, the static tile stride, streamed instead of resident weights in the CTA-pair W-halo kernel.  All must agree with torch."""
     import os
     import subprocess
     import sys
@@ -285,7 +285,7 @@ for (n, d, h, w, cin) in ((2, 24, 28, 31, 64), (1, 32, 32, 45, 192)):
     assert torch.allclose(part.sum(0)[:, 0], y.float().reshape(-1, 64).sum(0), rtol=1e-4, atol=1e-2)
 print("ok")
 '''
-    for knobs in ({"MMAD_CONV_HALO_PAIR": "0"}, {"MMAD_CONV_DYN": "0"}, {"MMAD_CONV_WRES": "1"}, {"MMAD_CONV_HALO": "0"}):
+    for knobs in ({"MMAD_CONV_HALO_PAIR": "0"}, {"MMAD_CONV_DYN": "0"}, {"MMAD_CONV_WRES": "0"}, {"MMAD_CONV_HALO": "0"}):
         env = dict(os.environ, PYTHONPATH=root, **knobs)
         res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
         assert res.returncode == 0 and "ok" in res.stdout, (knobs, res.stdout[-500:], res.stderr[-1500:])
