@@ -26,6 +26,13 @@ print("KEYS", ",".join(net.state_dict().keys()))
 print("CHECKSUM", sum(float(p.detach().double().abs().sum()) for p in net.parameters()))
 import models
 print("OTHER", getattr(__import__("models.network", fromlist=["x"]), "__file__", "?"))
+try:
+    import types
+    sys.modules.setdefault("torchsummary", types.SimpleNamespace(summary=lambda *a, **k: None))   # the reference's unet3d.py imports it
+    from models.unet3d import UNet3D                             # image_features.py:6, verbatim
+    print("UNET", UNet3D.__module__)
+except Exception as e:
+    print("UNET", "error:" + type(e).__name__)
 '''
 
 
@@ -50,3 +57,5 @@ def test_reference_script_builds_the_accelerated_network_through_the_shim(tmp_pa
     assert abs(float(got["CHECKSUM"]) - float(ref["CHECKSUM"])) <= 1e-9 * float(ref["CHECKSUM"])
     # modules the accelerated path does not provide still resolve to the reference's own files
     assert got["OTHER"].startswith(REF)
+    # image_features.py:6 `from models.unet3d import UNet3D`
+    assert ref["UNET"] == "models.unet3d" and got["UNET"] == "multimodal_ad_b200.models.unet3d"
