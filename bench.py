@@ -10,6 +10,7 @@ Nested objects on the same JSON line (each with its own roofline):
   resnet3d18_train_91x109x91  the same training step on the reference's own volume (config/config_unet.json input_D/H/W)
   resnet3d50_train            configs[3] as the reference can run it (cfg_denseNet.json: model_type resnet, depth 50)
   unet3d_roi_extract          configs[4]'s image branch: UNet3D forward (eval) + on-device ROI pooling of the 64-channel map
+  unet3d_train                UNet3D forward + backward + Adam (models/unet3d.py stacks through the same kernels)
   torch_gpu_baseline          stock PyTorch / cuDNN on the same GPU for the same ResNet3D-18 step (context, not the target)
 
     python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
@@ -764,6 +765,71 @@ def run_unet_roi_extract(args, rank, world, dev, dist, batch=8, steps=10, want_c
     return res
 
 
+def run_unet_train(args, rank, world, dev, dist, batch=4, steps=5):
+    """UNet3D(1, 1) training step on batch `batch` of 1x91x109x91 volumes per GPU: forward + voxel-wise MSE loss + backward
+    (+ one coalesced gradient all-reduce under data parallel) + Adam - the forward AND backward of unet3d.py's Conv3d + BatchNorm3d +
+    ReLU stacks through the C-ABI kernels."""
+    import torch
+
+    from multimodal_ad_b200 import _lib
+    from multimodal_ad_b200.models import unet3d
+    from multimodal_ad_b200.sharding import max_over_ranks
+
+    torch.manual_seed(0)
+    model = unet3d.UNet3D(in_channels=1, num_classes=1).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5, fused=True)
+    g = torch.Generator(device=dev).manual_seed(400 + rank)
+    x = torch.rand((batch, 1) + SHAPE, device=dev, generator=g)
+    y = torch.rand((batch, 1) + SHAPE, device=dev, generator=g)
+    params = [p for p in model.parameters()]
+
+    def step():
+        loss = ((model(x) - y) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if dist is not None:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    f0, l0 = _lib.executed_mma_flops(), _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(a.elapsed_time(b), dev) / steps
+    executed = (_lib.executed_mma_flops() - f0) / steps
+    flops = 3.0 * unet3d_forward_flops() * batch                          # forward + dgrad + wgrad of (nearly) every convolution
+    peak, peak_src = tensor_peak()
+    ach = flops / (ms * 1e-3) / 1e12
+    res = {"metric": "unet3d_train_volumes_per_sec", "value": world * batch / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms,
+           "steps": steps, "dtype": "bf16", "scaling": "weak",
+           "config": {"workload": f"unet3d_bf16_train_batch{batch}_1x91x109x91 (models/unet3d.py, padded grid 96x112x96)", "batch_per_gpu": batch,
+                      "parallelism": f"data parallel x{world}" + (", one coalesced gradient all-reduce after backward" if world > 1 else ""),
+                      "step": "forward + MSE loss + backward + Adam", "launch": "eager"},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_flops_per_step": flops, "executed_flops_per_step": executed,
+                        "executed_frac": executed / (ms * 1e-3) / 1e12 / peak},
+           "gpu_launches": _lib.launch_count() - l0, "loss": float(loss.detach())}
+    del model, opt, x, y
+    torch.cuda.empty_cache()
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # arms
 # ---------------------------------------------------------------------------------------------------------------------
@@ -829,6 +895,7 @@ def run_cuda_arm(args, rank: int, local_rank: int, world: int):
             metric="resnet3d50_train_volumes_per_sec"))
         guarded("unet3d_roi_extract", lambda: run_unet_roi_extract(args, rank, world, dev, dist, steps=min(args.steps, 10),
                                                                    want_cpu=solo and not args.no_cpu_baseline))
+        guarded("unet3d_train", lambda: run_unet_train(args, rank, world, dev, dist, steps=min(args.steps, 5)))
         if solo:
             guarded("torch_gpu_baseline", lambda: torch_gpu_baseline(dev))
     cpu_baseline = None

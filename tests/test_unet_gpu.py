@@ -361,3 +361,32 @@ def test_eval_mode_with_autograd_and_frozen_parameters(built_lib):
     for k, v in model.state_dict().items():
         if "running" in k or "tracked" in k:
             assert torch.equal(v.cpu(), sd[k]), k
+
+
+def test_two_output_classes_train_and_eval(built_lib):
+    """num_classes = 2 (the constructor argument of unet3d.py:100): the head kernels take K <= 8 classes, in the fused eval tail
+    and in the training path."""
+    from multimodal_ad_b200.models import unet3d
+
+    target = (16, 16, 24)
+    torch.manual_seed(6)
+    model = unet3d.UNet3D(in_channels=1, num_classes=2).cuda()
+    model.target = target
+    x = torch.rand((2, 1, 15, 13, 22), device="cuda")
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.eval()
+    with torch.no_grad():
+        out_e = model(x)
+    ref_e = unet3d_oracle(sd, x.cpu(), False, emulate_bf16=True, target=target)
+    assert out_e.shape == ref_e.shape == (2, 2, 15, 13, 22) and _rel(out_e.cpu(), ref_e) < 2e-2
+    model.train()
+    out = model(x)
+    wgt = torch.randn_like(out) / out.numel() ** 0.5
+    (out * wgt).sum().backward()
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    ref = unet3d_oracle(leaves, x.cpu(), True, emulate_bf16=True, target=target)
+    (ref * wgt.cpu()).sum().backward()
+    assert _rel(out.detach().cpu(), ref.detach()) < 3e-2                    # free-running, batch statistics over 2 x 16x16x24 voxels
+    named = dict(model.named_parameters())
+    for k in ("s_block1.conv3.weight", "s_block1.conv3.bias"):
+        assert named[k].grad.shape == leaves[k].grad.shape and _rel(named[k].grad.cpu(), leaves[k].grad) < 5e-2, k
