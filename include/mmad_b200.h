@@ -13,8 +13,10 @@
  *   the empty /root/reference/models/ROI_pol.py the north star names.
  * Part 2  — Conv3d / BatchNorm3d / ReLU stacks of the 3D-CNN image branch
  *   replaces the torch.nn.Conv3d / BatchNorm3d / ReLU / MaxPool3d calls of
- *   /root/reference/models/resnet.py:14-23,40-69,112-215 (and resnet18.py,
- *   ImageEncoder.py, unet3d.py which repeat them), forward and backward.
+ *   /root/reference/models/resnet.py:14-23,40-109,112-215 (and resnet18.py,
+ *   ImageEncoder.py which repeat them) and of /root/reference/models/unet3d.py:14-46,
+ *   51-84,116-157 (Conv3d with bias, MaxPool3d(2,2), ConvTranspose3d(2,2), channel
+ *   concatenation, pad to 96x112x96 / crop back), forward and backward.
  */
 #ifndef MMAD_B200_H
 #define MMAD_B200_H

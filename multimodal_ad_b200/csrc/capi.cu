@@ -14,7 +14,7 @@ long long mma_flops_stem();
 
 extern "C" {
 const char* mmad_last_error(void) { return mmad::last_error_ref().c_str(); }
-int mmad_abi_version(void) { return 1; }
+int mmad_abi_version(void) { return 2; }   // 2: round 2 (im2col stem entry points removed, UNet3D entry points added)
 int64_t mmad_launch_count(void) { return mmad::g_launches.load(); }
 int64_t mmad_executed_mma_flops(void) {
     const long long a = mmad::mma_flops_igemm(), b = mmad::mma_flops_wgrad(), c = mmad::mma_flops_stem();

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"declared in include/ but not exported: {missing}"
     lib.mmad_abi_version.restype = ctypes.c_int
-    assert lib.mmad_abi_version() == 1
+    assert lib.mmad_abi_version() == 2
     lib.mmad_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.mmad_last_error(), bytes)       # the LAST failure of this thread: earlier tests may have provoked one
 
