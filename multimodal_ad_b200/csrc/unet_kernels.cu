@@ -40,8 +40,10 @@ constexpr int kF1Sx = (kF1Td + 2) * (kF1Th + 2) * (kF1Tw + 2);
 
 // STATS: per-channel sum / sum of squares of the stored values (training).  EPI: stored = relu(acc * scale[c] + shift[c]) - in
 // eval mode the BatchNorm3d + ReLU that follow the convolution (and its bias) are folded in, the pre-activation is never written.
-// A thread computes two W-adjacent voxels x 32 channels: every weight vector fetched from shared memory (a broadcast LDS.128)
-// feeds 8 FMAs, so the kernel is bound by the FP32 pipe (864 FMAs per voxel), not by shared-memory traffic.
+// A thread computes 8 W-consecutive voxels x 8 channels (one 16-byte chunk of the output row): the four lanes of a voxel group
+// write 64 contiguous bytes per store (full sectors - one voxel's 32 channels), every broadcast weight vector feeds 16 FMAs and
+// every staged input value 24, so the kernel is bound by the FP32 pipe (864 FMAs per voxel) and by the 128-byte-per-voxel
+// output stream, not by shared-memory traffic or partial-sector writes.
 template <bool STATS, bool EPI>
 __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt, uint4* __restrict__ y,
                                                             float* __restrict__ stats_partials, const float* __restrict__ ep_scale,
@@ -56,10 +58,12 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
     for (int i = threadIdx.x; i < 27 * 32; i += 256) sw[i] = wgt[(i & 31) * 27 + (i >> 5)];      // [tap][co]
     if (threadIdx.x < 128) sred[threadIdx.x] = 0.f;
     if (EPI && threadIdx.x < 64) sep[threadIdx.x] = threadIdx.x < 32 ? ep_scale[threadIdx.x] : ep_shift[threadIdx.x - 32];
-    const int pw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
-    float ssum[STATS ? 32 : 1], ssq[STATS ? 32 : 1];
+    const int cq = threadIdx.x & 3;                         // channel chunk: channels 8 cq .. 8 cq + 7
+    const int vg = threadIdx.x >> 2;                        // voxel group: 8 consecutive voxels along W
+    const int wg = vg & 1, th = (vg >> 1) & 7, td = vg >> 4;
+    float ssum[STATS ? 8 : 1], ssq[STATS ? 8 : 1];
 #pragma unroll
-    for (int c = 0; c < (STATS ? 32 : 1); ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+    for (int c = 0; c < (STATS ? 8 : 1); ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
     const long long total = (long long)N * tiles_d * tiles_h * tiles_w;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         long long r = t;
@@ -75,62 +79,65 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
                         ? __ldg(x + (((long long)n * D + id) * H + ih) * W + iw) : 0.f;
         }
         __syncthreads();
-        float acc0[32], acc1[32];
+        float acc[8][8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+        for (int v = 0; v < 8; ++v)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
-                const float* row = sx + ((td + a) * (kF1Th + 2) + th + b) * (kF1Tw + 2) + 2 * pw;
-                const float xr[4] = {row[0], row[1], row[2], row[3]};
+                const float* row = sx + ((td + a) * (kF1Th + 2) + th + b) * (kF1Tw + 2) + wg * 8;
+                float xr[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) xr[k] = row[k];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float4* wp = reinterpret_cast<const float4*>(sw + ((a * 3 + b) * 3 + c) * 32);
+                    const float4* wp = reinterpret_cast<const float4*>(sw + ((a * 3 + b) * 3 + c) * 32 + cq * 8);
+                    const float4 wa = wp[0], wb = wp[1];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 w4 = wp[q];
-                        acc0[4 * q] = fmaf(xr[c], w4.x, acc0[4 * q]); acc0[4 * q + 1] = fmaf(xr[c], w4.y, acc0[4 * q + 1]);
-                        acc0[4 * q + 2] = fmaf(xr[c], w4.z, acc0[4 * q + 2]); acc0[4 * q + 3] = fmaf(xr[c], w4.w, acc0[4 * q + 3]);
-                        acc1[4 * q] = fmaf(xr[c + 1], w4.x, acc1[4 * q]); acc1[4 * q + 1] = fmaf(xr[c + 1], w4.y, acc1[4 * q + 1]);
-                        acc1[4 * q + 2] = fmaf(xr[c + 1], w4.z, acc1[4 * q + 2]); acc1[4 * q + 3] = fmaf(xr[c + 1], w4.w, acc1[4 * q + 3]);
+                    for (int v = 0; v < 8; ++v) {
+                        const float xv = xr[v + c];
+                        acc[v][0] = fmaf(xv, wa.x, acc[v][0]); acc[v][1] = fmaf(xv, wa.y, acc[v][1]);
+                        acc[v][2] = fmaf(xv, wa.z, acc[v][2]); acc[v][3] = fmaf(xv, wa.w, acc[v][3]);
+                        acc[v][4] = fmaf(xv, wb.x, acc[v][4]); acc[v][5] = fmaf(xv, wb.y, acc[v][5]);
+                        acc[v][6] = fmaf(xv, wb.z, acc[v][6]); acc[v][7] = fmaf(xv, wb.w, acc[v][7]);
                     }
                 }
             }
         const int oh = h0 + th, od = d0 + td;
+        if (oh < Ho && od < Do) {
+            uint4* line = y + (((long long)n * Do + od) * Ho + oh) * Wo * 8;        // 64 channels = 8 vectors per voxel
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int ow = w0 + 2 * pw + v;
-            if (ow < Wo && oh < Ho && od < Do) {
-                uint4* dst = y + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 8;      // 64 channels = 8 vectors
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
+            for (int v = 0; v < 8; ++v) {
+                const int ow = w0 + wg * 8 + v;
+                if (ow < Wo) {
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        f[j] = v ? acc1[8 * q + j] : acc0[8 * q + j];
-                        if (EPI) f[j] = fmaxf(fmaf(f[j], sep[8 * q + j], sep[32 + 8 * q + j]), 0.f);
+                        f[j] = acc[v][j];
+                        if (EPI) f[j] = fmaxf(fmaf(f[j], sep[cq * 8 + j], sep[32 + cq * 8 + j]), 0.f);
                     }
                     const uint4 pk = u_pack8(f);
-                    dst[q] = pk;
+                    line[(long long)ow * 8 + cq] = pk;
+                    line[(long long)ow * 8 + 4 + cq] = make_uint4(0u, 0u, 0u, 0u);   // padding channels 32..63
                     if (STATS) {
                         u_unpack8(pk, f);                   // statistics of the rounded values, as the tensor-core epilogue does
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { ssum[8 * q + j] += f[j]; ssq[8 * q + j] += f[j] * f[j]; }
+                        for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
                     }
                 }
-#pragma unroll
-                for (int q = 4; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
     }
     if (STATS && stats_partials) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            float a = ssum[c], b = ssq[c];
+        for (int j = 0; j < 8; ++j) {
+            float a = ssum[j], b = ssq[j];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-            if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[2 * c], a); atomicAdd(&sred[2 * c + 1], b); }
+            for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if ((threadIdx.x & 31) < 4) { atomicAdd(&sred[2 * (cq * 8 + j)], a); atomicAdd(&sred[2 * (cq * 8 + j) + 1], b); }
         }
         __syncthreads();
         if (threadIdx.x < 128) stats_partials[(size_t)blockIdx.x * 128 + threadIdx.x] = threadIdx.x < 64 ? sred[threadIdx.x] : 0.f;
