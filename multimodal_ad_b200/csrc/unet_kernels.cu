@@ -145,26 +145,32 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
 }
 
 // Weight gradient of the first layer: dW[co][tap] = sum_v dy[v][co] * x_ext[v + tap - 1], co < 32 (dy: 64-channel rows, the upper
-// 32 channels are ignored).  Same 8 x 8 x 4 tiles; thread (co = t & 31, tap group = t >> 5) keeps up to 4 taps (g, g+8, g+16, g+24)
-// in registers across all the tiles of its block and writes partials[block][co][tap] (summed by mmad_wgrad_reduce).
+// 32 channels are ignored).  8 x 8 x 4 voxel tiles staged in shared memory (input halo + the 32 dy channels as fp32).  Thread =
+// (4 output channels, 7 taps, one of 8 voxel slices): per voxel one 16-byte load of dy and 7 input loads feed 28 FMAs, all 32
+// lanes of a warp walk the same voxels (the warp IS the voxel slice), so every load is a broadcast / conflict-free.  The 28
+// accumulators live in registers across all tiles of the block; the 8 slices are summed through shared memory at the end and the
+// block writes partials[block][co][tap] (summed over blocks by mmad_wgrad_reduce).
 __global__ void __launch_bounds__(256) conv3d_c1_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dy, float* __restrict__ partials,
                                                               int N, int D, int H, int W, int Do, int Ho, int Wo, int tiles_w, int tiles_h,
                                                               int tiles_d) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sx[6 * 10 * 10];
-    __shared__ float sdy[256 * 33];                         // [voxel][co], padded
-    const int co = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    int toff[4];
-    bool tok[4];
+    __shared__ __align__(16) float sdy[256 * 36];           // [voxel][co], rows 36 floats apart (16-byte aligned, bank-staggered)
+    __shared__ float sred[32 * 28];
+    const int cg = threadIdx.x & 7, tg = (threadIdx.x >> 3) & 3, vs = threadIdx.x >> 5;
+    int toff[7];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int tap = grp + 8 * j;
-        tok[j] = tap < 27;
-        const int tp = tok[j] ? tap : 0;
-        toff[j] = ((tp / 9) * 10 + (tp / 3) % 3) * 10 + tp % 3;
+    for (int j = 0; j < 7; ++j) {
+        const int tap = min(tg * 7 + j, 26);                 // tap 27 (tg == 3, j == 6) does not exist: computed on tap 26, never stored
+        toff[j] = ((tap / 9) * 10 + (tap / 3) % 3) * 10 + tap % 3;
     }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4][7];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[c][j] = 0.f;
+    for (int i = threadIdx.x; i < 32 * 28; i += 256) sred[i] = 0.f;
     const long long total = (long long)N * tiles_d * tiles_h * tiles_w;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         long long r = t;
@@ -185,21 +191,32 @@ __global__ void __launch_bounds__(256) conv3d_c1_wgrad_kernel(const float* __res
             const int ow = w0 + (v & 7), oh = h0 + ((v >> 3) & 7), od = d0 + (v >> 6);
             float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (ow < Wo && oh < Ho && od < Do) u_unpack8(__ldg(dy + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * 8 + q), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sdy[v * 33 + 8 * q + j] = f[j];
+            float4* dst = reinterpret_cast<float4*>(sdy + v * 36 + 8 * q);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
         }
         __syncthreads();
 #pragma unroll 4
-        for (int v = 0; v < 256; ++v) {
-            const float g = sdy[v * 33 + co];
+        for (int k = 0; k < 32; ++k) {
+            const int v = vs * 32 + k;
+            const float4 g = *reinterpret_cast<const float4*>(sdy + v * 36 + cg * 4);
             const int base = ((v >> 6) * 10 + ((v >> 3) & 7)) * 10 + (v & 7);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(g, sx[base + toff[j]], acc[j]);
+            for (int j = 0; j < 7; ++j) {
+                const float xv = sx[base + toff[j]];
+                acc[0][j] = fmaf(g.x, xv, acc[0][j]); acc[1][j] = fmaf(g.y, xv, acc[1][j]);
+                acc[2][j] = fmaf(g.z, xv, acc[2][j]); acc[3][j] = fmaf(g.w, xv, acc[3][j]);
+            }
         }
     }
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (tok[j]) partials[((size_t)blockIdx.x * 32 + co) * 27 + grp + 8 * j] = acc[j];
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+            atomicAdd(&sred[(cg * 4 + c) * 28 + tg * 7 + j], acc[c][j]);     // 8 voxel slices (warps) meet here, once per kernel
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 27; i += 256) partials[(size_t)blockIdx.x * 32 * 27 + i] = sred[(i / 27) * 28 + i % 27];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
