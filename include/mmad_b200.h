@@ -308,6 +308,11 @@ int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
                          float* dgamma, float* dbeta, float* coef, void* stream);
 int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef,
                       void* dx, int64_t rows, int C, void* stream);
+/* The same with the ReLU mask recomputed in THIS pass: g is the unmasked upstream gradient (bf16), the mask is
+ * relu(x*mask_scale + mask_shift) > 0.  With mmad_bn_bwd_reduce(g_out = NULL, mask_scale / mask_shift given) a BatchNorm + ReLU
+ * backward costs four tensor passes instead of six: no masked gradient is written, no stored activation is read as the mask. */
+int mmad_bn_bwd_apply_ex(const void* g, const void* x, const float* coef, const float* mask_scale, const float* mask_shift,
+                         void* dx, int64_t rows, int C, void* stream);
 
 /* MaxPool3d(kernel 3, stride 2, padding 1) (resnet.py:136), NDHWC bf16; idx
  * keeps the winning tap per element (uint8, rows x C) for the backward. */

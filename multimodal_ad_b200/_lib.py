@@ -106,6 +106,7 @@ def load() -> ctypes.CDLL:
         "mmad_bn_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, L, I, P],
         "mmad_bn_bwd_finalize": [P, I, I, D_, P, P, P, I, P, P, P, P],
         "mmad_bn_bwd_apply": [P, P, P, P, L, I, P],
+        "mmad_bn_bwd_apply_ex": [P, P, P, P, P, P, L, I, P],
         "mmad_maxpool3d_fwd": [P, P, P, I, I, I, I, I, P],
         "mmad_maxpool3d_bwd": [P, P, P, I, I, I, I, I, P],
         "mmad_upsample_zero2": [P, P] + [I] * 8 + [P],

@@ -449,7 +449,11 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __res
     coef[2 * C + c] = a * (mean[c] * invstd[c] * mgx - mg);
 }
 // pass 2: dx = A*g + B*x + Cc
+// mscale / mshift (optional): g is the UNMASKED upstream gradient and the ReLU mask relu(x * mscale + mshift) > 0 is recomputed here
+// from the pre-BatchNorm tensor - pass 1 then never writes g (and never reads a stored activation as the mask): four tensor passes
+// per BatchNorm backward instead of six.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const float* __restrict__ coef,
+                                                           const float* __restrict__ mscale, const float* __restrict__ mshift,
                                                            uint4* __restrict__ dx, long long nvec, int C) {
     pdl_launch_dependents();
     pdl_wait();                                        // see launch_pdl (common.cuh)
@@ -458,15 +462,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     const int cv = C >> 3;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c0 = (int)(i0 % cv) * 8;
-    float A[8], B[8], Cc[8];
+    float A[8], B[8], Cc[8], ms[8], mb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { A[j] = coef[c0 + j]; B[j] = coef[C + c0 + j]; Cc[j] = coef[2 * C + c0 + j]; }
+    for (int j = 0; j < 8; ++j) {
+        A[j] = coef[c0 + j]; B[j] = coef[C + c0 + j]; Cc[j] = coef[2 * C + c0 + j];
+        ms[j] = mscale ? mscale[c0 + j] : 0.f; mb[j] = mscale ? mshift[c0 + j] : 1.f;       // no mask: 0 * x + 1 > 0 always
+    }
     for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         float gv[8], xv[8], o[8];
         unpack8(g[i], gv);
         unpack8(x[i], xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
+        for (int j = 0; j < 8; ++j) {
+            const float gm = fmaf(xv[j], ms[j], mb[j]) > 0.f ? gv[j] : 0.f;
+            o[j] = fmaf(A[j], gm, fmaf(B[j], xv[j], Cc[j]));
+        }
         dx[i] = pack8(o);
     }
 }
@@ -1036,11 +1046,17 @@ int mmad_bn_bwd_finalize(const float* partials, int nparts, int C, double count,
     launch_pdl(bn_bwd_finalize_kernel, dim3((C + 3) / 4), dim3(128), 0, ST, partials, nparts, C, count, gamma, mean, invstd, training, dgamma, dbeta, coef);
     LAUNCH_OK();
 }
-int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
+int mmad_bn_bwd_apply_ex(const void* g, const void* x, const float* coef, const float* mask_scale, const float* mask_shift, void* dx,
+                         int64_t rows, int C, void* stream) {
     MMAD_CHECK_ARG(g && x && coef && dx && C % 8 == 0, "bn_bwd_apply: bad argument");
+    MMAD_CHECK_ARG((mask_scale == nullptr) == (mask_shift == nullptr), "bn_bwd_apply: mask scale and shift come together");
     const long long nvec = rows * (C / 8);
-    launch_pdl(bn_bwd_apply_kernel, dim3(grid_for_channels(nvec, C / 8, sm_count() * 8)), dim3(256), 0, ST, (const uint4*)g, (const uint4*)x, coef, (uint4*)dx, nvec, C);
+    launch_pdl(bn_bwd_apply_kernel, dim3(grid_for_channels(nvec, C / 8, sm_count() * 8)), dim3(256), 0, ST, (const uint4*)g, (const uint4*)x, coef,
+               mask_scale, mask_shift, (uint4*)dx, nvec, C);
     LAUNCH_OK();
+}
+int mmad_bn_bwd_apply(const void* g, const void* x, const float* coef, void* dx, int64_t rows, int C, void* stream) {
+    return mmad_bn_bwd_apply_ex(g, x, coef, nullptr, nullptr, dx, rows, C, stream);
 }
 int mmad_maxpool3d_fwd(const void* x, void* y, void* idx, int N, int D, int H, int W, int C, void* stream) {
     MMAD_CHECK_ARG(x && y && idx && C % 8 == 0, "maxpool3d_fwd: bad argument");

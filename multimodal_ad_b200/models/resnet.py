@@ -258,8 +258,15 @@ class _Run:
         self.chk(self.lib.mmad_bn_bwd_finalize(_p(part), npart, c, float(rows), _p(gamma), _p(vec[0]), _p(vec[1]), 1 if training else 0,
                                                _p(out[0]), _p(out[1]), _p(coef), self.stream), "mmad_bn_bwd_finalize")
         dx = self.empty(x.shape)
-        src = g if want_g else dy
-        self.chk(self.lib.mmad_bn_bwd_apply(_p(src), _p(x), _p(coef), _p(dx), rows, c, self.stream), "mmad_bn_bwd_apply")
+        if want_g:
+            self.chk(self.lib.mmad_bn_bwd_apply(_p(g), _p(x), _p(coef), _p(dx), rows, c, self.stream), "mmad_bn_bwd_apply")
+        else:
+            # no masked gradient was written: pass 2 reads the upstream gradient itself and, when the layer has a ReLU whose mask
+            # comes from x, recomputes that mask (four tensor passes per BatchNorm backward instead of six)
+            if dy_is_f32 or dy2 is not None or mask is not None:
+                raise _lib.MmadError("bn_bwd(want_g=False) takes one bf16 upstream gradient and no stored mask")
+            self.chk(self.lib.mmad_bn_bwd_apply_ex(_p(dy), _p(x), _p(coef), _p(vec[2]) if mask_from_x else None,
+                                                   _p(vec[3]) if mask_from_x else None, _p(dx), rows, c, self.stream), "mmad_bn_bwd_apply_ex")
         return dx, g, out[0], out[1]
 
 
@@ -457,11 +464,11 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             grads[blk.bn3.weight], grads[blk.bn3.bias] = dg, db
             wgrad_of(blk.conv3.weight, rec["a2"], dc3, outc, 1, 1, 0, 1)
             da2, _ = r.conv(dc3, rec["w3t"], planes, 1, 1, 0, 1, False)
-            dc2, _, dg, db = r.bn_bwd(da2, None, rec["a2"], rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, want_g=True)
+            dc2, _, dg, db = r.bn_bwd(da2, None, None, rec["c2"], rec["v2"], blk.bn2.weight.detach(), training, want_g=False, mask_from_x=True)
             grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
             wgrad_of(blk.conv2.weight, rec["a1"], dc2, planes, 3, st, dil, dil)
             da1 = dgrad_3x3(dc2, rec["w2t"], blk.conv2, rec["a1"].shape, planes, planes, st, dil)
-            dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
+            dc1, _, dg, db = r.bn_bwd(da1, None, None, rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=False, mask_from_x=True)
             grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
             wgrad_of(blk.conv1.weight, xin, dc1, planes, 1, 1, 0, 1)
             dx1, _ = r.conv(dc1, rec["w1t"], inpl, 1, 1, 0, 1, False)
@@ -473,7 +480,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
             grads[blk.bn2.weight], grads[blk.bn2.bias] = dg, db
             wgrad_of(blk.conv2.weight, rec["a1"], dc2, planes, 3, 1, dil, dil)
             da1, _ = r.conv(dc2, rec["w2t"], planes, 3, 1, dil, dil, False)            # dgrad of conv2 (unit stride)
-            dc1, _, dg, db = r.bn_bwd(da1, None, rec["a1"], rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=True)
+            dc1, _, dg, db = r.bn_bwd(da1, None, None, rec["c1"], rec["v1"], blk.bn1.weight.detach(), training, want_g=False, mask_from_x=True)
             grads[blk.bn1.weight], grads[blk.bn1.bias] = dg, db
             wgrad_of(blk.conv1.weight, rec["xin"], dc1, planes, 3, st, dil, dil)
             dx1 = dgrad_3x3(dc1, rec["w1t"], blk.conv1, xin.shape, inpl, planes, st, dil)      # dgrad of conv1
@@ -513,7 +520,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
     da0 = r.empty(c0.shape)
     r.chk(lib.mmad_maxpool3d_bwd(_p(dsum), _p(stem["idx0"]), _p(da0), n, c0.shape[1], c0.shape[2], c0.shape[3], 64, r.stream),
           "mmad_maxpool3d_bwd")
-    dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=True, mask_from_x=True)
+    dc0, _, dg, db = r.bn_bwd(da0, None, None, c0, v0, model.bn1.weight.detach(), training, want_g=False, mask_from_x=True)
     grads[model.bn1.weight], grads[model.bn1.bias] = dg, db
     gw = None
     if grads.wanted(model.conv1.weight):

@@ -344,7 +344,9 @@ def _unet_backward(model: "UNet3D", tape, grad_out: torch.Tensor, wanted=None):
         """Backward of relu(bn(conv(xin) + bias)) given d(activation) = dy (+ dy2).  Returns dc (gradient of the conv output).
         Weight / bias / BatchNorm gradients are stored; the data gradient is left to the caller (it depends on the input)."""
         conv, bn = rec["conv"], rec["bn"]
-        dc, _, dgamma, dbeta = r.bn_bwd(dy, dy2, None, rec["c"], rec["vec"], rec["gamma"], training, want_g=True, mask_from_x=True)
+        # one upstream gradient: four-pass form (no masked gradient written, the mask recomputed from c in both passes); the skip
+        # tensors receive two (max-pool path + decoder path) and keep the form that materialises their masked sum
+        dc, _, dgamma, dbeta = r.bn_bwd(dy, dy2, None, rec["c"], rec["vec"], rec["gamma"], training, want_g=dy2 is not None, mask_from_x=True)
         c = bn.num_features
         put(bn.weight, dgamma[:c])
         put(bn.bias, dbeta[:c])
@@ -454,7 +456,7 @@ def _unet_backward(model: "UNet3D", tape, grad_out: torch.Tensor, wanted=None):
         if l1.get("first"):
             # conv1 of a_block1: direct kernel; the MRI volume is data, no input gradient
             conv, bn = l1["conv"], l1["bn"]
-            dc1, _, dgamma, dbeta = r.bn_bwd(da1, None, None, l1["c"], l1["vec"], l1["gamma"], training, want_g=True, mask_from_x=True)
+            dc1, _, dgamma, dbeta = r.bn_bwd(da1, None, None, l1["c"], l1["vec"], l1["gamma"], training, want_g=False, mask_from_x=True)
             c = bn.num_features
             put(bn.weight, dgamma[:c])
             put(bn.bias, dbeta[:c])

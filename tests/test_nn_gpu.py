@@ -186,6 +186,26 @@ def test_maxpool_forward_backward(shape, run):
     assert torch.all((dx.float() - ref).abs() <= 2 ** -7 * ref.abs() + 1e-6)      # sum of <= 8 bf16 terms, rounded once
 
 
+@pytest.mark.parametrize("c,rows", [(64, 5000), (256, 333)])
+def test_batchnorm_backward_four_pass_form_equals_six_pass_form(c, rows, run):
+    """want_g=False + mask_from_x: pass 1 writes no masked gradient, pass 2 recomputes the ReLU mask from x - same dx, dgamma, dbeta
+    as the form that stores g (bit for bit: the masked gradient of a single bf16 upstream tensor is exactly representable)."""
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = (torch.randn((1, 1, 1, rows, c), device="cuda", generator=g) * 1.3).to(torch.bfloat16)
+    dy = torch.randn((1, 1, 1, rows, c), device="cuda", generator=g).to(torch.bfloat16)
+    vec = torch.stack([torch.randn(c, device="cuda", generator=g) * 0.1, torch.rand(c, device="cuda", generator=g) + 0.5,
+                       torch.rand(c, device="cuda", generator=g) + 0.5, torch.randn(c, device="cuda", generator=g) * 0.3]).contiguous()
+    gamma = vec[2] / vec[1]
+    for training in (True, False):
+        dx6, _, dg6, db6 = run.bn_bwd(dy, None, None, x, vec, gamma, training, want_g=True, mask_from_x=True)
+        dx4, g4, dg4, db4 = run.bn_bwd(dy, None, None, x, vec, gamma, training, want_g=False, mask_from_x=True)
+        assert g4 is None and torch.equal(dx4, dx6) and torch.equal(dg4, dg6) and torch.equal(db4, db6)
+    # without a ReLU (downsample branch): the unmasked form
+    dxa, _, _, _ = run.bn_bwd(dy, None, None, x, vec, gamma, True, want_g=True)
+    dxb, _, _, _ = run.bn_bwd(dy, None, None, x, vec, gamma, True, want_g=False)
+    assert torch.equal(dxa, dxb)
+
+
 def test_layout_transpose(run):
     from multimodal_ad_b200.models.resnet import _p
 
