@@ -427,7 +427,6 @@ def _unet_backward(model: "UNet3D", tape, grad_out: torch.Tensor, wanted=None):
         dcur, _ = r.conv(dup, wf_t, cin_up, 2, 2, 0, 1, False)
 
     # ---- analysis path, bottleneck first ----
-    cats = {id(rec["cat"]): rec["cat"] for rec in tape["dec"]}
     level_cat = {tuple(rec["grid"]): rec["cat"] for rec in tape["dec"]}
     for rec in reversed(tape["enc"]):
         blk, g = rec["blk"], rec["grid"]
@@ -482,7 +481,6 @@ def _unet_backward(model: "UNet3D", tape, grad_out: torch.Tensor, wanted=None):
     r.join_side()
     for fn in post:
         fn()
-    del cats
     return grads
 
 
