@@ -47,3 +47,37 @@ def test_cpu_tensor_raises_instead_of_falling_back(built_lib):
     pool = ROIPool(np.ones((2, 2, 2), np.int32))
     with pytest.raises(_lib.MmadError, match="CUDA"):
         pool(torch.zeros(1, 1, 2, 2, 2))
+
+
+def test_ctypes_signatures_match_the_header(built_lib):
+    """Every entry point's ctypes argtypes (multimodal_ad_b200/_lib.py) has as many parameters as its declaration in
+    include/mmad_b200.h, with pointers where the header has pointers - a drifted binding would otherwise only show up as a crash
+    on the GPU box."""
+    import ctypes as C
+
+    from multimodal_ad_b200 import _lib
+
+    lib = _lib.load()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mmad_b200.h")).read(), flags=re.S)
+    decls = re.findall(r"\b(?:const\s+char\*|int64_t|int)\s+(mmad_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 50
+    checked = 0
+    for name, params in decls:
+        plist = [p.strip() for p in params.replace("\n", " ").split(",")]
+        if plist == ["void"] or plist == [""]:
+            plist = []
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == len(plist), (name, len(fn.argtypes), plist)
+        for at, p in zip(fn.argtypes, plist):
+            is_ptr = "*" in p
+            at_ptr = at in (C.c_void_p, C.c_char_p) or hasattr(at, "contents") or getattr(at, "_type_", None) is not None and hasattr(at, "_length_")
+            if is_ptr:
+                assert at_ptr, (name, p, at)
+            else:
+                assert not at_ptr, (name, p, at)
+                want64 = p.startswith("int64_t") or p.startswith("double")
+                assert (C.sizeof(at) == 8) == want64, (name, p, at)
+        checked += 1
+    assert checked >= 45
