@@ -208,10 +208,14 @@ int mmad_stem_s2d_wgrad_reduce(const float* partials, int nsplit, float* dw, voi
  * 0, ep_relu != 0 = ReLU): a convolution bias (unet3d.py:37-40), or in eval mode the BatchNorm3d + ReLU that follows the
  * convolution folded into the producing kernel; (c) an fp32 side output out_f32[voxel][Cout] = acc + f32_bias[c] (NULL bias
  * = 0), dense NDHWC: the raw convolution output image_features.py:58-60 hooks (s_block1.conv2), kept at accumulator
- * precision for the ROI pooling.  stats_partials are the statistics of the STORED bf16 values. */
+ * precision for the ROI pooling.  stats_partials are the statistics of the STORED bf16 values.  (d) cin_tensor (0 = Cin): the
+ * input tensor has only cin_tensor < Cin = 64 channels per voxel (unet3d.py's 32-channel a_block1.conv1 output): x is
+ * (N,D,H,W,cin_tensor), the weights keep Cin = 64 with zero columns, and TMA zero-fills the rest of every 128-byte K slice in
+ * flight - the padding is neither stored nor fetched. */
 int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, float* stats_partials,
                             const float* ep_scale, const float* ep_shift, int ep_relu, float* out_f32, const float* f32_bias,
-                            int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil, void* stream);
+                            int N, int D, int H, int W, int Cin, int Cout, int k, int stride, int pad, int dil,
+                            int cin_tensor, void* stream);
 /* The tail of unet3d.py's eval-mode forward as one kernel: 3x3x3 convolution (padding 1) to 64 channels, the BatchNorm3d + ReLU
  * that follow it (ep_scale / ep_shift), the 1x1x1 head (unet3d.py:72 conv3: head_w float[K][64], head_b float[K], K <= 8) and the
  * crop back to (Dc,Hc,Wc) (unet3d.py:126-135) - the 64-channel activation is never written.  head_out fp32 (N,K,Dc,Hc,Wc);
@@ -243,12 +247,13 @@ int mmad_convtranspose3d_k2s2_fwd_bf16(const void* x, const void* w_phases, cons
  * channels 32..63 written as zeros (the next convolution reads 64-channel rows); no bias (add it through the BatchNorm
  * shift).  Training: stats_partials float[mmad_conv3d_c1_blocks][64][2] like mmad_conv3d_fwd_bf16 (ep_* NULL).  Eval:
  * ep_scale / ep_shift float[32] fold BatchNorm3d + ReLU (and the bias) in, stored = relu(acc * scale[c] + shift[c])
- * (stats_partials NULL).  Weight gradient: partials float[mmad_conv3d_c1_wgrad_blocks][32][27], summed by
+ * (stats_partials NULL).  out_channels = 64: y (N,Do,Ho,Wo,64) as above; 32: y (N,Do,Ho,Wo,32), no padding channels stored - the
+ * next convolution then reads it with cin_tensor = 32 (mmad_conv3d_fwd_ex_bf16).  Weight gradient: partials float[mmad_conv3d_c1_wgrad_blocks][32][27], summed by
  * mmad_wgrad_reduce(partials, blocks, dw, 32, 1, 27). */
 int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo);
 int mmad_conv3d_c1_wgrad_blocks(int N, int Do, int Ho, int Wo);
 int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials, const float* ep_scale, const float* ep_shift,
-                       int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);
+                       int N, int D, int H, int W, int Do, int Ho, int Wo, int out_channels, void* stream);
 int mmad_conv3d_c1_wgrad(const float* x, const void* dy, float* partials,
                          int N, int D, int H, int W, int Do, int Ho, int Wo, void* stream);
 

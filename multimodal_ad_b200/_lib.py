@@ -71,14 +71,14 @@ def load() -> ctypes.CDLL:
         "mmad_conv3d_wgrad_bf16": [P, P, P] + [I] * 10 + [P],
         "mmad_wgrad_reduce": [P, I, P, I, I, I, P],
         "mmad_wgrad_reduce_ex": [P, I, P, I, I, I, I, I, P],
-        "mmad_conv3d_fwd_ex_bf16": [P, P, P, L, P, P, P, I, P, P] + [I] * 10 + [P],
+        "mmad_conv3d_fwd_ex_bf16": [P, P, P, L, P, P, P, I, P, P] + [I] * 11 + [P],
         "mmad_conv3d_wgrad_ex_bf16": [P, L, P, P] + [I] * 10 + [P],
         "mmad_conv3d_fwd_head_bf16": [P] * 9 + [I] * 9 + [P],
         "mmad_convtranspose3d_prep_weights": [P, P, I, I, P],
         "mmad_convtranspose3d_k2s2_fwd_bf16": [P, P, P, P, L, I, I, I, I, I, I, P],
         "mmad_conv3d_c1_blocks": [I, I, I, I],
         "mmad_conv3d_c1_wgrad_blocks": [I, I, I, I],
-        "mmad_conv3d_c1_fwd": [P, P, P, P, P, P] + [I] * 7 + [P],
+        "mmad_conv3d_c1_fwd": [P, P, P, P, P, P] + [I] * 8 + [P],
         "mmad_conv3d_c1_wgrad": [P, P, P] + [I] * 7 + [P],
         "mmad_maxpool3d_k2_fwd": [P, L, P, P, I, I, I, I, I, P],
         "mmad_maxpool3d_k2_bwd": [P, P, P, I, I, I, I, I, P],

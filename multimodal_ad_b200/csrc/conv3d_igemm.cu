@@ -80,6 +80,7 @@ struct ConvEpi {
     float* head_out;
     int head_k, hD, hH, hW;
     int nostore;
+    int cin_tensor;               // host only: channels the input tensor really has (< Cin: the rest of every K slice is TMA zero fill)
 };
 constexpr int kHeadMaxK = 8;
 
@@ -1042,6 +1043,8 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     MMAD_CHECK_ARG(!ep.head_out || (Cout == 64 && ep.head_w && ep.head_b && ep.head_k >= 1 && ep.head_k <= kHeadMaxK),
                    "conv3d_fwd: the fused 1x1x1 head needs Cout == 64 and 1..8 classes");
     MMAD_CHECK_ARG(!ep.nostore || !stats_partials, "conv3d_fwd: statistics need the stored output");
+    MMAD_CHECK_ARG(ep.cin_tensor == 0 || (ep.cin_tensor % 8 == 0 && ep.cin_tensor <= Cin && Cin == 64),
+                   "conv3d_fwd: a narrower input tensor needs Cin == 64 and a multiple of 8 channels (16-byte rows)");
     MMAD_CHECK_ARG(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.f32_ld % 4 == 0), "conv3d_fwd: fp32 side output must be 16-byte aligned");
     if ((!ov || ov->standard) && kd == kh && kh == kw && pad == 1 && use_halo_kernel(Cin, Cout, k, stride, dil)) {
         // the halo variant needs 8 x 4 x 4 tiles; mmad_conv3d_stats_partials (which does not know Cin) sizes the statistics
@@ -1086,8 +1089,12 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
 
     CUtensorMap tmA, tmB, tmC;
     {
-        const uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
-        const uint64_t str[4] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2, (uint64_t)D * H * W * Cin * 2};
+        // ct < Cin: the tensor has only ct channels per voxel (a 32-channel activation: 64-byte rows); the 64-wide box then
+        // reaches past dimension 0 and TMA zero-fills the rest of the 128-byte row - the K slice is padded in flight, neither
+        // stored nor fetched (half of the L2 -> SM bytes of that layer)
+        const uint64_t ct = (uint64_t)(ep.cin_tensor > 0 ? ep.cin_tensor : Cin);
+        const uint64_t dims[5] = {ct, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+        const uint64_t str[4] = {ct * 2, (uint64_t)W * ct * 2, (uint64_t)H * W * ct * 2, (uint64_t)D * H * W * ct * 2};
         const uint32_t box[5] = {64, (uint32_t)(halo ? g.tw + 2 : g.tw * stride), (uint32_t)(g.th * stride), (uint32_t)(g.td * stride), (uint32_t)g.tn};
         const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, (uint32_t)stride, 1};
         int rc = make_tmap_bf16(&tmA, x, 5, dims, str, box, es);
@@ -1193,9 +1200,10 @@ int mmad_conv3d_fwd_bf16(const void* x, const void* w, void* y, float* stats_par
 // buffer of unet3d.py:77 is written in place, no torch.cat copy), per-channel epilogue (ConvEpi) and fp32 side output.
 int mmad_conv3d_fwd_ex_bf16(const void* x, const void* w, void* y, int64_t ldy, float* stats_partials, const float* ep_scale,
                             const float* ep_shift, int ep_relu, float* out_f32, const float* f32_bias, int N, int D, int H, int W,
-                            int Cin, int Cout, int k, int stride, int pad, int dil, void* stream) {
+                            int Cin, int Cout, int k, int stride, int pad, int dil, int cin_tensor, void* stream) {
     MMAD_CHECK_ARG(ldy == 0 || (ldy >= Cout && ldy % 8 == 0), "conv3d_fwd_ex: ldy must be 0 (dense) or >= Cout and a multiple of 8");
     ConvEpi ep = {ep_scale, ep_shift, f32_bias, out_f32, (long long)Cout, ep_relu};
+    ep.cin_tensor = cin_tensor;
     ConvOut ov = {};
     ov.Do = (D + 2 * pad - dil * (k - 1) - 1) / stride + 1;
     ov.Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1;

@@ -48,7 +48,7 @@ template <bool STATS, bool EPI>
 __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wgt, uint4* __restrict__ y,
                                                             float* __restrict__ stats_partials, const float* __restrict__ ep_scale,
                                                             const float* __restrict__ ep_shift, int N, int D, int H, int W, int Do, int Ho,
-                                                            int Wo, int tiles_w, int tiles_h, int tiles_d) {
+                                                            int Wo, int tiles_w, int tiles_h, int tiles_d, int out_c8) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ __align__(16) float sw[27 * 32];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
             }
         const int oh = h0 + th, od = d0 + td;
         if (oh < Ho && od < Do) {
-            uint4* line = y + (((long long)n * Do + od) * Ho + oh) * Wo * 8;        // 64 channels = 8 vectors per voxel
+            uint4* line = y + (((long long)n * Do + od) * Ho + oh) * Wo * out_c8;   // out_c8 = 8: 64-channel rows (upper half zero), 4: 32-channel rows
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
                 const int ow = w0 + wg * 8 + v;
@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(256) conv3d_c1_fwd_kernel(const float* __restr
                         if (EPI) f[j] = fmaxf(fmaf(f[j], sep[cq * 8 + j], sep[32 + cq * 8 + j]), 0.f);
                     }
                     const uint4 pk = u_pack8(f);
-                    line[(long long)ow * 8 + cq] = pk;
-                    line[(long long)ow * 8 + 4 + cq] = make_uint4(0u, 0u, 0u, 0u);   // padding channels 32..63
+                    line[(long long)ow * out_c8 + cq] = pk;
+                    if (out_c8 == 8) line[(long long)ow * 8 + 4 + cq] = make_uint4(0u, 0u, 0u, 0u);   // padding channels 32..63
                     if (STATS) {
                         u_unpack8(pk, f);                   // statistics of the rounded values, as the tensor-core epilogue does
 #pragma unroll
@@ -436,16 +436,18 @@ int mmad_conv3d_c1_blocks(int N, int Do, int Ho, int Wo) { return c1_blocks(N, D
 int mmad_conv3d_c1_wgrad_blocks(int N, int Do, int Ho, int Wo) { return c1_blocks(N, Do, Ho, Wo, kC1Tw, kC1Th, kC1Td); }
 
 int mmad_conv3d_c1_fwd(const float* x, const float* w, void* y, float* stats_partials, const float* ep_scale, const float* ep_shift, int N,
-                       int D, int H, int W, int Do, int Ho, int Wo, void* stream) {
+                       int D, int H, int W, int Do, int Ho, int Wo, int out_channels, void* stream) {
+    MMAD_CHECK_ARG(out_channels == 64 || out_channels == 32, "conv3d_c1_fwd: y has 64-channel rows (upper half zero) or 32-channel rows");
+    const int oc8 = out_channels / 8;
     MMAD_CHECK_ARG(x && w && y && N > 0 && D > 0 && H > 0 && W > 0, "conv3d_c1_fwd: bad argument");
     MMAD_CHECK_ARG(Do >= D && Ho >= H && Wo >= W, "conv3d_c1_fwd: the output grid is the input grid zero-extended on the right");
     MMAD_CHECK_ARG((ep_scale == nullptr) == (ep_shift == nullptr), "conv3d_c1_fwd: epilogue scale and shift come together");
     MMAD_CHECK_ARG(!(ep_scale && stats_partials), "conv3d_c1_fwd: statistics are those of the raw output (no epilogue in training mode)");
     const dim3 grid(mmad_conv3d_c1_blocks(N, Do, Ho, Wo));
     const int tws = (Wo + kF1Tw - 1) / kF1Tw, ths = (Ho + kF1Th - 1) / kF1Th, tds = (Do + kF1Td - 1) / kF1Td;
-    if (ep_scale) launch_pdl(conv3d_c1_fwd_kernel<false, true>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
-    else if (stats_partials) launch_pdl(conv3d_c1_fwd_kernel<true, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
-    else launch_pdl(conv3d_c1_fwd_kernel<false, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds);
+    if (ep_scale) launch_pdl(conv3d_c1_fwd_kernel<false, true>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds, oc8);
+    else if (stats_partials) launch_pdl(conv3d_c1_fwd_kernel<true, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds, oc8);
+    else launch_pdl(conv3d_c1_fwd_kernel<false, false>, grid, dim3(256), 0, ST, x, w, (uint4*)y, stats_partials, ep_scale, ep_shift, N, D, H, W, Do, Ho, Wo, tws, ths, tds, oc8);
     LAUNCH_OK();
 }
 

@@ -104,12 +104,15 @@ class _UNetRun(_Run):
     def conv_ex(self, x, w_fwd, cout, y_ptr, ldy, want_stats, scale=None, shift=None, relu=False, out_f32=None, f32_bias=None,
                 k=3, stride=1, pad=1):
         n, d, h, w, cin = x.shape
+        cin_tensor = 0
+        if cin < 64:                                       # a 32-channel tensor: K slices stay 64 wide, TMA zero-fills the rest in flight
+            cin_tensor, cin = cin, 64
         part = None
         if want_stats:
             npart = self.lib.mmad_conv3d_stats_partials(n, d, h, w, cout, k, stride, pad, 1)
             part = self.empty((npart, cout, 2), torch.float32)
         self.chk(self.lib.mmad_conv3d_fwd_ex_bf16(_p(x), _p(w_fwd), y_ptr, ldy, _p(part), _p(scale), _p(shift), 1 if relu else 0,
-                                                  _p(out_f32), _p(f32_bias), n, d, h, w, cin, cout, k, stride, pad, 1, self.stream),
+                                                  _p(out_f32), _p(f32_bias), n, d, h, w, cin, cout, k, stride, pad, 1, cin_tensor, self.stream),
                  "mmad_conv3d_fwd_ex_bf16")
         return part
 
@@ -234,17 +237,18 @@ def _unet_forward(model: "UNet3D", x: torch.Tensor, training: bool, need_grad: b
             wsrc = blk.conv1.weight.detach().contiguous()
             if fold:
                 # eval without autograd: BatchNorm + ReLU (and the bias) folded into the kernel, one pass, one tensor written
+                # ... and only the 32 real channels: the next convolution reads 64-byte rows and TMA pads its K slices in flight
                 vec, gamma = _bn_vec(r, blk.bn1, None, rows, blk.conv1.bias, False, width=width)
-                a1 = r.empty((n,) + g + (width,))
-                r.chk(lib.mmad_conv3d_c1_fwd(_p(x), _p(wsrc), _p(a1), None, _p(vec[2]), _p(vec[3]), n, d, h, w, g[0], g[1], g[2], r.stream),
-                      "mmad_conv3d_c1_fwd")
+                a1 = r.empty((n,) + g + (mid,))
+                r.chk(lib.mmad_conv3d_c1_fwd(_p(x), _p(wsrc), _p(a1), None, _p(vec[2]), _p(vec[3]), n, d, h, w, g[0], g[1], g[2], mid,
+                                             r.stream), "mmad_conv3d_c1_fwd")
                 rec["l1"] = dict(conv=blk.conv1, bn=blk.bn1, first=True)
             else:
                 cc = r.empty((n,) + g + (width,))
                 nb = lib.mmad_conv3d_c1_blocks(n, *g)
                 part = r.empty((nb, width, 2), torch.float32) if training else None
-                r.chk(lib.mmad_conv3d_c1_fwd(_p(x), _p(wsrc), _p(cc), _p(part), None, None, n, d, h, w, g[0], g[1], g[2], r.stream),
-                      "mmad_conv3d_c1_fwd")
+                r.chk(lib.mmad_conv3d_c1_fwd(_p(x), _p(wsrc), _p(cc), _p(part), None, None, n, d, h, w, g[0], g[1], g[2], width,
+                                             r.stream), "mmad_conv3d_c1_fwd")
                 vec, gamma = _bn_vec(r, blk.bn1, part, rows, blk.conv1.bias, training, width=width)
                 a1 = r.empty(cc.shape)
                 r.chk(lib.mmad_bn_apply_ex(_p(cc), _p(vec[2]), _p(vec[3]), None, None, None, 1, _p(a1), 0, None, rows, width, r.stream),

@@ -106,7 +106,7 @@ def test_first_layer_direct_convolution_forward_and_weight_gradient(run):
     y = run.empty((n, do, ho, wo, 64))
     nb = run.lib.mmad_conv3d_c1_blocks(n, do, ho, wo)
     part = run.empty((nb, 64, 2), torch.float32)
-    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(y), _p(part), None, None, n, d, h, w, do, ho, wo, run.stream), "c1 fwd")
+    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(y), _p(part), None, None, n, d, h, w, do, ho, wo, 64, run.stream), "c1 fwd")
     xe = F.pad(x, (0, wo - w, 0, ho - h, 0, do - d)).requires_grad_(True)
     wr = wt.clone().requires_grad_(True)
     ref = F.conv3d(xe, wr, padding=1)
@@ -118,9 +118,20 @@ def test_first_layer_direct_convolution_forward_and_weight_gradient(run):
     # eval-mode epilogue: relu(acc * scale + shift) in the same pass, no statistics
     scale, shift = torch.rand(32, device="cuda", generator=g) + 0.5, torch.randn(32, device="cuda", generator=g) * 0.3
     ye = run.empty((n, do, ho, wo, 64))
-    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(ye), None, _p(scale), _p(shift), n, d, h, w, do, ho, wo, run.stream), "c1 fwd epi")
+    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(ye), None, _p(scale), _p(shift), n, d, h, w, do, ho, wo, 64, run.stream), "c1 fwd epi")
     want = F.relu(ref.detach() * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
     assert torch.all((_nc(ye[..., :32]) - want).abs() <= 2 ** -8 * want.abs() + 1e-6) and torch.all(ye[..., 32:] == 0)
+    # 32-channel rows (no padding channels stored), read back by a convolution whose K slices TMA pads in flight
+    y32 = run.empty((n, do, ho, wo, 32))
+    run.chk(run.lib.mmad_conv3d_c1_fwd(_p(x), _p(wt), _p(y32), None, _p(scale), _p(shift), n, d, h, w, do, ho, wo, 32, run.stream), "c1 fwd 32")
+    assert torch.equal(y32, ye[..., :32])
+    w2 = torch.randn((64, 32, 3, 3, 3), device="cuda", generator=g) / (27 * 32) ** 0.5
+    wf2, _ = run.prep_w(F.pad(w2, (0, 0, 0, 0, 0, 0, 0, 32)), False)
+    for src in (y32, ye):
+        o2 = run.empty((n, do, ho, wo, 64))
+        run.conv_ex(src, wf2, 64, _p(o2), 0, False)
+        ref2 = F.conv3d(_nc(y32), w2.to(torch.bfloat16).float(), padding=1)
+        assert torch.all((_nc(o2) - ref2).abs() <= 2 ** -8 * ref2.abs() + 1e-3)
     dy = torch.randn_like(ref).to(torch.bfloat16).float()
     ref.backward(dy)
     dyb = torch.zeros((n, do, ho, wo, 64), device="cuda", dtype=torch.bfloat16)
