@@ -41,6 +41,7 @@ struct ConvGeom {
     int sched_depth;              // tile-ring slots in use: 2 when dynamic (a CTA holds at most one tile it has not started), 4 when static
     int tiles_w, tiles_h, tiles_d, tiles_n, m_tiles, n_tiles;   // tile index: sample tile fastest, then w, h, d
     int kc;                       // Cin / 64
+    int kj;                       // K16 MMAs per 64-channel slice: 4, fewer when the tensor has < 64 channels (the rest is zero fill)
     int stages;
     int nout;                     // epilogue staging buffers (1 or 2)
 };
@@ -306,6 +307,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ============================ MMA issuer (whole warp walks the loop, one elected lane issues) ============================
         {
             uint32_t s = 0, ph = 0, it = 0, nmma = 0;
+            const int kj = g.kj;
             for (;; ++it) {
                 const int tile = next_tile();
                 if (tile >= total_tiles) break;
@@ -338,8 +340,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const uint64_t bdesc = umma_desc_sw128(sa + A_REGION + q * B_TILE, 16, 1024);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)           // 4 x K16 inside the 64-wide (128-byte) swizzled row
-                                umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
-                            nmma += 4;
+                                if (j < kj) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                            nmma += kj;
                         }
                         umma_commit(empty0 + 8 * s);              // frees the smem slot when these MMAs retire
                     }
@@ -580,10 +582,12 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int sc_static = pair;
     auto next_tile = [&]() -> int {
         if (!g.dyn) { const int t = sc_static; sc_static += n_pairs; return t; }
-        mbar_wait_cluster(sfull0 + 8 * sc_slot, sc_ph);
+        // the index lives in shared memory (never in L1), so the CTA-scope wait is enough - the cluster-scope acquire would add
+        // a CCTL.IVALL per tile and evict the epilogue's scale / shift vectors from L1
+        mbar_wait(sfull0 + 8 * sc_slot, sc_ph);
         const int t = sched_tile[sc_slot];
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(sempty0 + 8 * sc_slot, 0);
+        if (lane == 0 && t >= 0) mbar_signal_remote(sempty0 + 8 * sc_slot, 0);   // t >= 0 always: the test makes the arrive wait for the load
         if (++sc_slot == (uint32_t)g.sched_depth) { sc_slot = 0; sc_ph ^= 1; }
         return t;
     };
@@ -611,7 +615,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (leader) {
             uint32_t slot = 0, ph = 0;
             for (; g.dyn;) {
-                mbar_wait_cluster(sempty0 + 8 * slot, ph ^ 1);
+                mbar_wait(sempty0 + 8 * slot, ph ^ 1);
                 int t = 0;
                 if (lane == 0) {
                     t = (int)atomicAdd(sched_counter, 1u);
@@ -707,6 +711,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             while (next_tile() < total_super) {}
         } else {
             uint32_t s = 0, ph = 0, it = 0, nmma = 0;
+            const int kj = g.kj;
             if (wres) { mbar_wait(wfull, 0); tc_fence_after(); }
             for (;; ++it) {
                 const int st = next_tile();
@@ -731,15 +736,17 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                 const uint64_t adesc = umma_desc_sw128(sa + q * 128, 16, 1280);
                                 const uint64_t bdesc = umma_desc_sw128(sb + q * B_TAP, 16, 1024);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < kj) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
                             }
-                            nmma += 12;
+                            nmma += 3 * kj;
                         } else {
                             const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
                             const uint64_t bdesc = umma_desc_sw128(sa + A_REGION, 16, 1024);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
-                            nmma += 4;
+                            for (int j = 0; j < 4; ++j)
+                                if (j < kj) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                            nmma += kj;
                         }
                         umma_commit_2sm(empty0 + 8 * s, 3);       // frees the slot in both CTAs
                     }
@@ -872,7 +879,7 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(tempty0 + 8 * acc, 0);   // the leader's MMA issuer waits for both CTAs
+            if (lane == 0) mbar_signal_remote(tempty0 + 8 * acc, 0);   // the leader's MMA issuer waits for both CTAs
         }
         if (et == 0) tma_store_wait<0>();
         if (stats_partials) {
@@ -1060,6 +1067,7 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     const int bn = std::min(256, Cout);
     g.n_tiles = Cout / bn;
     g.kc = Cin / 64;
+    g.kj = ep.cin_tensor > 0 ? (ep.cin_tensor + 15) / 16 : 4;          // K16 steps that can be non-zero
     static int halo_pair_mode = -1;                        // CTA-pair W-halo kernel: on unless MMAD_CONV_HALO_PAIR=0
     if (halo_pair_mode < 0) { const char* e = getenv("MMAD_CONV_HALO_PAIR"); halo_pair_mode = e ? atoi(e) : 1; }
     const bool halo_pair = halo && halo_pair_mode != 0 && g.m_tiles >= 2;
@@ -1141,8 +1149,16 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     // start / end latency than they can gain: +0.6 ms on that network's 16.7 ms step.  Dynamic from 4 tiles per CTA (pair) on.
     const long long work_items = pairk ? (long long)((g.m_tiles + 1) / 2) * g.n_tiles : (long long)g.m_tiles * g.n_tiles;
     const long long ctas = pairk ? sms / 2 : sms;
+    // The per-tile hand-off is a few plain shared-memory / mbarrier operations (mbar_signal_remote: no fences); with the fenced
+    // arrives of the first version a UNet3D eval forward was 3.5 % SLOWER with dynamic draws than without (16.70 vs 16.14 ms),
+    // now it is 2.4 % faster (15.63 vs 16.02 ms, batch 8).
     g.dyn = (use_dynamic_scheduler() && kd * kh * kw * g.kc >= 16 && work_items >= 4 * ctas) ? 1 : 0;
-    g.sched_depth = g.dyn ? 2 : kSchedSlots;
+    // ring depth 2: a CTA holds at most one tile it has not started.  Deeper look-ahead was measured twice and lost both times
+    // (ResNet3D-18 step 12.31 ms at depth 2, 13.62 ms at depth 4 for layers with >= 16 tiles per CTA; UNet3D eval 16.77 / 16.66 /
+    // 16.97 ms at depth 2 / 3 / 4).  MMAD_CONV_SCHED_DEPTH overrides (2..4) for experiments.
+    static int depth_knob = -1;
+    if (depth_knob < 0) { const char* e = getenv("MMAD_CONV_SCHED_DEPTH"); depth_knob = e ? std::max(2, std::min(kSchedSlots, atoi(e))) : 2; }
+    g.sched_depth = g.dyn ? depth_knob : kSchedSlots;
     if (g.dyn) {
         sched = sched_counter_slot();
         if (!sched) return fail(MMAD_ECUDA, "conv3d_fwd: cannot allocate the tile-scheduler counters");

@@ -173,11 +173,22 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask)
                  "h"(cta_mask)
                  : "memory");
 }
-// arrive on the mbarrier at local offset `bar` in the CTA with cluster rank `rank`
+// arrive on the mbarrier at local offset `bar` in the CTA with cluster rank `rank`, publishing this thread's earlier writes to
+// that CTA (release.cluster).  ptxas lowers the cluster-scope release to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the
+// arrive - use it only where data written with ordinary stores travels with the signal.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// the same arrive as a pure signal (default semantics: a bare SYNCS.ARRIVE, no fences): "this warp is done with the slot /
+// the accumulator".  Nothing the waiter reads was written by the arriving thread; TMEM reads are ordered by the caller's
+// tcgen05.fence::before_thread_sync.  25 % of all stall samples of the pair W-halo kernel sat in the fenced form
+// (profiles/r02_conv_halo_pair32_fenced_stalls.txt).
+__device__ __forceinline__ void mbar_signal_remote(uint32_t bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 
 // Executed tensor-core work: every MMA-issuing loop counts its tcgen05.mma instructions in a register (one IADD next to each

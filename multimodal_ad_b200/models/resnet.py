@@ -182,7 +182,7 @@ class _Run:
         taps = k * k * k
         wf = self.empty((cout, taps, cin))
         wt = self.empty((cin, taps, cout)) if want_dgrad else None
-        self.chk(self.lib.mmad_conv3d_prep_weights(_p(conv.weight.detach()), _p(wf), _p(wt), cout, cin, taps, self.stream),
+        self.chk(self.lib.mmad_conv3d_prep_weights(_p(conv.weight.detach().contiguous()), _p(wf), _p(wt), cout, cin, taps, self.stream),
                  "mmad_conv3d_prep_weights")
         return wf, wt
 
@@ -291,7 +291,7 @@ def _backbone_forward(model: "ResNet", x: torch.Tensor, training: bool, need_gra
     xs = r.empty((xs_elems,))
     r.chk(lib.mmad_stem_s2d_pack(_p(x), _p(xs), n, d, h, w, r.stream), "mmad_stem_s2d_pack")
     wstem = r.empty((64, 512))
-    r.chk(lib.mmad_stem_s2d_prep_weights(_p(model.conv1.weight.detach()), _p(wstem), r.stream), "mmad_stem_s2d_prep_weights")
+    r.chk(lib.mmad_stem_s2d_prep_weights(_p(model.conv1.weight.detach().contiguous()), _p(wstem), r.stream), "mmad_stem_s2d_prep_weights")
     c0 = r.empty((n, do, ho, wo, 64))
     part = r.empty((lib.mmad_stem_s2d_stats_partials(n, d, h, w), 64, 2), torch.float32) if training else None
     r.chk(lib.mmad_stem_s2d_fwd(_p(xs), _p(wstem), _p(c0), _p(part), n, d, h, w, r.stream), "mmad_stem_s2d_fwd")
@@ -439,7 +439,7 @@ def _backbone_backward(model: "ResNet", tape, grad_out: torch.Tensor, need_input
         if st == 2 and dil == 1:
             # stride 2: eight interleaved phase convolutions of dc (no zero insertion, 1/8 of the MACs)
             wph = r.empty((27 * cin * cout,))
-            r.chk(lib.mmad_conv3d_prep_weights_s2(_p(conv.weight.detach()), _p(wph), cout, cin, r.stream), "mmad_conv3d_prep_weights_s2")
+            r.chk(lib.mmad_conv3d_prep_weights_s2(_p(conv.weight.detach().contiguous()), _p(wph), cout, cin, r.stream), "mmad_conv3d_prep_weights_s2")
             dx = r.empty(tuple(xin_shape[:4]) + (cin,))
             r.chk(lib.mmad_conv3d_dgrad_s2_bf16(_p(dc), _p(wph), _p(dx), xin_shape[0], xin_shape[1], xin_shape[2], xin_shape[3], cin, cout,
                                                 r.stream), "mmad_conv3d_dgrad_s2_bf16")

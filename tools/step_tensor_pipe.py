@@ -3,7 +3,7 @@ sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed (csv, one row pe
 
     ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
         --clock-control none -c 1200 --csv --log-file gpurun_out/step_pipe.csv python tools/resnet_bench.py ...
-    python tools/step_tensor_pipe.py gpurun_out/step_pipe.csv profiles/r02_resnet_step_tensor_pipe.json
+    python tools/step_tensor_pipe.py gpurun_out/step_pipe.csv profiles/r02_resnet_step_tensor_pipe.json [profiles/r02_resnet_launches.txt]
 
 The last training step of the capture (from its stem_s2d_pack launch on) is summarised: time-weighted mean of the per-kernel
 tensor-pipe activity over ALL launches of the step (ncu times are cold-cache and serialised, so this is a share-weighted figure,
@@ -45,6 +45,20 @@ def main():
                   "(batch 16 x 1x128^3, tools/resnet_bench.py)"}
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out))
+    if len(sys.argv) > 3:                                  # the per-kernel table of the same step (profiles/rNN_resnet_launches.txt)
+        agg = collections.OrderedDict()
+        for d in step:
+            name = re.sub(r"\(.*", "", re.sub(r"^void ", "", d["name"])).replace("mmad::", "")[:64]
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += d[tkey]
+            a[2] += d[tkey] * d.get(pkey, 0.0)
+        with open(sys.argv[3], "w") as f:
+            f.write("# one eager ResNet3D-18 training step (batch 16 x 1x128^3), ncu --clock-control none; per kernel: summed "
+                    "gpu__time_duration, share, launches, time-weighted sm__pipe_tensor_cycles_active (% of peak, elapsed)\n")
+            f.write(f"# {len(step)} launches, {tot / 1e6:.3f} ms (cold-cache, serialised: compare shares)\n")
+            for name, (cnt, t, tp) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f"{t / 1e6:8.3f} ms {100 * t / tot:5.1f}% x{cnt:3d}  tensor pipe {tp / t if t else 0.0:5.1f}%  {name}\n")
 
 
 main()
