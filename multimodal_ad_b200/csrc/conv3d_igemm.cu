@@ -333,16 +333,31 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t sa = stage0 + s * STAGE;
                     const int nv = min(KS, ksteps_t - k);
                     if (elect_one()) {
+                        // ONE descriptor pair per stage; every other operand is that pair plus a compile-time offset (a 64-bit
+                        // immediate add in the uniform datapath).  The issuing thread is the kernel's narrowest pipe: at ~3.6
+                        // cycles per instruction the 16 instructions per MMA of the first version (descriptor re-encoded per
+                        // tile, constants re-materialised) cost more than a 128 x 128 x 16 MMA takes (32 cycles).
+                        const uint32_t a0 = umma_desc_lo(sa, 16), b0 = umma_desc_lo(sa + A_REGION, 16);
+                        constexpr uint32_t AH = umma_desc_hi_sw128(WH ? 1280 : 1024), BH = umma_desc_hi_sw128(1024);
+                        constexpr uint32_t A_STEP = (WH ? 128 : kATileBytes) >> 4, B_STEP = B_TILE >> 4;
+                        if (kj == 4) {
 #pragma unroll
-                        for (int q = 0; q < KS; ++q) {
-                            if (q >= nv) break;
-                            const uint64_t adesc = WH ? umma_desc_sw128(sa + q * 128, 16, 1280) : umma_desc_sw128(sa + q * kATileBytes, 16, 1024);
-                            const uint64_t bdesc = umma_desc_sw128(sa + A_REGION + q * B_TILE, 16, 1024);
+                            for (int q = 0; q < KS; ++q) {
+                                if (q >= nv) break;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)           // 4 x K16 inside the 64-wide (128-byte) swizzled row
-                                if (j < kj) umma_bf16(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
-                            nmma += kj;
+                                for (int j = 0; j < 4; ++j)       // 4 x K16 inside the 64-wide (128-byte) swizzled row
+                                    umma_bf16_lohi(d_tmem, a0 + (q * A_STEP + 2 * j), AH, b0 + (q * B_STEP + 2 * j), BH, IDESC, (k | q | j) ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < KS; ++q) {
+                                if (q >= nv) break;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < kj) umma_bf16_lohi(d_tmem, a0 + (q * A_STEP + 2 * j), AH, b0 + (q * B_STEP + 2 * j), BH, IDESC, (k | q | j) ? 1u : 0u);
+                            }
                         }
+                        nmma += nv * kj;
                         umma_commit(empty0 + 8 * s);              // frees the smem slot when these MMAs retire
                     }
                     __syncwarp();
@@ -728,24 +743,45 @@ conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     tc_fence_after();
                     const uint32_t sa = stage0 + s * (WH ? stage_sz : (uint32_t)STAGE);
                     if (elect_one()) {
+                        // one descriptor pair per stage + compile-time offsets (see the single-CTA kernel's issuer)
                         if (WH) {
                             // stage k of a tile = (kd, kh) = (k / 3, k % 3) when the weights are resident (one channel slab)
                             const uint32_t sb = wres ? wres0 + (uint32_t)k * 3u * B_TAP : sa + A_REGION;
+                            const uint32_t a0 = umma_desc_lo(sa, 16), b0 = umma_desc_lo(sb, 16);
+                            constexpr uint32_t AH = umma_desc_hi_sw128(1280), BH = umma_desc_hi_sw128(1024);
+                            constexpr uint32_t B_STEP = B_TAP >> 4;
+                            // kw taps: operand = the halo box shifted by q rows (8 descriptor units), W lines 10 rows apart
+                            if (kj == 4) {
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) {         // kw taps: operand = the halo box shifted by q rows, W lines 10 rows apart
-                                const uint64_t adesc = umma_desc_sw128(sa + q * 128, 16, 1280);
-                                const uint64_t bdesc = umma_desc_sw128(sb + q * B_TAP, 16, 1024);
+                                for (int q = 0; q < 3; ++q)
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (j < kj) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | q | j) ? 1u : 0u);
+                                    for (int j = 0; j < 4; ++j)
+                                        umma_bf16_2sm_lohi(d_tmem, a0 + (q * 8 + 2 * j), AH, b0 + (q * B_STEP + 2 * j), BH, IDESC, (k | q | j) ? 1u : 0u);
+                            } else if (kj == 2) {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j)
+                                        umma_bf16_2sm_lohi(d_tmem, a0 + (q * 8 + 2 * j), AH, b0 + (q * B_STEP + 2 * j), BH, IDESC, (k | q | j) ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (j < kj) umma_bf16_2sm_lohi(d_tmem, a0 + (q * 8 + 2 * j), AH, b0 + (q * B_STEP + 2 * j), BH, IDESC, (k | q | j) ? 1u : 0u);
                             }
                             nmma += 3 * kj;
                         } else {
-                            const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-                            const uint64_t bdesc = umma_desc_sw128(sa + A_REGION, 16, 1024);
+                            const uint32_t a0 = umma_desc_lo(sa, 16), b0 = umma_desc_lo(sa + A_REGION, 16);
+                            constexpr uint32_t DH = umma_desc_hi_sw128(1024);
+                            if (kj == 4) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (j < kj) umma_bf16_2sm(d_tmem, adesc + 2 * j, bdesc + 2 * j, IDESC, (k | j) ? 1u : 0u);
+                                for (int j = 0; j < 4; ++j) umma_bf16_2sm_lohi(d_tmem, a0 + 2 * j, DH, b0 + 2 * j, DH, IDESC, (k | j) ? 1u : 0u);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j < kj) umma_bf16_2sm_lohi(d_tmem, a0 + 2 * j, DH, b0 + 2 * j, DH, IDESC, (k | j) ? 1u : 0u);
+                            }
                             nmma += kj;
                         }
                         umma_commit_2sm(empty0 + 8 * s, 3);       // frees the slot in both CTAs

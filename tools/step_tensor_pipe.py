@@ -28,10 +28,11 @@ def main():
         d[r[mi]] = float(r[vi].replace(",", ""))
     seq = list(launches.values())
     starts = [i for i, d in enumerate(seq) if "stem_s2d_pack" in d["name"]]
-    # the last step of the capture when it is complete (the first step also carries the optimizer's one-off state initialisation),
-    # else the one before it
+    # the last step of the capture when it is complete (the first step also carries the optimizer's one-off state initialisation:
+    # ~190 fill kernels), else the one before it
     step = seq[starts[-1]:]
-    if len(starts) >= 2 and len(step) < 0.55 * (starts[-1] - starts[-2]):
+    complete = any("multi_tensor_apply" in d["name"] for d in step[-12:])      # ends with the fused Adam update
+    if len(starts) >= 2 and not complete:
         step = seq[starts[-2]:starts[-1]]
     tkey = "gpu__time_duration.sum"
     pkey = [k for k in step[0] if k.startswith("sm__pipe_tensor_cycles_active")][0]
