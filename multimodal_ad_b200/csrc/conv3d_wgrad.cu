@@ -523,21 +523,30 @@ conv3d_wgrad_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         uint32_t s = 0, ph = 0, nmma = 0;
+        // descriptor low words = stage base + a per-block constant (tap row offset, LBO = row distance to the next tap) + a
+        // compile-time K16 offset; the high words are constants - one 32-bit add per operand in the issue loop (see
+        // umma_bf16_lohi, tc_common.cuh: the issuing thread is the narrowest pipe of an N = 64 kernel)
+        uint32_t aoff[7];
+#pragma unroll
+        for (int blk = 0; blk < 7; ++blk) {
+            const int t = tap0 + 2 * blk;
+            aoff[blk] = (uint32_t)halo_row(t) * 8u + ((((uint32_t)(halo_row(t + 1) - halo_row(t)) * 128u) >> 4) << 16);
+        }
+        constexpr uint32_t AH = umma_desc_hi_sw128(1280), BH = umma_desc_hi_sw128(1024);
+        constexpr uint32_t BOFF = (kHaloBoxBytes >> 4) + ((kHaloDyBytes >> 4) << 16);
         for (int c = c_begin; c < c_end; ++c) {
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
             const uint32_t sb = base + s * STAGE;
             if (elect_one()) {
+                const uint32_t s_lo = (sb & 0x3ffffu) >> 4;
 #pragma unroll
                 for (int blk = 0; blk < 7; ++blk) {
-                    const int t = tap0 + 2 * blk;
-                    const uint32_t r0 = (uint32_t)halo_row(t), lbo = (uint32_t)(halo_row(t + 1) - halo_row(t)) * 128u;
+                    const uint32_t a_blk = s_lo + aoff[blk];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {                 // K16 = W lines (h, h+1) of slice d: 2j -> h = 2 * (j & 1), d = j >> 1
-                        const uint32_t line = (uint32_t)((j >> 1) * 6 + (j & 1) * 2) * 10u;
-                        const uint64_t adesc = umma_desc_sw128(sb + (r0 + line) * 128u, lbo, 1280);
-                        const uint64_t bdesc = umma_desc_sw128(sb + kHaloBoxBytes + j * 2048, kHaloDyBytes, 1024);
-                        umma_bf16(tmem_base + blk * 64, adesc, bdesc, IDESC, (c > c_begin || j) ? 1u : 0u);
+                        const uint32_t line8 = (uint32_t)((j >> 1) * 6 + (j & 1) * 2) * 10u * 8u;
+                        umma_bf16_lohi(tmem_base + blk * 64, a_blk + line8, AH, s_lo + (BOFF + j * 128), BH, IDESC, (c > c_begin || j) ? 1u : 0u);
                     }
                 }
                 nmma += 56;
