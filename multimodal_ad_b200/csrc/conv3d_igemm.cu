@@ -522,13 +522,18 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // 64-channel super tile, every CTA stages its own 10 x 4 x 4 halo box per (kd, kh, channel slab) and only 32 of the 64 weight rows
 // of the three kw taps.  The single-CTA N = 64 kernel is bound by shared-memory bandwidth (44 KB of TMA writes + 72 KB of operand
 // reads per 384 MMA cycles); here a CTA moves 32 + 60 KB per stage.
-template <bool WH, bool EPI = false>
+//
+// BNP = 128 (WH = false): 128-channel N tiles on the pair.  The single-CTA 128 x 128 tile moves 32 KB per 256 MMA cycles and runs
+// AT the L2 -> SM limit (17.5 TB/s, tensor pipe 55 %: profiles/r02_conv_gen128_ncu_full.csv); the pair stages 16 KB of A and
+// only 8 KB of B per CTA for the same MMA time.
+template <bool WH, bool EPI = false, int BNP = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3d_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                          const __grid_constant__ CUtensorMap tmC, const ConvGeom g, float* __restrict__ stats_partials, const ConvEpi ep,
                          unsigned int* __restrict__ sched_counter) {
     pdl_launch_dependents();
-    constexpr int BN = WH ? 64 : 256;
+    constexpr int BN = BNP ? BNP : (WH ? 64 : 256);
+    static_assert(!WH || BN == 64, "the W-halo variant is for 64-channel tiles");
     constexpr int B_TAP = (BN / 2) * 128;                   // this CTA's half of one tap's weight rows
     constexpr int B_HALF = (WH ? 3 : 1) * B_TAP;
     constexpr int A_REGION = WH ? kHaloTileBytes : kATileBytes;
@@ -1026,7 +1031,10 @@ static bool use_halo_kernel(int Cin, int Cout, int k, int stride, int dil) {
 static bool use_pair_kernel(int bn, long long m_tiles) {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("MMAD_CONV_PAIR"); mode = e ? atoi(e) : 1; }
-    return mode != 0 && bn == 256 && m_tiles >= 2;
+    // 128-channel tiles on the pair kernel too: on unless MMAD_CONV_PAIR128=0
+    static int mode128 = -1;
+    if (mode128 < 0) { const char* e = getenv("MMAD_CONV_PAIR128"); mode128 = e ? atoi(e) : 1; }
+    return mode != 0 && (bn == 256 || (bn == 128 && mode128 != 0)) && m_tiles >= 2;
 }
 
 }  // namespace mmad
@@ -1117,7 +1125,8 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
     const int bn_stage = pairk ? bn / 2 : bn;              // weight rows a CTA stages per K-step
     static int ks_mode = -1;                               // MMAD_CONV_KS=1 forces one K-step per stage (tuning knob)
     if (ks_mode < 0) { const char* e = getenv("MMAD_CONV_KS"); ks_mode = e ? atoi(e) : 0; }
-    const int ks = halo ? 3 : (ks_mode == 1 ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));     // K-steps per stage (one weight box per stage)
+    // K-steps per stage (one weight box per stage); the pair kernel stages one K-step
+    const int ks = halo ? 3 : ((ks_mode == 1 || pairk) ? 1 : (bn == 64 ? 4 : (bn == 128 ? 2 : 1)));
     g.nout = ((bn == 256 && !pairk) || g.wres) ? 1 : 2;   // resident weights: one staging buffer buys the fifth input stage
     int stages = 8;
     while (stages > 2 && conv_smem_bytes(bn_stage, ks, stages, g.nout, Cout, halo, g.epi != 0, g.wres != 0) > 227 * 1024) --stages;
@@ -1206,11 +1215,15 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, float* stats_par
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMAD_CUDA(cudaFuncSetAttribute(conv3d_igemm_pair_kernel<false, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }
         const int pairs = (int)std::min<long long>((long long)((g.m_tiles + 1) / 2) * g.n_tiles, sms / 2);
         const dim3 pgrid(2 * pairs);
         if (halo_pair && g.epi) launch_pdl(conv3d_igemm_pair_kernel<true, true>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         else if (halo_pair) launch_pdl(conv3d_igemm_pair_kernel<true, false>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else if (bn == 128 && g.epi) launch_pdl(conv3d_igemm_pair_kernel<false, true, 128>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
+        else if (bn == 128) launch_pdl(conv3d_igemm_pair_kernel<false, false, 128>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         else if (g.epi) launch_pdl(conv3d_igemm_pair_kernel<false, true>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         else launch_pdl(conv3d_igemm_pair_kernel<false, false>, pgrid, dim3(kConvThreads), smem, st, tmA, tmB, tmC, g, stats_partials, ep, sched);
         MMAD_CUDA(cudaGetLastError());
